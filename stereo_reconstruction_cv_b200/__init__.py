@@ -1,0 +1,9 @@
+"""B200-native dense-stereo engine: drop-in for the cv2 calls on the reference's dense
+reconstruction path (main.ipynb:655-668, 697).  See stereo.py and include/sgbm_b200.h."""
+from .stereo import (DISP_SCALE, DISP_SHIFT, MODE_HH, MODE_HH4, MODE_SGBM, MODE_SGBM_3WAY, StereoSGBM,
+                     StereoSGBM_create, device_info, disparityToFloat, error, filterSpeckles, medianBlur3,
+                     microbench_int16, reprojectCompact, reprojectImageTo3D)
+
+__all__ = ["StereoSGBM", "StereoSGBM_create", "reprojectImageTo3D", "reprojectCompact", "disparityToFloat",
+           "filterSpeckles", "medianBlur3", "microbench_int16", "device_info", "error", "MODE_SGBM", "MODE_HH",
+           "MODE_SGBM_3WAY", "MODE_HH4", "DISP_SHIFT", "DISP_SCALE"]

@@ -1,0 +1,73 @@
+"""ctypes binding of libsgbm_b200.so (C ABI: include/sgbm_b200.h).  There is no CPU fallback:
+if the library is missing or no CUDA device is present, the calls raise."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsgbm_b200.so")
+_LIB = None
+
+# every symbol include/sgbm_b200.h declares
+SYMBOLS = [
+    "sgbm_last_error", "sgbm_version", "sgbm_device_info", "sgbm_create", "sgbm_destroy",
+    "sgbm_set_params", "sgbm_get_params", "sgbm_workspace_bytes", "sgbm_compute", "sgbm_compute_host",
+    "sgbm_disp_to_float", "sgbm_reproject_f32", "sgbm_reproject_i16", "sgbm_reproject_compact",
+    "sgbm_reproject_compact_scratch_bytes", "sgbm_filter_speckles", "sgbm_median3x3",
+    "sgbm_debug_keep", "sgbm_debug_fetch", "sgbm_microbench_int16",
+]
+
+
+class SgbmParams(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("minDisparity", "numDisparities", "blockSize", "P1", "P2",
+                                       "disp12MaxDiff", "preFilterCap", "uniquenessRatio",
+                                       "speckleWindowSize", "speckleRange", "mode")]
+
+
+class error(Exception):
+    """Raised where cv2 would raise cv2.error (bad size / type / parameter) and on CUDA errors."""
+
+    def __init__(self, code, msg):
+        super().__init__("sgbm_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a). This engine has no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i, sz, pd = C.c_void_p, C.c_int, C.c_size_t, C.c_ssize_t
+    L.sgbm_last_error.restype = C.c_char_p
+    L.sgbm_version.restype = C.c_char_p
+    L.sgbm_device_info.argtypes = [C.POINTER(i), C.POINTER(i), C.POINTER(i), C.c_char_p, i]
+    L.sgbm_create.argtypes = [C.POINTER(SgbmParams), C.POINTER(vp)]
+    L.sgbm_destroy.argtypes = [vp]
+    L.sgbm_set_params.argtypes = [vp, C.POINTER(SgbmParams)]
+    L.sgbm_get_params.argtypes = [vp, C.POINTER(SgbmParams)]
+    L.sgbm_workspace_bytes.argtypes = [vp, i, i, i, C.POINTER(sz)]
+    L.sgbm_compute.argtypes = [vp, vp, vp, i, i, i, pd, i, vp, pd, vp]
+    L.sgbm_compute_host.argtypes = [vp, vp, vp, i, i, i, pd, i, vp, pd]
+    L.sgbm_disp_to_float.argtypes = [vp, i, i, vp, vp]
+    L.sgbm_reproject_f32.argtypes = [vp, vp, i, i, vp, vp, vp]
+    L.sgbm_reproject_i16.argtypes = [vp, vp, i, i, vp, vp, vp]
+    L.sgbm_reproject_compact.argtypes = [vp, vp, i, i, vp, i, pd, vp, vp, vp, vp, sz, vp]
+    L.sgbm_reproject_compact_scratch_bytes.argtypes = [i, i, C.POINTER(sz)]
+    L.sgbm_filter_speckles.argtypes = [vp, i, i, i, i, i, vp, sz, vp]
+    L.sgbm_median3x3.argtypes = [vp, vp, i, i, vp]
+    L.sgbm_debug_keep.argtypes = [vp, i]
+    L.sgbm_debug_fetch.argtypes = [vp, i, vp, sz]
+    L.sgbm_microbench_int16.argtypes = [i, C.POINTER(C.c_double)]
+    for name in SYMBOLS:
+        fn = getattr(L, name)
+        if fn.restype is C.c_int or fn.restype is None:
+            fn.restype = C.c_int
+    _LIB = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise error(rc, lib().sgbm_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,564 @@
+// sgbm_api.cu -- the C ABI of libsgbm_b200.so (see include/sgbm_b200.h): parameter handling
+// (effective values), validation, workspace management and the per-frame kernel
+// schedule that replaces cv2.StereoSGBM.compute / reprojectImageTo3D at main.ipynb:655-668, 697.
+#include "../../include/sgbm_b200.h"
+#include "sgbm_common.cuh"
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <atomic>
+#include <new>
+#include <vector>
+
+// ---- launchers implemented in the other translation units -------------------------------------
+int sgbm_launch_prefilter(const Geo &g, const uint8_t *left, const uint8_t *right, long long pitch, uint8_t *planes, cudaStream_t st);
+int sgbm_launch_cost(const Geo &g, const uint8_t *planes, uint16_t *out, int y0, int nrows, int ylo, int zeroTail, cudaStream_t st);
+int sgbm_launch_horizontal(const Geo &g, const uint16_t *C, uint16_t *LhA, uint16_t *LhB, int y0, int nrows, cudaStream_t st);
+int sgbm_launch_vertical(VertArgs &a, int ndir, int numSMs, cudaStream_t st);
+int sgbm_launch_fill_i16(int16_t *p, size_t n, int v, cudaStream_t st);
+int sgbm_launch_lrcheck(const Geo &g, int16_t *raw, const unsigned int *d2key, cudaStream_t st);
+int sgbm_launch_median(const int16_t *src, int16_t *dst, int W, int H, long long dstPitchElems, cudaStream_t st);
+int sgbm_launch_speckles(int16_t *img, int W, int H, int newVal, int maxSize, int maxDiff, void *scratch, cudaStream_t st);
+int sgbm_launch_disp_to_float(const int16_t *d, float *out, size_t n, cudaStream_t st);
+int sgbm_launch_reproject(const void *disp, int isFloat, const double *Qh, int W, int H, float *xyz, uint8_t *valid, cudaStream_t st);
+size_t sgbm_compact_scratch_bytes(int W, int H);
+int sgbm_launch_compact(const int16_t *disp, const double *Qh, int W, int H, const uint8_t *bgr, int bgrCn, long long bgrPitch,
+                        float *xyz, uint8_t *rgb, unsigned long long *nOut, void *scratch, cudaStream_t st);
+int sgbm_run_microbench(int which, double *out);
+
+// ---- error reporting ----------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+int sgbm_fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int sgbm_fail_cuda(cudaError_t e, const char *what, const char *file, int line)
+{
+    snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return SGBM_E_CUDA;
+}
+
+// ---- handle -------------------------------------------------------------------------------------
+static std::atomic<unsigned long long> g_launches{0};
+void sgbm_count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+enum { ST_START = 0, ST_PREFILTER, ST_COST, ST_COST_ALT, ST_HORIZONTAL, ST_INIT, ST_VERT_FWD, ST_VERT_WTA, ST_LRCHECK,
+       ST_MEDIAN, ST_SPECKLE, ST_COUNT };
+static const char *const kStageNames[ST_COUNT] = {"start", "prefilter", "cost", "cost_alt", "horizontal", "init",
+                                                  "vertical_fwd", "vertical_wta", "lrcheck", "median", "speckle"};
+struct ProfMark { int stage; cudaEvent_t ev; unsigned long long launches; };
+
+struct sgbm_handle {
+    sgbm_params p{};
+    int numSMs = 0;
+    // device workspace (grown on demand)
+    void *ws = nullptr;
+    size_t wsBytes = 0;
+    // pinned + device staging for the _host entry point
+    void *hostIn = nullptr, *hostOut = nullptr, *devIn = nullptr, *devOut = nullptr;
+    size_t hostInBytes = 0, hostOutBytes = 0, devInBytes = 0, devOutBytes = 0;
+    cudaStream_t ownStream = nullptr;
+    // debug
+    int keep = 0;
+    Geo lastGeo{};
+    uint16_t *lastC = nullptr, *lastS = nullptr;
+    int16_t *lastRaw = nullptr;
+    int lastValid = 0;
+    // profiling
+    int prof = 0;
+    cudaStream_t profStream = nullptr;
+    std::vector<cudaEvent_t> evPool;
+    size_t evUsed = 0;
+    std::vector<ProfMark> marks;
+};
+
+static int prof_mark(sgbm_handle *h, int stage, cudaStream_t st)
+{
+    if (!h->prof) return 0;
+    if (h->evUsed == h->evPool.size()) {
+        cudaEvent_t e;
+        SGBM_CUDA_CHECK(cudaEventCreate(&e));
+        h->evPool.push_back(e);
+    }
+    cudaEvent_t e = h->evPool[h->evUsed++];
+    SGBM_CUDA_CHECK(cudaEventRecord(e, st));
+    h->marks.push_back({stage, e, g_launches.load()});
+    h->profStream = st;
+    return 0;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Effective parameters and geometry (A.0) + lane mapping.  Returns 0 or an error code.
+static int make_geo(const sgbm_params &p, int W, int H, int cn, Geo &g)
+{
+    memset(&g, 0, sizeof(g));
+    if (W <= 0 || H <= 0) return sgbm_fail(SGBM_E_INVALID_ARG, "empty image %dx%d", W, H);
+    if (cn != 1 && cn != 3) return sgbm_fail(SGBM_E_INVALID_ARG, "channels must be 1 or 3 (got %d)", cn);
+    if (p.mode < 0 || p.mode > 3) return sgbm_fail(SGBM_E_INVALID_ARG, "unknown mode %d", p.mode);
+    g.W = W; g.H = H; g.cn = cn; g.mode = p.mode;
+    g.minD = p.minDisparity; g.D = p.numDisparities; g.maxD = g.minD + g.D;
+    if (g.D <= 0) return sgbm_fail(SGBM_E_BAD_SIZE, "numDisparities must be > 0 (got %d)", g.D);
+    if (p.mode == SGBM_MODE_SGBM_3WAY) g.r = (p.blockSize > 0 ? p.blockSize : 3) / 2;
+    else g.r = (p.blockSize > 0 ? p.blockSize : 5) / 2;
+    g.P1 = p.P1 > 0 ? p.P1 : 2;
+    g.P2 = p.P2 > 0 ? p.P2 : 5;
+    if (g.P2 < g.P1 + 1) g.P2 = g.P1 + 1;
+    g.UR = p.uniquenessRatio >= 0 ? p.uniquenessRatio : 10;
+    g.DMD = p.disp12MaxDiff > 0 ? p.disp12MaxDiff : 1;
+    g.ftzero = (p.preFilterCap > 15 ? p.preFilterCap : 15) | 1;
+    g.INV = (g.minD - 1) * 16;
+    g.minX1 = g.maxD > 0 ? g.maxD : 0;
+    g.maxX1 = W + (g.minD < 0 ? g.minD : 0);
+    g.W1 = g.maxX1 - g.minX1;
+    // cv2.error site stereosgbm.cpp:511 [P15] and the empty-valid-range case cv2 crashes on [P18]
+    if (!(W - (g.minD + g.D) > p.blockSize / 2) || g.W1 <= 0)
+        return sgbm_fail(SGBM_E_BAD_SIZE, "image width %d too small for minDisparity=%d numDisparities=%d blockSize=%d",
+                         W, g.minD, g.D, p.blockSize);
+    if (g.D % 8 != 0 || g.D > 1024)
+        return sgbm_fail(SGBM_E_UNSUPPORTED, "numDisparities must be a multiple of 8 and <= 1024 (got %d)", g.D);
+    if (g.P2 > 32767) return sgbm_fail(SGBM_E_UNSUPPORTED, "P2 must be <= 32767 (got %d)", g.P2);
+    if (g.UR > 100 || (p.mode == SGBM_MODE_SGBM_3WAY && g.UR >= 100))
+        return sgbm_fail(SGBM_E_UNSUPPORTED, "uniquenessRatio %d is not supported", g.UR);
+    if (g.INV < -32768 || g.maxD * 16 > 32767 || g.minD * 16 < -32768)
+        return sgbm_fail(SGBM_E_UNSUPPORTED, "disparity range does not fit the int16 x16 output");
+    if (g.W1 > 65535) return sgbm_fail(SGBM_E_UNSUPPORTED, "valid width %d > 65535", g.W1);
+    // lane mapping: D = 2*nreg*lanesUsed, lpc = pow2 >= lanesUsed (>= 2); maximise lanesUsed/lpc
+    static const int prefBig[4] = {16, 12, 8, 4}, prefSmall[4] = {8, 12, 16, 4};
+    const int *pref = g.D >= 192 ? prefBig : prefSmall;
+    const char *env = getenv("SGBM_NREG");
+    int forced = env ? atoi(env) : 0;
+    double bestEff = -1;
+    for (int i = 0; i < 4; i++) {
+        int nreg = pref[i];
+        if (forced && nreg != forced) continue;
+        if (g.D % (2 * nreg)) continue;
+        int lanes = g.D / (2 * nreg);
+        if (lanes > 32) continue;
+        int lpc = 2;
+        while (lpc < lanes) lpc <<= 1;
+        double eff = (double)lanes / lpc;
+        if (eff > bestEff + 1e-9) { bestEff = eff; g.nreg = nreg; g.lpc = lpc; g.lanesUsed = lanes; }
+    }
+    if (bestEff < 0) return sgbm_fail(SGBM_E_UNSUPPORTED, "no lane mapping for numDisparities=%d", g.D);
+    g.Dp = 2 * g.nreg * g.lpc;
+    g.lpcShift = 0;
+    while ((1 << g.lpcShift) < g.lpc) g.lpcShift++;
+    g.rowStride = (long long)g.W1 * g.Dp;
+    return 0;
+}
+
+struct WsLayout {
+    size_t planes, C, LhA, LhB, Calt, raw, d2key, med, speck, haloA, haloC, flags, sdbg, total;
+};
+
+static void ws_layout(const Geo &g, const sgbm_params &p, int numSMs, int keep, WsLayout &L)
+{
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    size_t vol = (size_t)g.rowStride * g.H * 2;
+    L.planes = take((size_t)2 * g.cn * 6 * g.W * g.H);
+    L.C = take(vol);
+    L.LhA = take(vol);
+    L.LhB = take(vol);
+    L.Calt = take(p.mode == SGBM_MODE_SGBM_3WAY ? (size_t)3 * (g.r > 0 ? g.r : 1) * g.rowStride * 2 : 16);
+    L.raw = take((size_t)g.W * g.H * 2);
+    L.d2key = take((size_t)g.W * g.H * 4);
+    L.med = take((size_t)g.W * g.H * 2);
+    L.speck = take((size_t)g.W * g.H * 8);
+    int maxStrips = g.W1 < numSMs ? g.W1 : numSMs;
+    L.haloA = take((size_t)maxStrips * 2 * (g.Dp + 8) * 2);
+    L.haloC = take((size_t)maxStrips * 2 * (g.Dp + 8) * 2);
+    L.flags = take((size_t)2 * maxStrips * 4);
+    L.sdbg = take(keep ? vol : 16);
+    L.total = off;
+}
+
+extern "C" const char *sgbm_last_error(void) { return g_err; }
+extern "C" const char *sgbm_version(void) { return "sgbm_b200 0.1 (sm_100a)"; }
+
+extern "C" int sgbm_device_info(int *sm_count, int *cc_major, int *cc_minor, char *name, int name_len)
+{
+    int dev = 0;
+    SGBM_CUDA_CHECK(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    SGBM_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (name && name_len > 0) { strncpy(name, prop.name, name_len - 1); name[name_len - 1] = 0; }
+    return 0;
+}
+
+extern "C" int sgbm_create(const sgbm_params *p, sgbm_handle **out)
+{
+    if (!p || !out) return sgbm_fail(SGBM_E_INVALID_ARG, "null argument");
+    if (p->mode < 0 || p->mode > 3) return sgbm_fail(SGBM_E_INVALID_ARG, "unknown mode %d", p->mode);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return sgbm_fail(SGBM_E_CUDA, "no CUDA device available (%s): this engine has no CPU fallback", cudaGetErrorString(e));
+    sgbm_handle *h = new (std::nothrow) sgbm_handle();
+    if (!h) return sgbm_fail(SGBM_E_NOMEM, "out of host memory");
+    h->p = *p;
+    int dev = 0;
+    SGBM_CUDA_CHECK(cudaGetDevice(&dev));
+    SGBM_CUDA_CHECK(cudaDeviceGetAttribute(&h->numSMs, cudaDevAttrMultiProcessorCount, dev));
+    *out = h;
+    return 0;
+}
+
+extern "C" int sgbm_destroy(sgbm_handle *h)
+{
+    if (!h) return 0;
+    if (h->ws) cudaFree(h->ws);
+    if (h->devIn) cudaFree(h->devIn);
+    if (h->devOut) cudaFree(h->devOut);
+    if (h->hostIn) cudaFreeHost(h->hostIn);
+    if (h->hostOut) cudaFreeHost(h->hostOut);
+    if (h->ownStream) cudaStreamDestroy(h->ownStream);
+    for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
+    delete h;
+    return 0;
+}
+
+extern "C" int sgbm_set_params(sgbm_handle *h, const sgbm_params *p)
+{
+    if (!h || !p) return sgbm_fail(SGBM_E_INVALID_ARG, "null argument");
+    if (p->mode < 0 || p->mode > 3) return sgbm_fail(SGBM_E_INVALID_ARG, "unknown mode %d", p->mode);
+    h->p = *p;
+    h->lastValid = 0;
+    return 0;
+}
+extern "C" int sgbm_get_params(const sgbm_handle *h, sgbm_params *p)
+{
+    if (!h || !p) return sgbm_fail(SGBM_E_INVALID_ARG, "null argument");
+    *p = h->p;
+    return 0;
+}
+
+extern "C" int sgbm_workspace_bytes(const sgbm_handle *h, int W, int H, int channels, size_t *out)
+{
+    if (!h || !out) return sgbm_fail(SGBM_E_INVALID_ARG, "null argument");
+    Geo g;
+    int rc = make_geo(h->p, W, H, channels, g);
+    if (rc) return rc;
+    WsLayout L;
+    ws_layout(g, h->p, h->numSMs, h->keep, L);
+    *out = L.total;
+    return 0;
+}
+
+static int ensure_ws(sgbm_handle *h, size_t bytes, cudaStream_t st)
+{
+    if (h->wsBytes >= bytes) return 0;
+    if (h->ws) {
+        SGBM_CUDA_CHECK(cudaStreamSynchronize(st));
+        SGBM_CUDA_CHECK(cudaFree(h->ws));
+        h->ws = nullptr; h->wsBytes = 0;
+    }
+    cudaError_t e = cudaMalloc(&h->ws, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return sgbm_fail(SGBM_E_NOMEM, "cudaMalloc of %zu workspace bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    h->wsBytes = bytes;
+    return 0;
+}
+
+// One frame: the kernel schedule for each mode.
+static int compute_frame(sgbm_handle *h, const Geo &g, const WsLayout &L, const uint8_t *left, const uint8_t *right,
+                         long long pitch, int16_t *out, long long outPitchElems, cudaStream_t st)
+{
+    const sgbm_params &p = h->p;
+    uint8_t *base = (uint8_t *)h->ws;
+    uint8_t *planes = base + L.planes;
+    uint16_t *C = (uint16_t *)(base + L.C), *LhA = (uint16_t *)(base + L.LhA), *LhB = (uint16_t *)(base + L.LhB);
+    uint16_t *Calt = (uint16_t *)(base + L.Calt);
+    int16_t *raw = (int16_t *)(base + L.raw), *med = (int16_t *)(base + L.med);
+    unsigned int *d2key = (unsigned int *)(base + L.d2key);
+    int rc;
+    if ((rc = prof_mark(h, ST_START, st))) return rc;
+    if ((rc = sgbm_launch_prefilter(g, left, right, pitch, planes, st))) return rc;
+    if ((rc = prof_mark(h, ST_PREFILTER, st))) return rc;
+    if ((rc = sgbm_launch_cost(g, planes, C, 0, g.H, 0, p.mode == SGBM_MODE_HH4, st))) return rc;
+    if ((rc = prof_mark(h, ST_COST, st))) return rc;
+    const int ss = (g.H + 3) / 4;
+    int ov = 0;
+    if (p.mode == SGBM_MODE_SGBM_3WAY) {
+        ov = (p.blockSize / 2 + 1) + (int)ceil(0.1 * (double)ss);    // same double expression as the reference (A.6)
+        for (int n = 1; n < 4 && g.r > 0; n++) {
+            int o0 = n * ss;
+            if (o0 >= g.H) break;
+            int s0 = o0 - ov > 0 ? o0 - ov : 0;
+            if (s0 == 0) continue;
+            int nr = g.r < g.H - s0 ? g.r : g.H - s0;
+            if ((rc = sgbm_launch_cost(g, planes, Calt + (size_t)(n - 1) * g.r * g.rowStride, s0, nr, s0, 0, st))) return rc;
+        }
+    }
+    if (p.mode == SGBM_MODE_SGBM_3WAY && (rc = prof_mark(h, ST_COST_ALT, st))) return rc;
+    if ((rc = sgbm_launch_horizontal(g, C, LhA, LhB, 0, g.H, st))) return rc;
+    if ((rc = prof_mark(h, ST_HORIZONTAL, st))) return rc;
+    if ((rc = sgbm_launch_fill_i16(raw, (size_t)g.W * g.H, g.INV, st))) return rc;
+    SGBM_CUDA_CHECK(cudaMemsetAsync(d2key, 0xFF, (size_t)g.W * g.H * 4, st));
+    if ((rc = prof_mark(h, ST_INIT, st))) return rc;
+
+    VertArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = g; a.C = C; a.Calt = Calt; a.raw = raw; a.d2key = d2key;
+    a.haloA = (uint16_t *)(base + L.haloA); a.haloC = (uint16_t *)(base + L.haloC);
+    a.flagA = (unsigned int *)(base + L.flags); a.flagC = a.flagA + (g.W1 < h->numSMs ? g.W1 : h->numSMs);
+    a.ss = ss; a.ov = ov;
+    a.sdbg = h->keep ? (uint16_t *)(base + L.sdbg) : nullptr;
+    switch (p.mode) {
+    case SGBM_MODE_SGBM:
+        a.inA = LhA; a.inB = LhB; a.sout = nullptr; a.backward = 0;
+        if ((rc = sgbm_launch_vertical(a, 3, h->numSMs, st))) return rc;
+        break;
+    case SGBM_MODE_HH:
+        a.inA = LhA; a.inB = LhB; a.sout = LhA; a.backward = 0;      // S_fwd overwrites LhA in place
+        if ((rc = sgbm_launch_vertical(a, 3, h->numSMs, st))) return rc;
+        if ((rc = prof_mark(h, ST_VERT_FWD, st))) return rc;
+        a.inA = LhA; a.inB = nullptr; a.sout = nullptr; a.backward = 1;
+        if ((rc = sgbm_launch_vertical(a, 3, h->numSMs, st))) return rc;
+        break;
+    case SGBM_MODE_SGBM_3WAY:
+        a.inA = LhA; a.inB = LhB; a.sout = nullptr; a.threeway = 1;
+        if ((rc = sgbm_launch_vertical(a, 1, h->numSMs, st))) return rc;
+        break;
+    case SGBM_MODE_HH4:
+        a.inA = LhA; a.inB = LhB; a.sout = LhA; a.backward = 0;
+        if ((rc = sgbm_launch_vertical(a, 1, h->numSMs, st))) return rc;
+        if ((rc = prof_mark(h, ST_VERT_FWD, st))) return rc;
+        a.inA = LhA; a.inB = nullptr; a.sout = nullptr; a.backward = 1;
+        if ((rc = sgbm_launch_vertical(a, 1, h->numSMs, st))) return rc;
+        break;
+    }
+    if ((rc = prof_mark(h, ST_VERT_WTA, st))) return rc;
+    if ((rc = sgbm_launch_lrcheck(g, raw, d2key, st))) return rc;
+    if ((rc = prof_mark(h, ST_LRCHECK, st))) return rc;
+    const bool dense = outPitchElems == g.W;
+    const bool speck = p.speckleWindowSize > 0;
+    int16_t *mdst = (speck && !dense) ? med : out;
+    long long mpitch = (speck && !dense) ? g.W : outPitchElems;
+    if ((rc = sgbm_launch_median(raw, mdst, g.W, g.H, mpitch, st))) return rc;
+    if ((rc = prof_mark(h, ST_MEDIAN, st))) return rc;
+    if (speck) {
+        if ((rc = sgbm_launch_speckles(mdst, g.W, g.H, g.INV, p.speckleWindowSize, 16 * p.speckleRange, base + L.speck, st))) return rc;
+        if (!dense)
+            SGBM_CUDA_CHECK(cudaMemcpy2DAsync(out, (size_t)outPitchElems * 2, med, (size_t)g.W * 2, (size_t)g.W * 2, g.H,
+                                              cudaMemcpyDeviceToDevice, st));
+    }
+    if (speck && (rc = prof_mark(h, ST_SPECKLE, st))) return rc;
+    h->lastGeo = g; h->lastC = C; h->lastS = a.sdbg; h->lastRaw = raw; h->lastValid = 1;
+    return 0;
+}
+
+extern "C" int sgbm_compute(sgbm_handle *h, const uint8_t *left, const uint8_t *right, int W, int H, int channels,
+                            ptrdiff_t pitch_bytes, int batch, int16_t *disp_out, ptrdiff_t out_pitch_bytes,
+                            void *cuda_stream)
+{
+    if (!h || !left || !right || !disp_out) return sgbm_fail(SGBM_E_INVALID_ARG, "null argument");
+    if (batch <= 0) return sgbm_fail(SGBM_E_INVALID_ARG, "batch must be >= 1");
+    if (pitch_bytes < (ptrdiff_t)W * channels || out_pitch_bytes < (ptrdiff_t)W * 2 || (out_pitch_bytes & 1))
+        return sgbm_fail(SGBM_E_INVALID_ARG, "bad pitch (in %td, out %td) for width %d", pitch_bytes, out_pitch_bytes, W);
+    Geo g;
+    int rc = make_geo(h->p, W, H, channels, g);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    WsLayout L;
+    ws_layout(g, h->p, h->numSMs, h->keep, L);
+    if ((rc = ensure_ws(h, L.total, st))) return rc;
+    for (int b = 0; b < batch; b++) {
+        rc = compute_frame(h, g, L, left + (size_t)b * pitch_bytes * H, right + (size_t)b * pitch_bytes * H, pitch_bytes,
+                           (int16_t *)((uint8_t *)disp_out + (size_t)b * out_pitch_bytes * H), out_pitch_bytes / 2, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+static int ensure_buf(void **p, size_t *have, size_t need, bool pinned)
+{
+    if (*have >= need) return 0;
+    if (*p) { if (pinned) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; *have = 0; }
+    cudaError_t e = pinned ? cudaMallocHost(p, need) : cudaMalloc(p, need);
+    if (e != cudaSuccess) { cudaGetLastError(); return sgbm_fail(SGBM_E_NOMEM, "staging allocation of %zu bytes failed: %s", need, cudaGetErrorString(e)); }
+    *have = need;
+    return 0;
+}
+
+extern "C" int sgbm_compute_host(sgbm_handle *h, const uint8_t *left, const uint8_t *right, int W, int H, int channels,
+                                 ptrdiff_t pitch_bytes, int batch, int16_t *disp_out, ptrdiff_t out_pitch_bytes)
+{
+    if (!h || !left || !right || !disp_out) return sgbm_fail(SGBM_E_INVALID_ARG, "null argument");
+    if (batch <= 0) return sgbm_fail(SGBM_E_INVALID_ARG, "batch must be >= 1");
+    if (pitch_bytes < (ptrdiff_t)W * channels || out_pitch_bytes < (ptrdiff_t)W * 2)
+        return sgbm_fail(SGBM_E_INVALID_ARG, "bad pitch");
+    Geo g;
+    int rc = make_geo(h->p, W, H, channels, g);
+    if (rc) return rc;
+    if (!h->ownStream) SGBM_CUDA_CHECK(cudaStreamCreateWithFlags(&h->ownStream, cudaStreamNonBlocking));
+    cudaStream_t st = h->ownStream;
+    const size_t rowIn = (size_t)W * channels, frameIn = rowIn * H, frameOut = (size_t)W * H * 2;
+    // frames are staged one pair at a time through pinned memory (dense rows)
+    if ((rc = ensure_buf(&h->hostIn, &h->hostInBytes, 2 * frameIn, true))) return rc;
+    if ((rc = ensure_buf(&h->hostOut, &h->hostOutBytes, frameOut, true))) return rc;
+    if ((rc = ensure_buf(&h->devIn, &h->devInBytes, 2 * frameIn, false))) return rc;
+    if ((rc = ensure_buf(&h->devOut, &h->devOutBytes, frameOut, false))) return rc;
+    WsLayout L;
+    ws_layout(g, h->p, h->numSMs, h->keep, L);
+    if ((rc = ensure_ws(h, L.total, st))) return rc;
+    for (int b = 0; b < batch; b++) {
+        const uint8_t *l = left + (size_t)b * pitch_bytes * H, *r = right + (size_t)b * pitch_bytes * H;
+        uint8_t *hi = (uint8_t *)h->hostIn;
+        for (int y = 0; y < H; y++) {
+            memcpy(hi + (size_t)y * rowIn, l + (size_t)y * pitch_bytes, rowIn);
+            memcpy(hi + frameIn + (size_t)y * rowIn, r + (size_t)y * pitch_bytes, rowIn);
+        }
+        SGBM_CUDA_CHECK(cudaMemcpyAsync(h->devIn, h->hostIn, 2 * frameIn, cudaMemcpyHostToDevice, st));
+        rc = compute_frame(h, g, L, (const uint8_t *)h->devIn, (const uint8_t *)h->devIn + frameIn, (long long)rowIn,
+                           (int16_t *)h->devOut, W, st);
+        if (rc) return rc;
+        SGBM_CUDA_CHECK(cudaMemcpyAsync(h->hostOut, h->devOut, frameOut, cudaMemcpyDeviceToHost, st));
+        SGBM_CUDA_CHECK(cudaStreamSynchronize(st));
+        uint8_t *o = (uint8_t *)disp_out + (size_t)b * out_pitch_bytes * H;
+        for (int y = 0; y < H; y++) memcpy(o + (size_t)y * out_pitch_bytes, (uint8_t *)h->hostOut + (size_t)y * W * 2, (size_t)W * 2);
+    }
+    return 0;
+}
+
+extern "C" int sgbm_disp_to_float(const int16_t *disp_x16, int W, int H, float *out, void *cuda_stream)
+{
+    if (!disp_x16 || !out || W <= 0 || H <= 0) return sgbm_fail(SGBM_E_INVALID_ARG, "bad argument");
+    return sgbm_launch_disp_to_float(disp_x16, out, (size_t)W * H, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int sgbm_reproject_f32(const float *disp, const double *Q, int W, int H, float *xyz, uint8_t *valid_or_null,
+                                  void *cuda_stream)
+{
+    if (!disp || !Q || !xyz || W <= 0 || H <= 0) return sgbm_fail(SGBM_E_INVALID_ARG, "bad argument");
+    return sgbm_launch_reproject(disp, 1, Q, W, H, xyz, valid_or_null, (cudaStream_t)cuda_stream);
+}
+extern "C" int sgbm_reproject_i16(const int16_t *disp, const double *Q, int W, int H, float *xyz, uint8_t *valid_or_null,
+                                  void *cuda_stream)
+{
+    if (!disp || !Q || !xyz || W <= 0 || H <= 0) return sgbm_fail(SGBM_E_INVALID_ARG, "bad argument");
+    return sgbm_launch_reproject(disp, 0, Q, W, H, xyz, valid_or_null, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int sgbm_reproject_compact_scratch_bytes(int W, int H, size_t *out)
+{
+    if (!out || W <= 0 || H <= 0) return sgbm_fail(SGBM_E_INVALID_ARG, "bad argument");
+    *out = sgbm_compact_scratch_bytes(W, H);
+    return 0;
+}
+extern "C" int sgbm_reproject_compact(const int16_t *disp_x16, const double *Q, int W, int H, const uint8_t *bgr,
+                                      int bgr_channels, ptrdiff_t bgr_pitch_bytes, float *xyz_out, uint8_t *rgb_out,
+                                      unsigned long long *n_out, void *scratch, size_t scratch_bytes, void *cuda_stream)
+{
+    if (!disp_x16 || !Q || !xyz_out || !n_out || !scratch || W <= 0 || H <= 0) return sgbm_fail(SGBM_E_INVALID_ARG, "bad argument");
+    if (scratch_bytes < sgbm_compact_scratch_bytes(W, H)) return sgbm_fail(SGBM_E_INVALID_ARG, "scratch too small");
+    if (rgb_out && (!bgr || (bgr_channels != 1 && bgr_channels != 3))) return sgbm_fail(SGBM_E_INVALID_ARG, "bad colour image");
+    return sgbm_launch_compact(disp_x16, Q, W, H, bgr, bgr_channels, (long long)bgr_pitch_bytes, xyz_out,
+                               rgb_out ? rgb_out : nullptr, n_out, scratch, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int sgbm_filter_speckles(int16_t *img, int W, int H, int newVal, int maxSpeckleSize, int maxDiff, void *scratch,
+                                    size_t scratch_bytes, void *cuda_stream)
+{
+    if (!img || !scratch || W <= 0 || H <= 0) return sgbm_fail(SGBM_E_INVALID_ARG, "bad argument");
+    if (scratch_bytes < (size_t)W * H * 8) return sgbm_fail(SGBM_E_INVALID_ARG, "scratch too small (need W*H*8)");
+    return sgbm_launch_speckles(img, W, H, newVal, maxSpeckleSize, maxDiff, scratch, (cudaStream_t)cuda_stream);
+}
+extern "C" int sgbm_median3x3(const int16_t *src, int16_t *dst, int W, int H, void *cuda_stream)
+{
+    if (!src || !dst || src == dst || W <= 0 || H <= 0) return sgbm_fail(SGBM_E_INVALID_ARG, "bad argument");
+    return sgbm_launch_median(src, dst, W, H, W, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int sgbm_debug_keep(sgbm_handle *h, int on)
+{
+    if (!h) return sgbm_fail(SGBM_E_INVALID_ARG, "null handle");
+    h->keep = on ? 1 : 0;
+    h->lastValid = 0;
+    return 0;
+}
+
+extern "C" int sgbm_debug_fetch(sgbm_handle *h, int which, void *host_dst, size_t bytes)
+{
+    if (!h || !host_dst) return sgbm_fail(SGBM_E_INVALID_ARG, "null argument");
+    if (!h->lastValid) return sgbm_fail(SGBM_E_INVALID_ARG, "no frame has been computed");
+    const Geo &g = h->lastGeo;
+    SGBM_CUDA_CHECK(cudaDeviceSynchronize());
+    if (which == 2) {
+        size_t need = (size_t)g.W * g.H * 2;
+        if (bytes < need) return sgbm_fail(SGBM_E_INVALID_ARG, "buffer too small");
+        SGBM_CUDA_CHECK(cudaMemcpy(host_dst, h->lastRaw, need, cudaMemcpyDeviceToHost));
+        return 0;
+    }
+    const uint16_t *src = which == 0 ? h->lastC : h->lastS;
+    if (!src) return sgbm_fail(SGBM_E_INVALID_ARG, "stage %d was not kept (call sgbm_debug_keep first)", which);
+    size_t need = (size_t)g.H * g.W1 * g.D * 2;
+    if (bytes < need) return sgbm_fail(SGBM_E_INVALID_ARG, "buffer too small");
+    std::vector<uint16_t> tmp((size_t)g.rowStride * g.H);
+    SGBM_CUDA_CHECK(cudaMemcpy(tmp.data(), src, tmp.size() * 2, cudaMemcpyDeviceToHost));
+    uint16_t *dst = (uint16_t *)host_dst;
+    std::vector<int> pos(g.D);
+    for (int d = 0; d < g.D; d++) pos[d] = sgbm_pos(d, g.nreg, g.lpc);
+    for (size_t c = 0; c < (size_t)g.H * g.W1; c++)
+        for (int d = 0; d < g.D; d++) dst[c * g.D + d] = tmp[c * g.Dp + pos[d]];
+    return 0;
+}
+
+extern "C" int sgbm_microbench_int16(int which, double *giga_lane_ops_per_s)
+{
+    if (!giga_lane_ops_per_s) return sgbm_fail(SGBM_E_INVALID_ARG, "null argument");
+    return sgbm_run_microbench(which, giga_lane_ops_per_s);
+}
+
+extern "C" unsigned long long sgbm_kernel_launches(void) { return g_launches.load(); }
+
+extern "C" int sgbm_profile_enable(sgbm_handle *h, int on)
+{
+    if (!h) return sgbm_fail(SGBM_E_INVALID_ARG, "null handle");
+    h->prof = on ? 1 : 0;
+    h->marks.clear();
+    h->evUsed = 0;
+    return 0;
+}
+
+extern "C" int sgbm_profile_read(sgbm_handle *h, char *names32, double *total_ms, int *runs, int *kernels, int max_stages,
+                                 int *n_stages)
+{
+    if (!h || !names32 || !total_ms || !runs || !kernels || !n_stages) return sgbm_fail(SGBM_E_INVALID_ARG, "null argument");
+    if (max_stages < ST_COUNT - 1) return sgbm_fail(SGBM_E_INVALID_ARG, "need room for %d stages", ST_COUNT - 1);
+    if (!h->marks.empty()) SGBM_CUDA_CHECK(cudaEventSynchronize(h->marks.back().ev));
+    double ms[ST_COUNT] = {0};
+    int cnt[ST_COUNT] = {0}, ker[ST_COUNT] = {0};
+    for (size_t i = 1; i < h->marks.size(); i++) {
+        const ProfMark &a = h->marks[i - 1], &b = h->marks[i];
+        if (b.stage == ST_START) continue;
+        float t = 0;
+        SGBM_CUDA_CHECK(cudaEventElapsedTime(&t, a.ev, b.ev));
+        ms[b.stage] += t; cnt[b.stage]++; ker[b.stage] += (int)(b.launches - a.launches);
+    }
+    int n = 0;
+    for (int s = 1; s < ST_COUNT; s++) {
+        if (!cnt[s]) continue;
+        strncpy(names32 + 32 * n, kStageNames[s], 31);
+        names32[32 * n + 31] = 0;
+        total_ms[n] = ms[s]; runs[n] = cnt[s]; kernels[n] = ker[s];
+        n++;
+    }
+    *n_stages = n;
+    h->marks.clear();
+    h->evUsed = 0;
+    return 0;
+}

@@ -1,0 +1,163 @@
+// sgbm_common.cuh -- shared definitions of the sm_100a dense-stereo kernels.
+//
+// Arithmetic contract: SURVEY.md Appendix A (the validated restatement of what
+// cv2.StereoSGBM.compute does at the reference call site main.ipynb:655-668).
+//
+// Data layout in HBM (all internal volumes are uint16, values are non-negative int16 costs):
+//   volume[y][x1][pos]   x1 = x - minX1 in [0,W1),  pos in [0,Dp)
+// A column's disparity vector is owned by a group of LPC lanes of one warp, each lane holding
+// 2*NREG consecutive disparities as NREG packed u16x2 registers (lane l: d = l*2*NREG ...).
+// In memory the vector is stored chunk-interleaved so that the 16-byte chunk k of lane l sits at
+// byte offset 16*(LPC*k + l): every 128-bit load/store of a group is one contiguous segment.
+//   pos(d) = 8*(LPC*k + l) + e   with l = d / (2*NREG), k = (d % (2*NREG)) / 8, e = d % 8
+// Dp = 2*NREG*LPC >= D; lanes >= lanesUsed = D/(2*NREG) are whole padding lanes.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SGBM_MAX_S 0x7FFF7FFFu      // packed saturation value 32767 (A.4)
+#define SGBM_INF2  0xFFFFFFFFu      // packed +inf for out-of-range disparity neighbours
+
+struct Geo {
+    int W, H, cn;
+    int minD, D, maxD, r, P1, P2, UR, DMD, ftzero, INV, minX1, maxX1, W1, mode;
+    int nreg, lpc, Dp, lanesUsed;
+    int lpcShift;                    // log2(lpc)
+    long long rowStride;             // W1 * Dp  (u16 elements)
+};
+
+__host__ __device__ __forceinline__ int sgbm_pos(int d, int nreg, int lpc)
+{
+    int l = d / (2 * nreg), i = d % (2 * nreg);
+    return 8 * (lpc * (i >> 3) + l) + (i & 7);
+}
+
+// ---- packed u16x2 helpers (map 1:1 onto VIMNMX / VIMNMX3 / VIADDMNMX .U16x2 on sm_100a) -------
+__device__ __forceinline__ uint32_t pmin(uint32_t a, uint32_t b) { return __vminu2(a, b); }
+__device__ __forceinline__ uint32_t pmin3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
+__device__ __forceinline__ uint32_t paddmin(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_u16x2(a, b, c); }
+__device__ __forceinline__ uint32_t pswap(uint32_t a) { return __byte_perm(a, 0, 0x1032); }
+__device__ __forceinline__ uint32_t pbcast(uint32_t v) { return (v & 0xFFFFu) * 0x10001u; }
+
+// Group-wide (LPC lanes, aligned) min of a packed value whose halves are already equal.
+template <int LPC>
+__device__ __forceinline__ uint32_t group_min(uint32_t t)
+{
+#pragma unroll
+    for (int off = LPC / 2; off >= 1; off >>= 1) t = pmin(t, __shfl_xor_sync(0xFFFFFFFFu, t, off, LPC));
+    return t;
+}
+
+// Local min over NREG packed registers, both halves combined and broadcast to both halves.
+template <int NREG>
+__device__ __forceinline__ uint32_t local_min(const uint32_t (&v)[NREG])
+{
+    uint32_t t = v[0];
+#pragma unroll
+    for (int j = 1; j + 1 < NREG; j += 2) t = pmin3(t, v[j], v[j + 1]);
+    if ((NREG & 1) == 0) t = pmin(t, v[NREG - 1]);
+    return pmin(t, pswap(t));
+}
+
+// Vector load/store of one lane's NREG registers (NREG % 4 == 0) from a column base pointer.
+template <int NREG, int LPC>
+__device__ __forceinline__ void load_vec(uint32_t (&v)[NREG], const uint16_t *col, int lg)
+{
+    const uint4 *p = reinterpret_cast<const uint4 *>(col) + lg;
+#pragma unroll
+    for (int k = 0; k < NREG / 4; k++) {
+        uint4 q = p[LPC * k];
+        v[4 * k + 0] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+    }
+}
+template <int NREG, int LPC>
+__device__ __forceinline__ void load_vec_nc(uint32_t (&v)[NREG], const uint16_t *col, int lg)
+{
+    const uint4 *p = reinterpret_cast<const uint4 *>(col) + lg;
+#pragma unroll
+    for (int k = 0; k < NREG / 4; k++) {
+        uint4 q = __ldg(p + LPC * k);
+        v[4 * k + 0] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+    }
+}
+template <int NREG, int LPC>
+__device__ __forceinline__ void store_vec(const uint32_t (&v)[NREG], uint16_t *col, int lg)
+{
+    uint4 *p = reinterpret_cast<uint4 *>(col) + lg;
+#pragma unroll
+    for (int k = 0; k < NREG / 4; k++)
+        p[LPC * k] = make_uint4(v[4 * k + 0], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+}
+
+// One step of the SGM recurrence (A.4) for one column, distributed over a group of LPC lanes:
+//   Ln(d) = C(d) + min(Lp(d), Lp(d-1)+P1, Lp(d+1)+P1, m+P2) - m,   m = min_k Lp(k)
+// Lp / mp : predecessor's path costs and their (packed, broadcast) minimum.
+// Returns the new packed-broadcast minimum of Ln.  lg = lane in group, lastLane = lanesUsed-1.
+// Unsigned 16-bit arithmetic: every intermediate is <= m + P2 <= 65534 or <= C + P2.
+template <int NREG, int LPC>
+__device__ __forceinline__ uint32_t path_step(uint32_t (&Ln)[NREG], const uint32_t (&Lp)[NREG],
+                                              uint32_t mp, const uint32_t (&C)[NREG], uint32_t P1p,
+                                              uint32_t P2mP1p, int lg, int lastLane)
+{
+    uint32_t up = __shfl_up_sync(0xFFFFFFFFu, Lp[NREG - 1], 1, LPC);
+    uint32_t dn = __shfl_down_sync(0xFFFFFFFFu, Lp[0], 1, LPC);
+    if (lg == 0) up = SGBM_INF2;                 // L(-1) = +inf
+    if (lg >= lastLane) dn = SGBM_INF2;          // L(D)  = +inf
+    const uint32_t k1 = mp + P2mP1p;             // (m + P2 - P1) in both halves, no carry (<= 65535)
+    uint32_t sPrev = __byte_perm(up, Lp[0], 0x5432);   // (L[2j-1], L[2j]) for j = 0
+#pragma unroll
+    for (int j = 0; j < NREG; j++) {
+        uint32_t nxt = (j + 1 < NREG) ? Lp[j + 1] : dn;
+        uint32_t sNext = __byte_perm(Lp[j], nxt, 0x5432);   // (L[2j+1], L[2j+2])
+        uint32_t a = pmin3(sPrev, sNext, k1);               // min(L(d-1), L(d+1), m+P2-P1)
+        uint32_t b = paddmin(a, P1p, Lp[j]);                // min(a + P1, L(d))
+        Ln[j] = b + C[j] - mp;                              // halves stay in [0, 65535]: plain add
+        sPrev = sNext;
+    }
+    uint32_t t = local_min<NREG>(Ln);
+    if (lg > lastLane) t = SGBM_INF2;
+    return group_min<LPC>(t);
+}
+
+// Path start (predecessor outside the image): L = C, m = min C.
+template <int NREG, int LPC>
+__device__ __forceinline__ uint32_t path_start(uint32_t (&Ln)[NREG], const uint32_t (&C)[NREG], int lg,
+                                               int lastLane)
+{
+#pragma unroll
+    for (int j = 0; j < NREG; j++) Ln[j] = C[j];
+    uint32_t t = local_min<NREG>(Ln);
+    if (lg > lastLane) t = SGBM_INF2;
+    return group_min<LPC>(t);
+}
+
+// Arguments of the vertical sweep kernel (sgbm_paths.cu), filled by sgbm_api.cu.
+struct VertArgs {
+    Geo g;
+    const uint16_t *C;        // cost volume
+    const uint16_t *Calt;     // 3WAY: re-clamped first r rows of stripes 1..3 ([3][r][W1][Dp]) or null
+    const uint16_t *inA;      // volumes added into S before the paths of this sweep (may alias sout)
+    const uint16_t *inB;      // second input volume or null
+    uint16_t *sout;           // non-null: store S (no WTA)
+    uint16_t *sdbg;           // test hook: also store the final S of WTA rows here (or null)
+    int16_t *raw;             // WTA output, dense H x W int16 (pre-filled with INV)
+    unsigned int *d2key;      // WTA disp2 splat keys, dense H x W, pre-filled with 0xFFFFFFFF
+    int SW, nstrips;          // columns per strip, number of strips
+    int backward;             // 0: rows 0..H-1, 1: rows H-1..0
+    int threeway;             // MODE_SGBM_3WAY rules (stripes via blockIdx.y, tie-break, uniqueness)
+    int ss, ov;               // 3WAY stripe height and overlap
+    uint16_t *haloA;          // [nstrips][2][Dp + 8]  last column's (x-1)-path state of each strip
+    uint16_t *haloC;          // [nstrips][2][Dp + 8]  first column's (x+1)-path state of each strip
+    unsigned int *flagA;      // [nstrips] rows published
+    unsigned int *flagC;
+};
+
+#define SGBM_CUDA_CHECK(call)                                                              \
+    do {                                                                                   \
+        cudaError_t _e = (call);                                                           \
+        if (_e != cudaSuccess) return sgbm_fail_cuda(_e, #call, __FILE__, __LINE__);       \
+    } while (0)
+
+int sgbm_fail_cuda(cudaError_t e, const char *what, const char *file, int line);
+void sgbm_count_launch(int n);          // bump the process-wide kernel launch counter
+int sgbm_fail(int code, const char *fmt, ...);

@@ -1,0 +1,458 @@
+// sgbm_paths.cu -- stages 3+4 of StereoSGBM.compute (main.ipynb:668) for sm_100a:
+//   k_horizontal : the two horizontal SGM paths (-1,0) and (+1,0); one lane group per image row
+//                  walks the row, state in registers, min over disparities by warp shuffles.
+//   k_vertical   : the vertical + two diagonal paths of one sweep (top-down or bottom-up), all
+//                  columns in parallel, one persistent CTA per column strip; diagonal state is
+//                  exchanged through shared memory inside a strip and through L2-resident halo
+//                  buffers + release/acquire flags between neighbouring strips.  The sweep either
+//                  spills S once (MODE_HH forward sweep) or runs the fused winner-take-all:
+//                  uniqueness, sub-pixel fit, disp2 splat (A.5 / A.6).
+// Recurrence and saturation rules: SURVEY.md Appendix A.4; packed u16x2 DPX arithmetic
+// (VIMNMX3 / VIADDMNMX) as described in sgbm_common.cuh.
+#include "sgbm_common.cuh"
+
+// =================================================================================================
+// Horizontal paths
+// =================================================================================================
+#define HZ_THREADS 128
+#define HZ_PF 4                      // prefetch depth (columns in flight per lane group)
+
+template <int NREG, int LPC>
+__global__ void __launch_bounds__(HZ_THREADS) k_horizontal(Geo g, const uint16_t *__restrict__ C,
+                                                           uint16_t *__restrict__ LhA,
+                                                           uint16_t *__restrict__ LhB, int y0, int nrows)
+{
+    const int gpb = HZ_THREADS / LPC;
+    const int grp = threadIdx.x / LPC, lg = threadIdx.x % LPC;
+    int row = y0 + blockIdx.x * gpb + grp;
+    const bool act = row < y0 + nrows;
+    if (!act) row = y0 + nrows - 1;                       // keep the warp convergent, no stores
+    const int dir = blockIdx.y;                           // 0: predecessor (-1,0), 1: predecessor (+1,0)
+    const int W1 = g.W1, Dp = g.Dp, lastLane = g.lanesUsed - 1;
+    const uint16_t *crow = C + (size_t)row * g.rowStride;
+    uint16_t *orow = (dir ? LhB : LhA) + (size_t)row * g.rowStride;
+    const uint32_t P1p = (uint32_t)g.P1 * 0x10001u, P2mP1p = (uint32_t)(g.P2 - g.P1) * 0x10001u;
+
+    uint32_t L[NREG], m = 0;
+#pragma unroll
+    for (int j = 0; j < NREG; j++) L[j] = 0;              // "predecessor outside" == L = 0, m = 0 (A.4)
+    uint32_t cb[HZ_PF][NREG];
+#pragma unroll
+    for (int i = 0; i < HZ_PF; i++) {
+        int s = i < W1 ? i : W1 - 1;
+        load_vec_nc<NREG, LPC>(cb[i], crow + (size_t)(dir ? W1 - 1 - s : s) * Dp, lg);
+    }
+    for (int s0 = 0; s0 < W1; s0 += HZ_PF) {
+#pragma unroll
+        for (int i = 0; i < HZ_PF; i++) {
+            const int s = s0 + i;
+            if (s < W1) {
+                uint32_t Cc[NREG], Ln[NREG];
+#pragma unroll
+                for (int j = 0; j < NREG; j++) Cc[j] = cb[i][j];
+                if (s + HZ_PF < W1) {
+                    int sn = s + HZ_PF;
+                    load_vec_nc<NREG, LPC>(cb[i], crow + (size_t)(dir ? W1 - 1 - sn : sn) * Dp, lg);
+                }
+                m = path_step<NREG, LPC>(Ln, L, m, Cc, P1p, P2mP1p, lg, lastLane);
+#pragma unroll
+                for (int j = 0; j < NREG; j++) L[j] = Ln[j];
+                if (act) store_vec<NREG, LPC>(Ln, orow + (size_t)(dir ? W1 - 1 - s : s) * Dp, lg);
+            }
+        }
+    }
+}
+
+// =================================================================================================
+// Vertical sweep
+// =================================================================================================
+
+__device__ __forceinline__ unsigned int ld_acquire(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(unsigned int *p, unsigned int v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int NREG, int LPC>
+__device__ __forceinline__ void load_vec_cg(uint32_t (&v)[NREG], const uint16_t *col, int lg)
+{
+    const uint4 *p = reinterpret_cast<const uint4 *>(col) + lg;
+#pragma unroll
+    for (int k = 0; k < NREG / 4; k++) {
+        uint4 q = __ldcg(p + LPC * k);
+        v[4 * k + 0] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+    }
+}
+
+// NDIR = 3: vertical + both diagonals (MODE_SGBM / MODE_HH sweeps);  NDIR = 1: vertical only.
+// Register budget: ~5*NREG live packed registers + 3*NREG prefetch => cap the CTA size per NREG.
+template <int NREG> struct VertMaxThreads { static const int value = NREG >= 16 ? 384 : (NREG >= 12 ? 512 : (NREG >= 8 ? 640 : 1024)); };
+
+template <int NREG, int LPC, int NDIR>
+__global__ void __launch_bounds__(VertMaxThreads<NREG>::value, 1) k_vertical(VertArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const Geo &g = a.g;
+    const int Dp = g.Dp, W1 = g.W1, lastLane = g.lanesUsed - 1;
+    const int SW = a.SW, strip = blockIdx.x;
+    const int xs = strip * SW;
+    const int ncols = min(SW, W1 - xs);
+    const int ngroups = blockDim.x / LPC;
+    const int grp = threadIdx.x / LPC, lg = threadIdx.x % LPC;
+    const bool act = grp < ncols;
+    const int c = act ? grp : ncols - 1;                 // inactive groups mirror the last column
+    const int x1 = xs + c;
+    const uint32_t P1p = (uint32_t)g.P1 * 0x10001u, P2mP1p = (uint32_t)(g.P2 - g.P1) * 0x10001u;
+
+    // ---- row program ----------------------------------------------------------------------------
+    int yBegin, nRows, yStep, tOut;
+    const uint16_t *calt = nullptr;
+    int altRows = 0;
+    if (a.threeway) {
+        const int n = blockIdx.y;
+        const int o0 = n * a.ss, o1 = min((n + 1) * a.ss, g.H);
+        if (o0 >= o1) return;
+        const int s0 = max(o0 - a.ov, 0);
+        yBegin = s0; nRows = o1 - s0; yStep = 1; tOut = o0 - s0;
+        if (s0 > 0 && g.r > 0) { calt = a.Calt + (size_t)(n - 1) * g.r * g.rowStride; altRows = g.r; }
+    } else {
+        yBegin = a.backward ? g.H - 1 : 0; nRows = g.H; yStep = a.backward ? -1 : 1; tOut = 0;
+    }
+
+    // ---- shared memory --------------------------------------------------------------------------
+    // exA/exC [2][SW+2][Dp] u16 : previous-row state of the (x-1)/(x+1) paths, slot s <-> column xs+s-1
+    // exm     [2][2][SW+2] u32  : their packed minima
+    // ssm     [ngroups][Dp] u16 : WTA scratch
+    uint16_t *exA = reinterpret_cast<uint16_t *>(smem);
+    uint16_t *exC = exA + (size_t)2 * (SW + 2) * Dp;
+    uint32_t *exm = reinterpret_cast<uint32_t *>(exC + (size_t)2 * (SW + 2) * Dp);
+    uint16_t *ssm = reinterpret_cast<uint16_t *>(exm + 2 * 2 * (SW + 2)) + (size_t)grp * Dp;
+    if (NDIR == 3) {
+        uint32_t *z = reinterpret_cast<uint32_t *>(smem);
+        const int nz = (int)((2 * 2 * (size_t)(SW + 2) * Dp * 2 + 2 * 2 * (SW + 2) * 4) / 4);
+        for (int i = threadIdx.x; i < nz; i += blockDim.x) z[i] = 0;
+        __syncthreads();
+    }
+    const bool needLeft = (NDIR == 3) && act && c == 0 && strip > 0;                    // reads haloA[strip-1]
+    const bool needRight = (NDIR == 3) && act && c == ncols - 1 && strip < a.nstrips - 1;  // reads haloC[strip+1]
+    const bool pubA = needRight;     // the last column's (x-1)-path state feeds strip+1
+    const bool pubC = needLeft;      // the first column's (x+1)-path state feeds strip-1
+    const size_t haloStride = (size_t)Dp + 8;
+
+    uint32_t LB[NREG], mB = 0;
+#pragma unroll
+    for (int j = 0; j < NREG; j++) LB[j] = 0;
+
+    const bool hasB = a.inB != nullptr;
+    uint32_t Cn[NREG], An[NREG], Bn[NREG];               // prefetched next-row operands
+    auto crow_ptr = [&](int t) -> const uint16_t * {
+        const int y = yBegin + t * yStep;
+        return (t < altRows) ? calt + (size_t)t * g.rowStride + (size_t)x1 * Dp
+                             : a.C + (size_t)y * g.rowStride + (size_t)x1 * Dp;
+    };
+    load_vec_nc<NREG, LPC>(Cn, crow_ptr(0), lg);
+    if (0 >= tOut) {
+        load_vec<NREG, LPC>(An, a.inA + (size_t)yBegin * g.rowStride + (size_t)x1 * Dp, lg);
+        if (hasB) load_vec<NREG, LPC>(Bn, a.inB + (size_t)yBegin * g.rowStride + (size_t)x1 * Dp, lg);
+    }
+
+    for (int t = 0; t < nRows; t++) {
+        const int y = yBegin + t * yStep;
+        uint32_t Cc[NREG], S[NREG];
+#pragma unroll
+        for (int j = 0; j < NREG; j++) Cc[j] = Cn[j];
+        const bool outRow = t >= tOut;
+        if (outRow) {
+#pragma unroll
+            for (int j = 0; j < NREG; j++) S[j] = hasB ? paddmin(An[j], Bn[j], SGBM_MAX_S) : An[j];
+        }
+        if (t + 1 < nRows) {                              // prefetch the next row of this column
+            load_vec_nc<NREG, LPC>(Cn, crow_ptr(t + 1), lg);
+            if (t + 1 >= tOut) {
+                const size_t off = (size_t)(y + yStep) * g.rowStride + (size_t)x1 * Dp;
+                load_vec<NREG, LPC>(An, a.inA + off, lg);
+                if (hasB) load_vec<NREG, LPC>(Bn, a.inB + off, lg);
+            }
+        }
+        uint32_t Ln[NREG];
+        // ---- vertical path: predecessor (x, previous row), state in registers -------------------
+        mB = path_step<NREG, LPC>(Ln, LB, mB, Cc, P1p, P2mP1p, lg, lastLane);
+#pragma unroll
+        for (int j = 0; j < NREG; j++) LB[j] = Ln[j];
+        if (outRow) {
+#pragma unroll
+            for (int j = 0; j < NREG; j++) S[j] = paddmin(S[j], Ln[j], SGBM_MAX_S);
+        }
+        if (NDIR == 3) {
+            const int pp = (t + 1) & 1, pc = t & 1;      // previous / current parity
+            if (t > 0) {                                  // wait for the neighbour strips' row t-1
+                if (needLeft && lg == 0) while (ld_acquire(a.flagA + strip - 1) < (unsigned)t) { }
+                if (needRight && lg == 0) while (ld_acquire(a.flagC + strip + 1) < (unsigned)t) { }
+                __syncwarp();
+            }
+            uint32_t Lp[NREG], mp;
+            // ---- path with predecessor (x-1, previous row) --------------------------------------
+            if (needLeft && t > 0) {
+                const uint16_t *h = a.haloA + ((size_t)(strip - 1) * 2 + pp) * haloStride;
+                load_vec_cg<NREG, LPC>(Lp, h, lg);
+                mp = __ldcg(reinterpret_cast<const unsigned int *>(h + Dp));
+            } else {
+                load_vec<NREG, LPC>(Lp, exA + ((size_t)pp * (SW + 2) + c) * Dp, lg);
+                mp = exm[(0 * 2 + pp) * (SW + 2) + c];
+            }
+            uint32_t mA = path_step<NREG, LPC>(Ln, Lp, mp, Cc, P1p, P2mP1p, lg, lastLane);
+            if (act) {
+                store_vec<NREG, LPC>(Ln, exA + ((size_t)pc * (SW + 2) + c + 1) * Dp, lg);
+                if (lg == 0) exm[(0 * 2 + pc) * (SW + 2) + c + 1] = mA;
+                if (pubA) {
+                    uint16_t *h = a.haloA + ((size_t)strip * 2 + pc) * haloStride;
+                    store_vec<NREG, LPC>(Ln, h, lg);
+                    if (lg == 0) *reinterpret_cast<unsigned int *>(h + Dp) = mA;
+                }
+            }
+            if (outRow) {
+#pragma unroll
+                for (int j = 0; j < NREG; j++) S[j] = paddmin(S[j], Ln[j], SGBM_MAX_S);
+            }
+            // ---- path with predecessor (x+1, previous row) --------------------------------------
+            if (needRight && t > 0) {
+                const uint16_t *h = a.haloC + ((size_t)(strip + 1) * 2 + pp) * haloStride;
+                load_vec_cg<NREG, LPC>(Lp, h, lg);
+                mp = __ldcg(reinterpret_cast<const unsigned int *>(h + Dp));
+            } else {
+                load_vec<NREG, LPC>(Lp, exC + ((size_t)pp * (SW + 2) + c + 2) * Dp, lg);
+                mp = exm[(1 * 2 + pp) * (SW + 2) + c + 2];
+            }
+            uint32_t mC = path_step<NREG, LPC>(Ln, Lp, mp, Cc, P1p, P2mP1p, lg, lastLane);
+            if (act) {
+                store_vec<NREG, LPC>(Ln, exC + ((size_t)pc * (SW + 2) + c + 1) * Dp, lg);
+                if (lg == 0) exm[(1 * 2 + pc) * (SW + 2) + c + 1] = mC;
+                if (pubC) {
+                    uint16_t *h = a.haloC + ((size_t)strip * 2 + pc) * haloStride;
+                    store_vec<NREG, LPC>(Ln, h, lg);
+                    if (lg == 0) *reinterpret_cast<unsigned int *>(h + Dp) = mC;
+                }
+            }
+            if (outRow) {
+#pragma unroll
+                for (int j = 0; j < NREG; j++) S[j] = paddmin(S[j], Ln[j], SGBM_MAX_S);
+            }
+            // ---- publish row t to the neighbour strips ------------------------------------------
+            if (pubA || pubC) __threadfence();
+            __syncwarp();
+            if (pubA && lg == 0) st_release(a.flagA + strip, (unsigned)(t + 1));
+            if (pubC && lg == 0) st_release(a.flagC + strip, (unsigned)(t + 1));
+        }
+
+        if (outRow) {
+            if (a.sout) {
+                if (act) store_vec<NREG, LPC>(S, a.sout + (size_t)y * g.rowStride + (size_t)x1 * Dp, lg);
+            } else {
+                // ---- winner-take-all (A.5 / A.6) --------------------------------------------------
+                if (a.sdbg && act) store_vec<NREG, LPC>(S, a.sdbg + (size_t)y * g.rowStride + (size_t)x1 * Dp, lg);
+                uint32_t tm = local_min<NREG>(S);
+                if (lg > lastLane) tm = SGBM_INF2;
+                const uint32_t mS2 = group_min<LPC>(tm);
+                const int minS = (int)(mS2 & 0xFFFFu);
+                int best;
+                if (!a.threeway) {
+                    int idx = 0x7FFF;
+#pragma unroll
+                    for (int j = NREG - 1; j >= 0; j--) {
+                        const uint32_t e = S[j] ^ mS2;
+                        if ((e >> 16) == 0) idx = 2 * j + 1;
+                        if ((e & 0xFFFFu) == 0) idx = 2 * j;
+                    }
+                    int dl = (lg <= lastLane && idx != 0x7FFF) ? lg * 2 * NREG + idx : 0x7FFF;
+#pragma unroll
+                    for (int off = LPC / 2; off >= 1; off >>= 1)
+                        dl = min(dl, __shfl_xor_sync(0xFFFFFFFFu, dl, off, LPC));
+                    best = (minS == 32767) ? -1 : dl;                 // first minimum (A.5)
+                } else {
+                    // 8-lane SIMD tie-break of the reference (A.6): per class d%8 the largest tied d,
+                    // then the smallest of those.  q[i] halves hold (d/8 + 1) of classes 2i, 2i+1.
+                    uint32_t q[4] = {0u, 0u, 0u, 0u};
+                    const uint32_t qbase = (uint32_t)(lg * (NREG / 4));
+#pragma unroll
+                    for (int j = 0; j < NREG; j++) {
+                        const uint32_t e = S[j] ^ mS2;
+                        const uint32_t val = qbase + (uint32_t)(j >> 2) + 1u;
+                        const uint32_t v2 = (((e & 0xFFFFu) == 0) ? val : 0u) | (((e >> 16) == 0) ? (val << 16) : 0u);
+                        q[j & 3] = __vmaxu2(q[j & 3], v2);
+                    }
+                    best = 0x7FFFFFFF;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        uint32_t v = (lg > lastLane) ? 0u : q[i];
+#pragma unroll
+                        for (int off = LPC / 2; off >= 1; off >>= 1)
+                            v = __vmaxu2(v, __shfl_xor_sync(0xFFFFFFFFu, v, off, LPC));
+                        const int lo = (int)(v & 0xFFFFu), hi = (int)(v >> 16);
+                        if (lo) best = min(best, 8 * (lo - 1) + 2 * i);
+                        if (hi) best = min(best, 8 * (hi - 1) + 2 * i + 1);
+                    }
+                }
+                // S to shared scratch: sub-pixel neighbours and the masked uniqueness scan
+                __syncwarp();
+                store_vec<NREG, LPC>(S, ssm, lg);
+                __syncwarp();
+                int Sm = 0, Sp = 0;
+                const bool interior = best > 0 && best < g.D - 1;
+                if (lg == 0 && interior) {
+                    Sm = ssm[sgbm_pos(best - 1, NREG, LPC)];
+                    Sp = ssm[sgbm_pos(best + 1, NREG, LPC)];
+                }
+                bool reject = false;
+                if (g.UR > 0) {
+                    int T;
+                    const int av = 100 - g.UR;
+                    if (!a.threeway) {                        // S(d)*(100-UR) < minS*100  <=>  S(d) < T
+                        T = av > 0 ? min((100 * minS + av - 1) / av, 32768) : (minS > 0 ? 32768 : 0);
+                    } else {                                  // truncated threshold with (short) wrap (A.6)
+                        const int t1 = (int)(short)((100 * minS) / av + 1);
+                        T = max(t1, 0);
+                    }
+                    __syncwarp();
+                    if (lg == 0) {
+#pragma unroll
+                        for (int dd = -1; dd <= 1; dd++) {
+                            const int d = best + dd;
+                            if (d >= 0 && d < g.D) ssm[sgbm_pos(d, NREG, LPC)] = 0xFFFFu;
+                        }
+                    }
+                    __syncwarp();
+                    uint32_t S2[NREG];
+                    load_vec<NREG, LPC>(S2, ssm, lg);
+                    uint32_t t2 = local_min<NREG>(S2);
+                    if (lg > lastLane) t2 = SGBM_INF2;
+                    const int m2 = (int)(group_min<LPC>(t2) & 0xFFFFu);
+                    reject = m2 < T;
+                }
+                if (lg == 0 && act) {
+                    const int x = x1 + g.minX1;
+                    int out = g.INV;
+                    if (!reject) {
+                        const int x2 = x - best - g.minD;
+                        if (minS < 32767 && x2 >= 0 && x2 < g.W)
+                            atomicMin(a.d2key + (size_t)y * g.W + x2, ((unsigned)minS << 16) | (0xFFFFu - (unsigned)x1));
+                        int dq = best * 16;
+                        if (interior) {
+                            const int den = max(Sm + Sp - 2 * minS, 1);
+                            dq += ((Sm - Sp) * 16 + den) / (2 * den);
+                        }
+                        out = dq + g.minD * 16;
+                    }
+                    a.raw[(size_t)y * g.W + x] = (int16_t)out;
+                }
+            }
+        }
+        if (NDIR == 3) __syncthreads();
+    }
+}
+
+// =================================================================================================
+// Host side: template dispatch and launch configuration
+// =================================================================================================
+size_t sgbm_vertical_smem_bytes(const Geo &g, int SW, int threads)
+{
+    size_t ex = (size_t)2 * 2 * (SW + 2) * g.Dp * 2 + (size_t)2 * 2 * (SW + 2) * 4;
+    size_t ss = (size_t)(threads / g.lpc) * g.Dp * 2;
+    return (ex + ss + 15) & ~(size_t)15;
+}
+
+template <int NREG, int LPC>
+static int launch_horizontal_t(const Geo &g, const uint16_t *C, uint16_t *LhA, uint16_t *LhB, int y0,
+                               int nrows, cudaStream_t st)
+{
+    const int gpb = HZ_THREADS / LPC;
+    dim3 grid((nrows + gpb - 1) / gpb, 2);
+    k_horizontal<NREG, LPC><<<grid, HZ_THREADS, 0, st>>>(g, C, LhA, LhB, y0, nrows);
+    sgbm_count_launch(1);
+    SGBM_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+struct VertPlan { int SW, nstrips, threads; size_t smem; };
+
+template <int NREG, int LPC, int NDIR>
+static int launch_vertical_t(VertArgs &a, int numSMs, cudaStream_t st)
+{
+    const Geo &g = a.g;
+    auto kern = k_vertical<NREG, LPC, NDIR>;
+    static bool attrDone = false;
+    static int maxSmem = 0;
+    if (!attrDone) {
+        int dev = 0;
+        SGBM_CUDA_CHECK(cudaGetDevice(&dev));
+        SGBM_CUDA_CHECK(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        SGBM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        attrDone = true;
+    }
+    if (NDIR == 1) {
+        // independent columns: ordinary grid, 128 threads per CTA
+        const int threads = 128;
+        a.SW = threads / LPC;
+        a.nstrips = (g.W1 + a.SW - 1) / a.SW;
+        const size_t smem = sgbm_vertical_smem_bytes(g, a.SW, threads);
+        dim3 grid(a.nstrips, a.threeway ? 4 : 1);
+        kern<<<grid, threads, smem, st>>>(a);
+        sgbm_count_launch(1);
+        SGBM_CUDA_CHECK(cudaGetLastError());
+        return 0;
+    }
+    // NDIR == 3: all strips must be co-resident (neighbour flags) -> cooperative launch, <= 1 CTA per SM
+    int SW = (g.W1 + numSMs - 1) / numSMs;
+    if (SW < 1) SW = 1;
+    if (SW * LPC > VertMaxThreads<NREG>::value)
+        return sgbm_fail(-3, "image too wide for the vertical sweep (W1=%d, lanes/column=%d, SMs=%d)", g.W1, LPC, numSMs);
+    int threads = ((SW * LPC + 31) / 32) * 32;
+    size_t smem = sgbm_vertical_smem_bytes(g, SW, threads);
+    if (smem > (size_t)maxSmem) return sgbm_fail(-3, "vertical sweep needs %zu bytes of shared memory (max %d)", smem, maxSmem);
+    a.SW = SW;
+    a.nstrips = (g.W1 + SW - 1) / SW;
+    int occ = 0;
+    SGBM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    if (occ * numSMs < a.nstrips) return sgbm_fail(-3, "vertical sweep cannot be made co-resident (%d strips, %d x %d slots)", a.nstrips, occ, numSMs);
+    SGBM_CUDA_CHECK(cudaMemsetAsync(a.flagA, 0, sizeof(unsigned int) * a.nstrips, st));
+    SGBM_CUDA_CHECK(cudaMemsetAsync(a.flagC, 0, sizeof(unsigned int) * a.nstrips, st));
+    void *args[] = {&a};
+    SGBM_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)kern, dim3(a.nstrips), dim3(threads), args, smem, st));
+    sgbm_count_launch(1);
+    return 0;
+}
+
+#define SGBM_DISPATCH(NREG_, LPC_, EXPR)                                              \
+    if (g.nreg == NREG_ && g.lpc == LPC_) { constexpr int NREG = NREG_; constexpr int LPC = LPC_; return EXPR; }
+
+#define SGBM_DISPATCH_ALL(EXPR)                                                       \
+    SGBM_DISPATCH(4, 2, EXPR) SGBM_DISPATCH(4, 4, EXPR) SGBM_DISPATCH(4, 8, EXPR)     \
+    SGBM_DISPATCH(4, 16, EXPR) SGBM_DISPATCH(4, 32, EXPR)                             \
+    SGBM_DISPATCH(8, 2, EXPR) SGBM_DISPATCH(8, 4, EXPR) SGBM_DISPATCH(8, 8, EXPR)     \
+    SGBM_DISPATCH(8, 16, EXPR) SGBM_DISPATCH(8, 32, EXPR)                             \
+    SGBM_DISPATCH(12, 2, EXPR) SGBM_DISPATCH(12, 4, EXPR) SGBM_DISPATCH(12, 8, EXPR)  \
+    SGBM_DISPATCH(12, 16, EXPR) SGBM_DISPATCH(12, 32, EXPR)                           \
+    SGBM_DISPATCH(16, 2, EXPR) SGBM_DISPATCH(16, 4, EXPR) SGBM_DISPATCH(16, 8, EXPR)  \
+    SGBM_DISPATCH(16, 16, EXPR) SGBM_DISPATCH(16, 32, EXPR)
+
+int sgbm_launch_horizontal(const Geo &g, const uint16_t *C, uint16_t *LhA, uint16_t *LhB, int y0, int nrows,
+                           cudaStream_t st)
+{
+    SGBM_DISPATCH_ALL((launch_horizontal_t<NREG, LPC>(g, C, LhA, LhB, y0, nrows, st)))
+    return sgbm_fail(-3, "no kernel for lane mapping nreg=%d lpc=%d", g.nreg, g.lpc);
+}
+
+int sgbm_launch_vertical(VertArgs &a, int ndir, int numSMs, cudaStream_t st)
+{
+    const Geo &g = a.g;
+    if (ndir == 3) {
+        SGBM_DISPATCH_ALL((launch_vertical_t<NREG, LPC, 3>(a, numSMs, st)))
+    } else {
+        SGBM_DISPATCH_ALL((launch_vertical_t<NREG, LPC, 1>(a, numSMs, st)))
+    }
+    return sgbm_fail(-3, "no kernel for lane mapping nreg=%d lpc=%d", g.nreg, g.lpc);
+}

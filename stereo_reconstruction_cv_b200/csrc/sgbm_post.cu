@@ -1,0 +1,354 @@
+// sgbm_post.cu -- per-pixel tail of the path for sm_100a (all HBM-bound, one thread per pixel):
+//   k_lrcheck      : disp12MaxDiff left-right consistency check (A.5)
+//   k_median3x3    : the always-on 3x3 median of cv2.StereoSGBM.compute (A.7)
+//   k_cc_*         : cv2.filterSpeckles as connected components (lock-free union-find) (A.7)
+//   k_disp_to_float: .astype(float32)/16 and positivity mask               (main.ipynb:668-670)
+//   k_reproject    : cv2.reprojectImageTo3D in fp64, bit exact             (main.ipynb:697, A.8)
+//   k_compact_*    : finite/positive mask + ordered gather to XYZ/RGB      (main.ipynb:726-737)
+#include "sgbm_common.cuh"
+
+__global__ void k_fill_i16(int16_t *p, size_t n, int16_t v)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ---- LR check ---------------------------------------------------------------------------------
+// d2key[y][x2] = (cost << 16) | (0xFFFF - x1) of the winning left pixel, 0xFFFFFFFF if never hit.
+// disp2[x2] = (x1 + minX1) - x2 for a hit, INV (the x16-scaled marker, [P2]) otherwise.
+__device__ __forceinline__ int disp2_at(const unsigned int *krow, int p, int minX1, int INV)
+{
+    unsigned int k = krow[p];
+    if (k == 0xFFFFFFFFu) return INV;
+    return (int)(0xFFFFu - (k & 0xFFFFu)) + minX1 - p;
+}
+
+__global__ void k_lrcheck(int16_t *raw, const unsigned int *d2key, int W, int H, int minX1, int maxX1,
+                          int minD, int INV, int DMD)
+{
+    int x = minX1 + blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= maxX1) return;
+    int d1 = raw[(size_t)y * W + x];
+    if (d1 == INV) return;
+    const unsigned int *krow = d2key + (size_t)y * W;
+    int _d = d1 >> 4, d_ = (d1 + 15) >> 4;
+    int _x = x - _d, x_ = x - d_;
+    bool bad0 = false, bad1 = false;
+    if (0 <= _x && _x < W) { int v = disp2_at(krow, _x, minX1, INV); bad0 = v >= minD && abs(v - _d) > DMD; }
+    if (0 <= x_ && x_ < W) { int v = disp2_at(krow, x_, minX1, INV); bad1 = v >= minD && abs(v - d_) > DMD; }
+    if (bad0 && bad1) raw[(size_t)y * W + x] = (int16_t)INV;
+}
+
+// ---- 3x3 median, replicate border -----------------------------------------------------------------
+__device__ __forceinline__ void cswap(int &a, int &b) { int t = min(a, b); b = max(a, b); a = t; }
+
+__global__ void k_median3x3(const int16_t *src, int16_t *dst, int W, int H, long long dstPitchElems)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= W) return;
+    int xm = max(x - 1, 0), xp = min(x + 1, W - 1);
+    const int16_t *r0 = src + (size_t)max(y - 1, 0) * W, *r1 = src + (size_t)y * W, *r2 = src + (size_t)min(y + 1, H - 1) * W;
+    int p0 = r0[xm], p1 = r0[x], p2 = r0[xp], p3 = r1[xm], p4 = r1[x], p5 = r1[xp], p6 = r2[xm], p7 = r2[x], p8 = r2[xp];
+    // 19-exchange median-of-9 network
+    cswap(p1, p2); cswap(p4, p5); cswap(p7, p8); cswap(p0, p1); cswap(p3, p4); cswap(p6, p7);
+    cswap(p1, p2); cswap(p4, p5); cswap(p7, p8); cswap(p0, p3); cswap(p5, p8); cswap(p4, p7);
+    cswap(p3, p6); cswap(p1, p4); cswap(p2, p5); cswap(p4, p7); cswap(p4, p2); cswap(p6, p4);
+    cswap(p4, p2);
+    dst[(size_t)y * dstPitchElems + x] = (int16_t)p4;
+}
+
+// ---- speckle filter: connected components by union-find ----------------------------------------
+__device__ __forceinline__ int uf_find(const int *L, int i)
+{
+    int p = ((volatile const int *)L)[i];
+    while (p != i) { i = p; p = ((volatile const int *)L)[i]; }
+    return i;
+}
+__device__ __forceinline__ void uf_union(int *L, int a, int b)
+{
+    bool done;
+    do {
+        a = uf_find(L, a);
+        b = uf_find(L, b);
+        if (a < b) { int old = atomicMin(&L[b], a); done = (old == b); b = old; }
+        else if (b < a) { int old = atomicMin(&L[a], b); done = (old == a); a = old; }
+        else done = true;
+    } while (!done);
+}
+
+__global__ void k_cc_init(const int16_t *img, int *label, int *size, int n, int newVal)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    label[i] = (img[i] != newVal) ? i : -1;
+    size[i] = 0;
+}
+__global__ void k_cc_merge(const int16_t *img, int *label, int W, int H, int newVal, int maxDiff)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= W) return;
+    int i = y * W + x;
+    int v = img[i];
+    if (v == newVal) return;
+    if (x + 1 < W) { int w = img[i + 1]; if (w != newVal && abs(v - w) <= maxDiff) uf_union(label, i, i + 1); }
+    if (y + 1 < H) { int w = img[i + W]; if (w != newVal && abs(v - w) <= maxDiff) uf_union(label, i, i + W); }
+}
+__global__ void k_cc_count(int *label, int *size, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (label[i] < 0) return;
+    int r = uf_find(label, i);
+    label[i] = r;                       // path flattening; racing readers still see an ancestor
+    atomicAdd(&size[r], 1);
+}
+__global__ void k_cc_apply(int16_t *img, const int *label, const int *size, int n, int newVal, int maxSize)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int r = label[i];
+    if (r >= 0 && size[r] <= maxSize) img[i] = (int16_t)newVal;
+}
+
+// ---- float conversion + reprojection --------------------------------------------------------------
+__device__ __forceinline__ float disp_float_masked(int d16)
+{
+    float f = (float)d16 / 16.0f;                 // exact
+    return f * ((f > 0.0f) ? 1.0f : 0.0f);        // numpy: disparity_map * mask  (-0.0 for negatives)
+}
+
+__global__ void k_disp_to_float(const int16_t *d, float *out, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = disp_float_masked(d[i]);
+}
+
+struct QMat { double q[16]; };
+
+// h = Q * (x, y, d, 1)^T left to right in fp64 without contraction; out = f32( f64(f32(h_c)) * (1/h_3) )
+__device__ __forceinline__ void reproject_px(const QMat &Q, int x, int y, double d, float &X, float &Y, float &Z)
+{
+    double h[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        double s = __dadd_rn(__dmul_rn(Q.q[4 * k + 0], (double)x), __dmul_rn(Q.q[4 * k + 1], (double)y));
+        s = __dadd_rn(s, __dmul_rn(Q.q[4 * k + 2], d));
+        h[k] = __dadd_rn(s, Q.q[4 * k + 3]);
+    }
+    double iw = __ddiv_rn(1.0, h[3]);
+    X = __double2float_rn(__dmul_rn((double)__double2float_rn(h[0]), iw));
+    Y = __double2float_rn(__dmul_rn((double)__double2float_rn(h[1]), iw));
+    Z = __double2float_rn(__dmul_rn((double)__double2float_rn(h[2]), iw));
+}
+
+template <typename T>
+__global__ void k_reproject(const T *disp, QMat Q, int W, int H, float *xyz, uint8_t *valid)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= W) return;
+    size_t i = (size_t)y * W + x;
+    double d = (double)disp[i];
+    float X, Y, Z;
+    reproject_px(Q, x, y, d, X, Y, Z);
+    xyz[3 * i + 0] = X; xyz[3 * i + 1] = Y; xyz[3 * i + 2] = Z;
+    if (valid) valid[i] = (isfinite(X) && d > 0.0) ? 1 : 0;
+}
+
+// ---- fused tail: /16, mask, reproject, validity, ordered compaction ---------------------------------
+#define CP_THREADS 256
+#define CP_ITEMS 4                      // pixels per thread, CP_THREADS*CP_ITEMS pixels per block
+
+__global__ void k_compact_count(const int16_t *disp, QMat Q, int W, int H, unsigned int *blockCount)
+{
+    __shared__ unsigned int wsum[CP_THREADS / 32];
+    size_t n = (size_t)W * H;
+    size_t base = (size_t)blockIdx.x * CP_THREADS * CP_ITEMS + (size_t)threadIdx.x * CP_ITEMS;
+    unsigned int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < CP_ITEMS; k++) {
+        size_t i = base + k;
+        if (i < n) {
+            float f = disp_float_masked(disp[i]);
+            float X, Y, Z;
+            reproject_px(Q, (int)(i % W), (int)(i / W), (double)f, X, Y, Z);
+            cnt += (isfinite(X) && f > 0.0f) ? 1u : 0u;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int s = 0;
+        for (int w = 0; w < CP_THREADS / 32; w++) s += wsum[w];
+        blockCount[blockIdx.x] = s;
+    }
+}
+
+// single-CTA exclusive scan of the block counts (nblocks <= a few 10^4)
+__global__ void k_compact_scan(const unsigned int *blockCount, unsigned long long *blockOffset, int nblocks,
+                               unsigned long long *total)
+{
+    __shared__ unsigned long long carry;
+    __shared__ unsigned long long wtot[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nblocks; b0 += blockDim.x) {
+        int i = b0 + threadIdx.x;
+        unsigned long long v = i < nblocks ? blockCount[i] : 0, incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        unsigned long long woff = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) woff += wtot[w];
+        if (i < nblocks) blockOffset[i] = carry + woff + incl - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry += woff + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void k_compact_scatter(const int16_t *disp, QMat Q, int W, int H, const uint8_t *bgr, int bgrCn,
+                                  long long bgrPitch, const unsigned long long *blockOffset, float *xyz,
+                                  uint8_t *rgb)
+{
+    __shared__ unsigned int wsum[CP_THREADS / 32];
+    size_t n = (size_t)W * H;
+    size_t base = (size_t)blockIdx.x * CP_THREADS * CP_ITEMS + (size_t)threadIdx.x * CP_ITEMS;
+    float P[CP_ITEMS][3];
+    bool ok[CP_ITEMS];
+    unsigned int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < CP_ITEMS; k++) {
+        size_t i = base + k;
+        ok[k] = false;
+        if (i < n) {
+            float f = disp_float_masked(disp[i]);
+            reproject_px(Q, (int)(i % W), (int)(i / W), (double)f, P[k][0], P[k][1], P[k][2]);
+            ok[k] = isfinite(P[k][0]) && f > 0.0f;
+            cnt += ok[k] ? 1u : 0u;
+        }
+    }
+    unsigned int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    unsigned int woff = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); w++) woff += wsum[w];
+    unsigned long long pos = blockOffset[blockIdx.x] + woff + incl - cnt;
+#pragma unroll
+    for (int k = 0; k < CP_ITEMS; k++) {
+        if (ok[k]) {
+            size_t i = base + k;
+            xyz[3 * pos + 0] = P[k][0]; xyz[3 * pos + 1] = P[k][1]; xyz[3 * pos + 2] = P[k][2];
+            if (rgb) {
+                int x = (int)(i % W), y = (int)(i / W);
+                const uint8_t *s = bgr + (size_t)y * bgrPitch + (size_t)x * bgrCn;
+                if (bgrCn == 3) { rgb[3 * pos + 0] = s[2]; rgb[3 * pos + 1] = s[1]; rgb[3 * pos + 2] = s[0]; }
+                else { rgb[3 * pos + 0] = s[0]; rgb[3 * pos + 1] = s[0]; rgb[3 * pos + 2] = s[0]; }
+            }
+            pos++;
+        }
+    }
+}
+
+// =================================================================================================
+// host launchers
+// =================================================================================================
+int sgbm_launch_fill_i16(int16_t *p, size_t n, int v, cudaStream_t st)
+{
+    k_fill_i16<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, (int16_t)v);
+    sgbm_count_launch(1);
+    SGBM_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int sgbm_launch_lrcheck(const Geo &g, int16_t *raw, const unsigned int *d2key, cudaStream_t st)
+{
+    dim3 grid((g.W1 + 255) / 256, g.H);
+    k_lrcheck<<<grid, 256, 0, st>>>(raw, d2key, g.W, g.H, g.minX1, g.maxX1, g.minD, g.INV, g.DMD);
+    sgbm_count_launch(1);
+    SGBM_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int sgbm_launch_median(const int16_t *src, int16_t *dst, int W, int H, long long dstPitchElems, cudaStream_t st)
+{
+    dim3 grid((W + 255) / 256, H);
+    k_median3x3<<<grid, 256, 0, st>>>(src, dst, W, H, dstPitchElems);
+    sgbm_count_launch(1);
+    SGBM_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int sgbm_launch_speckles(int16_t *img, int W, int H, int newVal, int maxSize, int maxDiff, void *scratch,
+                         cudaStream_t st)
+{
+    int n = W * H;
+    int *label = (int *)scratch, *size = label + n;
+    k_cc_init<<<(n + 255) / 256, 256, 0, st>>>(img, label, size, n, newVal);
+    dim3 grid((W + 255) / 256, H);
+    k_cc_merge<<<grid, 256, 0, st>>>(img, label, W, H, newVal, maxDiff);
+    k_cc_count<<<(n + 255) / 256, 256, 0, st>>>(label, size, n);
+    k_cc_apply<<<(n + 255) / 256, 256, 0, st>>>(img, label, size, n, newVal, maxSize);
+    sgbm_count_launch(4);
+    SGBM_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int sgbm_launch_disp_to_float(const int16_t *d, float *out, size_t n, cudaStream_t st)
+{
+    k_disp_to_float<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, out, n);
+    sgbm_count_launch(1);
+    SGBM_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int sgbm_launch_reproject(const void *disp, int isFloat, const double *Qh, int W, int H, float *xyz,
+                          uint8_t *valid, cudaStream_t st)
+{
+    QMat Q;
+    for (int i = 0; i < 16; i++) Q.q[i] = Qh[i];
+    dim3 grid((W + 255) / 256, H);
+    if (isFloat) k_reproject<float><<<grid, 256, 0, st>>>((const float *)disp, Q, W, H, xyz, valid);
+    else k_reproject<int16_t><<<grid, 256, 0, st>>>((const int16_t *)disp, Q, W, H, xyz, valid);
+    sgbm_count_launch(1);
+    SGBM_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+size_t sgbm_compact_scratch_bytes(int W, int H)
+{
+    size_t nb = ((size_t)W * H + CP_THREADS * CP_ITEMS - 1) / (CP_THREADS * CP_ITEMS);
+    return nb * (sizeof(unsigned int) + sizeof(unsigned long long)) + 64;
+}
+
+int sgbm_launch_compact(const int16_t *disp, const double *Qh, int W, int H, const uint8_t *bgr, int bgrCn,
+                        long long bgrPitch, float *xyz, uint8_t *rgb, unsigned long long *nOut, void *scratch,
+                        cudaStream_t st)
+{
+    QMat Q;
+    for (int i = 0; i < 16; i++) Q.q[i] = Qh[i];
+    int nb = (int)(((size_t)W * H + CP_THREADS * CP_ITEMS - 1) / (CP_THREADS * CP_ITEMS));
+    unsigned long long *off = (unsigned long long *)scratch;
+    unsigned int *cnt = (unsigned int *)(off + nb);
+    k_compact_count<<<nb, CP_THREADS, 0, st>>>(disp, Q, W, H, cnt);
+    k_compact_scan<<<1, 1024, 0, st>>>(cnt, off, nb, nOut);
+    k_compact_scatter<<<nb, CP_THREADS, 0, st>>>(disp, Q, W, H, bgr, bgrCn, bgrPitch, off, xyz, rgb);
+    sgbm_count_launch(3);
+    SGBM_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,310 @@
+"""Host-side mirror of the cv2 API the reference calls on its dense-reconstruction path.
+
+    cv2.StereoSGBM_create(...)            main.ipynb:655-666  ->  StereoSGBM_create(...)
+    stereo.compute(imgL, imgR)            main.ipynb:668      ->  StereoSGBM.compute(left, right)
+    cv2.reprojectImageTo3D(disparity, Q)  main.ipynb:697      ->  reprojectImageTo3D(disparity, Q)
+    cv2.filterSpeckles / cv2.medianBlur   (stages of compute) ->  filterSpeckles / medianBlur3
+
+Same names, argument order, defaults and result dtypes as the cv2 binding, so the notebook's
+compute_disparity_map / reconstruct_3D run unchanged with `cv2` replaced by this module.  numpy
+arrays go through the C ABI's host entry point (pinned staging + H2D/D2H); torch CUDA tensors are
+passed as device pointers on the current stream and the result stays on the device.
+All arithmetic runs in libsgbm_b200.so (CUDA, sm_100a); there is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import SgbmParams, check, error  # noqa: F401
+
+MODE_SGBM = 0
+MODE_HH = 1
+MODE_SGBM_3WAY = 2
+MODE_HH4 = 3
+DISP_SHIFT = 4
+DISP_SCALE = 16
+
+_PARAM_NAMES = ("minDisparity", "numDisparities", "blockSize", "P1", "P2", "disp12MaxDiff",
+                "preFilterCap", "uniquenessRatio", "speckleWindowSize", "speckleRange", "mode")
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _is_tensor(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _stream_ptr(device):
+    torch = _torch()
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class StereoSGBM:
+    """Drop-in for the object returned by cv2.StereoSGBM_create (main.ipynb:655)."""
+
+    def __init__(self, **kw):
+        self._p = SgbmParams(*[int(kw.get(n, d)) for n, d in zip(_PARAM_NAMES, (0, 16, 3, 0, 0, 0, 0, 0, 0, 0, 0))])
+        self._h = C.c_void_p()
+        check(_lib.lib().sgbm_create(C.byref(self._p), C.byref(self._h)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                _lib.lib().sgbm_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    # -- cv2-style accessors ----------------------------------------------------------------------
+    def _set(self, name, v):
+        setattr(self._p, name, int(v))
+        check(_lib.lib().sgbm_set_params(self._h, C.byref(self._p)))
+
+    def getMinDisparity(self): return self._p.minDisparity
+    def setMinDisparity(self, v): self._set("minDisparity", v)
+    def getNumDisparities(self): return self._p.numDisparities
+    def setNumDisparities(self, v): self._set("numDisparities", v)
+    def getBlockSize(self): return self._p.blockSize
+    def setBlockSize(self, v): self._set("blockSize", v)
+    def getP1(self): return self._p.P1
+    def setP1(self, v): self._set("P1", v)
+    def getP2(self): return self._p.P2
+    def setP2(self, v): self._set("P2", v)
+    def getDisp12MaxDiff(self): return self._p.disp12MaxDiff
+    def setDisp12MaxDiff(self, v): self._set("disp12MaxDiff", v)
+    def getPreFilterCap(self): return self._p.preFilterCap
+    def setPreFilterCap(self, v): self._set("preFilterCap", v)
+    def getUniquenessRatio(self): return self._p.uniquenessRatio
+    def setUniquenessRatio(self, v): self._set("uniquenessRatio", v)
+    def getSpeckleWindowSize(self): return self._p.speckleWindowSize
+    def setSpeckleWindowSize(self, v): self._set("speckleWindowSize", v)
+    def getSpeckleRange(self): return self._p.speckleRange
+    def setSpeckleRange(self, v): self._set("speckleRange", v)
+    def getMode(self): return self._p.mode
+    def setMode(self, v): self._set("mode", v)
+
+    def workspaceBytes(self, W, H, channels=1):
+        out = C.c_size_t()
+        check(_lib.lib().sgbm_workspace_bytes(self._h, W, H, channels, C.byref(out)))
+        return out.value
+
+    # -- compute -----------------------------------------------------------------------------------
+    def compute(self, left, right, disparity=None):
+        """int16 disparity x16 (invalid = (minDisparity-1)*16), like cv2.StereoSGBM.compute.
+
+        numpy uint8 HxW or HxWx3 -> new C-contiguous numpy int16 HxW.
+        torch.uint8 CUDA tensors (H,W), (H,W,3), (B,H,W) or (B,H,W,3 with channels_last=True)
+        -> torch.int16 CUDA tensor of shape (H,W) / (B,H,W)."""
+        if _is_tensor(left):
+            return self._compute_torch(left, right, disparity)
+        left = np.asarray(left)
+        right = np.asarray(right)
+        if left.dtype != np.uint8 or right.dtype != np.uint8:
+            raise error(-1, "left/right must be uint8 (cv2: stereosgbm.cpp:2213 assertion)")
+        if left.shape != right.shape or left.ndim not in (2, 3):
+            raise error(-1, "left and right must have the same HxW[xC] shape")
+        cn = 1 if left.ndim == 2 else left.shape[2]
+        if cn == 1 and left.ndim == 3:
+            left, right = left[:, :, 0], right[:, :, 0]
+        # accept non-contiguous views the way cv2 does: rows must be dense, pitch may be anything
+        if left.strides[-1] != 1 or (left.ndim == 3 and left.strides[1] != cn):
+            left = np.ascontiguousarray(left)
+        if right.strides[-1] != 1 or (right.ndim == 3 and right.strides[1] != cn):
+            right = np.ascontiguousarray(right)
+        if left.strides[0] != right.strides[0] or left.strides[0] < left.shape[1] * cn:
+            left, right = np.ascontiguousarray(left), np.ascontiguousarray(right)
+        H, W = left.shape[:2]
+        out = np.empty((H, W), np.int16)
+        check(_lib.lib().sgbm_compute_host(self._h, left.ctypes.data, right.ctypes.data, W, H, cn,
+                                           left.strides[0], 1, out.ctypes.data, out.strides[0]))
+        if disparity is not None:
+            disparity[...] = out
+            return disparity
+        return out
+
+    def _compute_torch(self, left, right, disparity=None):
+        torch = _torch()
+        if not (left.is_cuda and right.is_cuda):
+            raise error(-1, "torch inputs must be CUDA tensors (use numpy arrays for host data)")
+        if left.dtype != torch.uint8 or right.dtype != torch.uint8 or left.shape != right.shape:
+            raise error(-1, "left/right must be uint8 tensors of the same shape")
+        left, right = left.contiguous(), right.contiguous()
+        shp = tuple(left.shape)
+        if left.dim() == 2:
+            B, H, W, cn = 1, shp[0], shp[1], 1
+        elif left.dim() == 3 and shp[2] == 3:                 # H x W x 3 colour image
+            B, H, W, cn = 1, shp[0], shp[1], 3
+        elif left.dim() == 3:
+            B, H, W, cn = shp[0], shp[1], shp[2], 1
+        elif left.dim() == 4 and shp[3] == 3:
+            B, H, W, cn = shp[0], shp[1], shp[2], 3
+        else:
+            raise error(-1, "unsupported tensor shape %s" % (shp,))
+        out_shape = (H, W) if (left.dim() == 2 or (left.dim() == 3 and cn == 3)) else (B, H, W)
+        if disparity is None:
+            disparity = torch.empty(out_shape, dtype=torch.int16, device=left.device)
+        elif tuple(disparity.shape) != out_shape or disparity.dtype != torch.int16 or not disparity.is_contiguous():
+            raise error(-1, "bad output tensor")
+        with torch.cuda.device(left.device):
+            check(_lib.lib().sgbm_compute(self._h, left.data_ptr(), right.data_ptr(), W, H, cn, W * cn, B,
+                                          disparity.data_ptr(), W * 2, _stream_ptr(left.device)))
+        return disparity
+
+    # -- test hooks ----------------------------------------------------------------------------------
+    def _debug_keep(self, on=True):
+        check(_lib.lib().sgbm_debug_keep(self._h, 1 if on else 0))
+
+    def _debug_fetch(self, which, shape):
+        out = np.empty(shape, np.int16)
+        check(_lib.lib().sgbm_debug_fetch(self._h, which, out.ctypes.data, out.nbytes))
+        return out
+
+
+def StereoSGBM_create(minDisparity=0, numDisparities=16, blockSize=3, P1=0, P2=0, disp12MaxDiff=0,
+                      preFilterCap=0, uniquenessRatio=0, speckleWindowSize=0, speckleRange=0,
+                      mode=MODE_SGBM):
+    """cv2.StereoSGBM_create with the binding's defaults ([P15])."""
+    return StereoSGBM(minDisparity=minDisparity, numDisparities=numDisparities, blockSize=blockSize, P1=P1,
+                      P2=P2, disp12MaxDiff=disp12MaxDiff, preFilterCap=preFilterCap,
+                      uniquenessRatio=uniquenessRatio, speckleWindowSize=speckleWindowSize,
+                      speckleRange=speckleRange, mode=mode)
+
+
+def _q16(Q):
+    Q = np.ascontiguousarray(np.asarray(Q, dtype=np.float64))
+    if Q.shape != (4, 4):
+        raise error(-1, "Q must be 4x4 (cv2: stereo_geom.cpp:19)")
+    return Q
+
+
+def reprojectImageTo3D(disparity, Q, _3dImage=None, handleMissingValues=False, ddepth=-1):
+    """cv2.reprojectImageTo3D (main.ipynb:697): float32 HxWx3.  Integer disparities are used as is."""
+    if handleMissingValues or ddepth not in (-1, 5):
+        raise error(-3, "handleMissingValues / integer ddepth are not implemented")
+    Q = _q16(Q)
+    L = _lib.lib()
+    torch = _torch()
+    if _is_tensor(disparity):
+        d = disparity.contiguous()
+        if not d.is_cuda or d.dim() != 2:
+            raise error(-1, "disparity tensor must be a 2-D CUDA tensor")
+        H, W = d.shape
+        out = torch.empty((H, W, 3), dtype=torch.float32, device=d.device)
+        with torch.cuda.device(d.device):
+            if d.dtype == torch.float32:
+                check(L.sgbm_reproject_f32(d.data_ptr(), Q.ctypes.data, W, H, out.data_ptr(), None, _stream_ptr(d.device)))
+            elif d.dtype == torch.int16:
+                check(L.sgbm_reproject_i16(d.data_ptr(), Q.ctypes.data, W, H, out.data_ptr(), None, _stream_ptr(d.device)))
+            else:
+                raise error(-1, "disparity must be float32 or int16")
+        return out
+    d = np.asarray(disparity)
+    if d.ndim != 2:
+        raise error(-1, "disparity must be HxW")
+    if d.dtype == np.float64:
+        raise error(-1, "float64 disparity is not accepted (cv2: stereo_geom.cpp:17)")
+    if d.dtype in (np.uint8, np.int32):
+        d = d.astype(np.float32)          # exact for the value ranges cv2 accepts here
+    if d.dtype not in (np.float32, np.int16):
+        raise error(-1, "unsupported disparity dtype %s" % d.dtype)
+    dt = torch.from_numpy(np.ascontiguousarray(d)).cuda()
+    res = reprojectImageTo3D(dt, Q).cpu().numpy()
+    if _3dImage is not None:
+        _3dImage[...] = res
+        return _3dImage
+    return res
+
+
+def disparityToFloat(disp_x16):
+    """disp.astype(float32)/16 followed by the positivity mask of main.ipynb:668-670 (CUDA tensor in/out)."""
+    torch = _torch()
+    d = disp_x16.contiguous()
+    out = torch.empty(d.shape, dtype=torch.float32, device=d.device)
+    H = int(np.prod(d.shape[:-1]))
+    with torch.cuda.device(d.device):
+        check(_lib.lib().sgbm_disp_to_float(d.data_ptr(), d.shape[-1], H, out.data_ptr(), _stream_ptr(d.device)))
+    return out
+
+
+def reprojectCompact(disp_x16, Q, colors_bgr=None):
+    """Fused tail of the notebook (main.ipynb:668-670, 697, 726-737) on the device.
+
+    disp_x16: int16 CUDA tensor HxW (output of compute).  Returns (xyz float32 Nx3, rgb uint8 Nx3 or None):
+    the points with finite X and disparity > 0 in row-major pixel order, colours swapped BGR->RGB."""
+    torch = _torch()
+    L = _lib.lib()
+    Q = _q16(Q)
+    d = disp_x16.contiguous()
+    H, W = d.shape
+    dev = d.device
+    xyz = torch.empty((H * W, 3), dtype=torch.float32, device=dev)
+    rgb = None
+    bgr_ptr, bgr_cn, bgr_pitch = None, 0, 0
+    if colors_bgr is not None:
+        cb = colors_bgr.contiguous()
+        bgr_cn = 1 if cb.dim() == 2 else int(cb.shape[2])
+        bgr_ptr, bgr_pitch = cb.data_ptr(), W * bgr_cn
+        rgb = torch.empty((H * W, 3), dtype=torch.uint8, device=dev)
+    nbytes = C.c_size_t()
+    check(L.sgbm_reproject_compact_scratch_bytes(W, H, C.byref(nbytes)))
+    scratch = torch.empty((nbytes.value,), dtype=torch.uint8, device=dev)
+    n = torch.zeros((1,), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        check(L.sgbm_reproject_compact(d.data_ptr(), Q.ctypes.data, W, H, bgr_ptr, bgr_cn, bgr_pitch, xyz.data_ptr(),
+                                       rgb.data_ptr() if rgb is not None else None, n.data_ptr(), scratch.data_ptr(),
+                                       nbytes.value, _stream_ptr(dev)))
+    cnt = int(n.item())
+    return xyz[:cnt], (rgb[:cnt] if rgb is not None else None)
+
+
+def filterSpeckles(img, newVal, maxSpeckleSize, maxDiff, buf=None):
+    """cv2.filterSpeckles: in place on an int16 image; returns (img, buf) like the cv2 binding."""
+    torch = _torch()
+    L = _lib.lib()
+    if _is_tensor(img):
+        if img.dtype != torch.int16 or not img.is_cuda or not img.is_contiguous() or img.dim() != 2:
+            raise error(-1, "img must be a contiguous 2-D int16 CUDA tensor")
+        H, W = img.shape
+        scratch = torch.empty((H * W * 8,), dtype=torch.uint8, device=img.device)
+        with torch.cuda.device(img.device):
+            check(L.sgbm_filter_speckles(img.data_ptr(), W, H, int(newVal), int(maxSpeckleSize), int(maxDiff),
+                                         scratch.data_ptr(), H * W * 8, _stream_ptr(img.device)))
+        return img, buf
+    a = np.asarray(img)
+    if a.dtype != np.int16 or a.ndim != 2:
+        raise error(-1, "img must be a 2-D int16 array")
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    filterSpeckles(t, newVal, maxSpeckleSize, maxDiff)
+    img[...] = t.cpu().numpy()
+    return img, buf
+
+
+def medianBlur3(img):
+    """cv2.medianBlur(img, 3) for int16 images (the always-on post filter of compute, A.7)."""
+    torch = _torch()
+    host = not _is_tensor(img)
+    t = torch.from_numpy(np.ascontiguousarray(np.asarray(img, np.int16))).cuda() if host else img.contiguous()
+    H, W = t.shape
+    out = torch.empty_like(t)
+    with torch.cuda.device(t.device):
+        check(_lib.lib().sgbm_median3x3(t.data_ptr(), out.data_ptr(), W, H, _stream_ptr(t.device)))
+    return out.cpu().numpy() if host else out
+
+
+def microbench_int16(which):
+    """Measured issue rate (G lane-ops/s) of the packed 16-bit integer instructions (roofline denominator)."""
+    v = C.c_double()
+    check(_lib.lib().sgbm_microbench_int16(int(which), C.byref(v)))
+    return v.value
+
+
+def device_info():
+    L = _lib.lib()
+    sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
+    name = C.create_string_buffer(128)
+    check(L.sgbm_device_info(C.byref(sm), C.byref(ma), C.byref(mi), name, 128))
+    return {"sm_count": sm.value, "cc": "%d.%d" % (ma.value, mi.value), "name": name.value.decode()}

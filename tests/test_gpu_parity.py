@@ -1,0 +1,259 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against the
+oracle (C port of SURVEY.md Appendix A), the cv2-generated golden vectors and -- when importable --
+the live cv2 binary.  Bit-exact for all integer outputs; reprojection bit-exact in fp32 (the
+north star's tolerance is 1e-5 relative; the test states both)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import OracleParams, cv2_ref
+from stereo_reconstruction_cv_b200.synth import make_noise_pair, make_pair
+
+pytestmark = pytest.mark.gpu
+
+MODES = {0: "SGBM", 1: "HH", 2: "3WAY", 3: "HH4"}
+
+
+@pytest.fixture(scope="module")
+def sg():
+    import torch
+    assert torch.cuda.is_available()
+    import stereo_reconstruction_cv_b200 as sg
+    return sg
+
+
+def _kw(p):
+    return dict(p.__dict__)
+
+
+def _mismatch(a, b):
+    return int((np.asarray(a) != np.asarray(b)).sum())
+
+
+# ------------------------------------------------------------------------------------------------
+# stage-wise: cost volume, aggregated S, raw disparity (before median) vs the oracle's stages
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("D,bs,minD", [(16, 3, 0), (64, 5, 0), (32, 7, -5), (48, 1, 3), (128, 5, 0)])
+def test_stages_vs_oracle(sg, mode, D, bs, minD):
+    W, H = 200 + D, 60
+    l, r, _ = make_pair(W, H, D + max(minD, 0), seed=D + mode)
+    p = OracleParams(minD, D, bs, 8 * bs * bs, 32 * bs * bs, 1, 63, 10, 0, 0, mode)
+    o = oracle.compute_debug(p, l, r, want_C=True, want_S=True, want_raw=True)
+    st = sg.StereoSGBM_create(**_kw(p))
+    st._debug_keep(True)
+    disp = st.compute(l, r)
+    W1 = oracle.port.valid_width(p, W)
+    if mode != 2:      # the oracle's C dump for 3WAY is stripe 0 only
+        C = st._debug_fetch(0, (H, W1, D))
+        assert _mismatch(C, o["C"]) == 0, "cost volume"
+    S = st._debug_fetch(1, (H, W1, D))
+    assert _mismatch(S, o["S"]) == 0, "aggregated cost S"
+    raw = st._debug_fetch(2, (H, W))
+    assert _mismatch(raw, o["raw"]) == 0, "raw disparity (WTA / uniqueness / subpixel / LR check)"
+    assert _mismatch(disp, o["disp"]) == 0, "final disparity"
+
+
+# ------------------------------------------------------------------------------------------------
+# golden vectors produced by the reference's implementation (cv2), committed under tests/golden
+# ------------------------------------------------------------------------------------------------
+def test_golden_small(sg, golden, golden_meta):
+    for name in sorted(golden_meta["cases"]):
+        p = OracleParams(**golden_meta["cases"][name])
+        st = sg.StereoSGBM_create(**_kw(p))
+        got = st.compute(golden[name + "__left"], golden[name + "__right"])
+        assert got.dtype == np.int16
+        assert _mismatch(got, golden[name + "__disp"]) == 0, name
+
+
+@pytest.mark.parametrize("name", ["mid_640x360_D64_SGBM", "mid_640x360_D64_HH", "mid_640x360_D64_3WAY",
+                                  "cfg2_1280x720_D128_SGBM", "cfg2_1280x720_D128_HH", "cfg2_1280x720_D128_3WAY",
+                                  "cfg4_1920x1080_D192_SGBM_seed0", "cfg3_3840x2160_D256_HH",
+                                  "cfg5_3840x2160_D256_3WAY"])
+def test_golden_digests(sg, golden_meta, name):
+    """BASELINE.json configs at full size: SHA-256 of the int16 disparity must equal cv2's."""
+    if name not in golden_meta["digests"]:
+        pytest.skip("digest not generated")
+    g = golden_meta["digests"][name]
+    l, r, _ = make_pair(g["W"], g["H"], g["D"], seed=g["seed"])
+    if hashlib.sha256(l.tobytes()).hexdigest() != g["left_sha256"] or \
+            hashlib.sha256(r.tobytes()).hexdigest() != g["right_sha256"]:
+        pytest.skip("synthetic generator differs from the one that made the digests")
+    st = sg.StereoSGBM_create(minDisparity=0, numDisparities=g["D"], blockSize=5, P1=200, P2=800, disp12MaxDiff=1,
+                              preFilterCap=63, uniquenessRatio=10, speckleWindowSize=100, speckleRange=32,
+                              mode=g["mode"])
+    got = st.compute(l, r)
+    assert abs(float((got >= 0).mean()) - g["valid_fraction"]) < 1e-12
+    assert hashlib.sha256(got.tobytes()).hexdigest() == g["disp_sha256"]
+
+
+# ------------------------------------------------------------------------------------------------
+# randomised sweep against the oracle (and live cv2 when importable)
+# ------------------------------------------------------------------------------------------------
+def test_random_sweep(sg):
+    rng = np.random.default_rng(77)
+    n = 0
+    use_cv2 = cv2_ref.available()
+    for it in range(120):
+        mode = it % 4
+        W = int(rng.integers(40, 200)); H = int(rng.integers(28, 70))
+        D = int(rng.choice([8, 16, 32, 48, 80, 96])); minD = int(rng.integers(-20, 21))
+        bs = int(rng.choice([0, 1, 3, 4, 5, 7, 9, 11]))
+        if rng.random() < 0.5:
+            P1, P2 = int(rng.integers(0, 400)), int(rng.integers(0, 3000))
+        else:
+            P1, P2 = 8 * 3 * bs * bs, 32 * 3 * bs * bs
+        p = OracleParams(minD, D, bs, P1, P2, int(rng.integers(-1, 4)), int(rng.integers(0, 80)),
+                         int(rng.integers(-1, 30)), int(rng.choice([0, 20, 100])), int(rng.choice([1, 2, 32])), mode)
+        r_eff = (bs if bs > 0 else (3 if mode == 2 else 5)) // 2
+        W1 = W + min(minD, 0) - max(minD + D, 0)
+        if W1 <= r_eff or not (W - (minD + D) > bs // 2):
+            continue
+        if mode == 2:
+            ss = (H + 3) // 4
+            if ss < bs // 2 + 1 + int(np.ceil(0.1 * ss)):
+                continue
+        if it % 3 == 0:
+            l, r = make_noise_pair(W, H, seed=it)
+        else:
+            l, r, _ = make_pair(W, H, max(D + max(minD, 0), 8), seed=it)
+        got = sg.StereoSGBM_create(**_kw(p)).compute(l, r)
+        assert _mismatch(got, oracle.compute(p, l, r)) == 0, (it, p, W, H)
+        if use_cv2 and mode != 3 and D % 16 == 0:
+            assert _mismatch(got, cv2_ref.compute(p, l, r)) == 0, ("cv2", it, p, W, H)
+        n += 1
+    assert n > 60
+
+
+def test_three_channel_and_views(sg):
+    l, r, _ = make_pair(160, 48, 16, seed=5)
+    l3 = np.stack([l, np.roll(l, 1, 1), l[::-1].copy()], -1)
+    r3 = np.stack([r, np.roll(r, 1, 1), r[::-1].copy()], -1)
+    p = OracleParams(0, 16, 5, 200, 800, 1, 63, 10, 0, 0, 0)
+    st = sg.StereoSGBM_create(**_kw(p))
+    assert _mismatch(st.compute(l3, r3), oracle.compute(p, l3, r3)) == 0
+    # non-contiguous views are accepted like cv2 does
+    big_l = np.zeros((48, 200), np.uint8); big_r = np.zeros((48, 200), np.uint8)
+    big_l[:, 20:180] = l; big_r[:, 20:180] = r
+    assert _mismatch(st.compute(big_l[:, 20:180], big_r[:, 20:180]), oracle.compute(p, l, r)) == 0
+
+
+def test_torch_batch_path(sg):
+    import torch
+    frames = [make_pair(256, 64, 32, seed=s) for s in range(3)]
+    L = torch.from_numpy(np.stack([f[0] for f in frames])).cuda()
+    R = torch.from_numpy(np.stack([f[1] for f in frames])).cuda()
+    p = OracleParams(0, 32, 5, 200, 800, 1, 63, 10, 50, 2, 1)
+    st = sg.StereoSGBM_create(**_kw(p))
+    out = st.compute(L, R)
+    assert out.shape == (3, 64, 256) and out.dtype == torch.int16 and out.is_cuda
+    for i, f in enumerate(frames):
+        assert _mismatch(out[i].cpu().numpy(), oracle.compute(p, f[0], f[1])) == 0
+
+
+def test_errors(sg):
+    l, r = make_noise_pair(40, 20, seed=0)
+    with pytest.raises(sg.error):
+        sg.StereoSGBM_create(numDisparities=48, blockSize=5).compute(l, r)            # cv2: stereosgbm.cpp:511
+    with pytest.raises(sg.error):
+        sg.StereoSGBM_create(minDisparity=-14, numDisparities=48, mode=2).compute(np.zeros((20, 47), np.uint8),
+                                                                                   np.zeros((20, 47), np.uint8))
+    with pytest.raises(sg.error):
+        sg.StereoSGBM_create(numDisparities=16).compute(l, r[:, :30])                 # size mismatch
+    with pytest.raises(sg.error):
+        sg.StereoSGBM_create(numDisparities=16).compute(l.astype(np.float32), r.astype(np.float32))
+    with pytest.raises(sg.error):
+        sg.reprojectImageTo3D(np.zeros((4, 4), np.float32), np.eye(3))                # cv2: stereo_geom.cpp:19
+    with pytest.raises(sg.error):
+        sg.reprojectImageTo3D(np.zeros((4, 4), np.float64), np.eye(4))                # cv2: stereo_geom.cpp:17
+
+
+# ------------------------------------------------------------------------------------------------
+# post filters and reprojection
+# ------------------------------------------------------------------------------------------------
+def test_post_filters_golden(sg, golden):
+    raw = golden["post__in"]
+    assert _mismatch(sg.medianBlur3(raw), golden["post__median"]) == 0
+    img = raw.copy()
+    sg.filterSpeckles(img, -16, 60, 32)
+    assert _mismatch(img, golden["post__speckle_60_32"]) == 0
+    rng = np.random.default_rng(3)
+    for (w, h, win, rg) in [(333, 97, 25, 1), (64, 64, 400, 3), (500, 300, 100, 32)]:
+        a = (rng.integers(-1, 40, (h, w)) * 16).astype(np.int16)
+        a[rng.random((h, w)) < 0.3] = -16
+        b = a.copy()
+        sg.filterSpeckles(b, -16, win, 16 * rg)
+        assert _mismatch(b, oracle.filter_speckles(a, -16, win, 16 * rg)) == 0
+
+
+def test_reproject_golden(sg, golden):
+    d = golden["reproj__disp_f32"]
+    for q, x in (("reproj__Q", "reproj__xyz"), ("reproj__Q_general", "reproj__xyz_general")):
+        got = sg.reprojectImageTo3D(d, golden[q])
+        ref = golden[x]
+        assert got.dtype == np.float32 and got.shape == ref.shape
+        fin = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(got), fin)                                    # same non-finite pattern
+        assert np.array_equal(got[~fin], ref[~fin]) or np.array_equal(np.sign(got[~fin]), np.sign(ref[~fin]))
+        rel = np.abs(got[fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1e-30)
+        assert rel.max() <= 1e-5                                                        # north-star tolerance
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))                 # and in fact bit exact
+    got = sg.reprojectImageTo3D(golden["post__in"], golden["reproj__Q"])                # int16 used as is
+    assert np.array_equal(got.view(np.uint32), golden["reproj__xyz_i16"].view(np.uint32))
+
+
+def test_fused_tail_matches_notebook_recipe(sg):
+    """int16 disparity -> /16, mask, reproject, finite/positive mask, gather (main.ipynb:668-670,697,726-737)."""
+    import torch
+    l, r, _ = make_pair(320, 120, 32, seed=9)
+    p = OracleParams(0, 32, 5, 200, 800, 1, 63, 10, 100, 32, 2)
+    st = sg.StereoSGBM_create(**_kw(p))
+    dt = st.compute(torch.from_numpy(l).cuda(), torch.from_numpy(r).cuda())
+    Q = np.array([[1, 0, 0, -160.0], [0, 1, 0, -60.0], [0, 0, 0, 400.0], [0, 0, -1, 0]], np.float64)
+    col = np.stack([l, r, (l // 2 + r // 2)], -1).astype(np.uint8)                       # BGR
+    xyz, rgb = sg.reprojectCompact(dt, Q, torch.from_numpy(col).cuda())
+    disp = dt.cpu().numpy()
+    f = disp.astype(np.float32) / 16.0
+    f = f * (f > 0).astype(np.float32)
+    assert np.array_equal(sg.disparityToFloat(dt).cpu().numpy().view(np.uint32), f.view(np.uint32))
+    pts = oracle.reproject_f32(f, Q)
+    mask = ~np.isnan(pts[:, :, 0]) & ~np.isinf(pts[:, :, 0]) & (f > 0)
+    assert xyz.shape[0] == int(mask.sum()) > 1000
+    assert np.array_equal(xyz.cpu().numpy().view(np.uint32), pts[mask].view(np.uint32))
+    assert np.array_equal(rgb.cpu().numpy(), col[:, :, ::-1][mask])
+
+
+# ------------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE.json's full sizes
+# ------------------------------------------------------------------------------------------------
+def test_full_size_properties(sg):
+    import torch
+    W, H, D = 3840, 2160, 256
+    l, r, gt = make_pair(W, H, D, seed=0)
+    st = sg.StereoSGBM_create(minDisparity=0, numDisparities=D, blockSize=5, P1=200, P2=800, disp12MaxDiff=1,
+                              preFilterCap=63, uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, mode=1)
+    lt, rt = torch.from_numpy(l).cuda(), torch.from_numpy(r).cuda()
+    d1 = st.compute(lt, rt)
+    d2 = st.compute(lt, rt)
+    assert torch.equal(d1, d2)                                             # deterministic
+    d = d1.cpu().numpy()
+    assert d.shape == (H, W) and (d[:, :D] == -16).all()                   # columns [0, minX1) invalid (A.0)
+    valid = d >= 0
+    assert 0.3 < valid.mean() < 0.95
+    assert d[valid].max() < D * 16
+    err = np.abs(d[valid] / 16.0 - gt[valid])
+    assert np.median(err) < 0.5                                            # recovers the synthetic ground truth
+    # speckle filter is idempotent; running it again on the output changes nothing
+    again = d1.clone()
+    sg.filterSpeckles(again, -16, 100, 16 * 32)
+    assert torch.equal(again, d1)
+    # a horizontally cropped band of rows reproduces the 3WAY stripe-independence: rows of stripe 0
+    st3 = sg.StereoSGBM_create(minDisparity=0, numDisparities=D, blockSize=5, P1=200, P2=800, disp12MaxDiff=1,
+                               preFilterCap=63, uniquenessRatio=10, speckleWindowSize=0, speckleRange=0, mode=2)
+    full = st3.compute(lt, rt).cpu().numpy()
+    ss = (H + 3) // 4
+    top = st3.compute(lt[:ss + 64].contiguous(), rt[:ss + 64].contiguous()).cpu().numpy()
+    # stripe 0 of the full image only sees rows < ss + r + 1 => identical away from the crop's own stripes
+    assert np.array_equal(full[: (ss + 64 + 3) // 4 - 8], top[: (ss + 64 + 3) // 4 - 8])
