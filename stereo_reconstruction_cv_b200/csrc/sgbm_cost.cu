@@ -64,10 +64,11 @@ __global__ void k_prefilter(const uint8_t *left, const uint8_t *right, long long
 // Per source row:  A) stage left/right prefiltered values in shared memory (right side as packed
 // reversed pairs so that one 32-bit load yields the operands of two adjacent disparities),
 // B) pixel costs for TX+2r columns (packed u16x2, biased by K so differences stay non-negative),
-// C) horizontal sum, ring update, running sum, coalesced 32-bit stores of C.
+//    one warp per column, lanes over disparity pairs,
+// C) each thread owns one 32-bit word (two disparities) of XPT consecutive columns: sliding
+//    horizontal window sum, ring update, running vertical sum, coalesced 32-bit stores of C.
+// blockDim = Dw * NXG with Dw = Dp/2 words per column; TX = NXG * XPT.
 // ------------------------------------------------------------------------------------------------
-#define COST_THREADS 256
-#define COST_NIT 16          // max packed items per thread: TX * Dp/2 <= COST_THREADS * COST_NIT
 #define COST_K 256u          // bias; multiple of 4 so that (bt_t + K) >> 2 == (bt_t >> 2) + K/4
 
 struct CostArgs {
@@ -76,19 +77,21 @@ struct CostArgs {
     uint16_t *out;           // row y is written at out + (y - y0) * rowStride
     int y0, nrows;           // output rows [y0, y0 + nrows)
     int ylo;                 // vertical clamp floor (0, or the stripe start for 3WAY)
-    int TX, RB;              // tile width (valid columns), rows per band
+    int NXG, RB;             // thread groups along x, rows per band
     int zeroTail;            // HH4 quirk (A.9): rows y >= H - r get C = 0
 };
 
-__global__ void __launch_bounds__(COST_THREADS) k_cost(CostArgs a)
+template <int NREG, int XPT>
+__global__ void __launch_bounds__(512) k_cost(CostArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const Geo &g = a.g;
-    const int r = g.r, TX = a.TX, TXH = TX + 2 * r, D = g.D, Dp = g.Dp, Dw = Dp / 2;   // Dw: u32 words/column
+    const int r = g.r, D = g.D, Dw = g.Dp / 2, HP = D / 2;
+    const int TX = a.NXG * XPT, TXH = TX + 2 * r;
     const int x0 = blockIdx.x * TX;                      // first valid column of the tile
     const int yb = a.y0 + blockIdx.y * a.RB;             // first output row of the band
     const int yend = min(yb + a.RB, a.y0 + a.nrows);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = COST_THREADS / 32;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
     const int cn = g.cn;
 
     // image-coordinate range of the tile incl. halo (clamped to the valid range)
@@ -96,7 +99,7 @@ __global__ void __launch_bounds__(COST_THREADS) k_cost(CostArgs a)
     const int xb = g.minX1 + min(max(x0 + TX - 1 + r, 0), g.W1 - 1);
     const int q0 = xa - g.maxD + 1;                      // first right-image column needed (pair base)
     const int NQ = (xb - xa) + D - 1;                    // pair entries q0 .. q0+NQ-1
-    const int NQh = (NQ + 1) / 2 + 1;                    // entries per parity array
+    const int NQh = (TXH + D) / 2 + 2;                   // entries per parity array (tile independent)
 
     // shared memory carve-up
     uint32_t *ring = reinterpret_cast<uint32_t *>(smem);                     // [(2r+1)][TX][Dw]
@@ -106,13 +109,16 @@ __global__ void __launch_bounds__(COST_THREADS) k_cost(CostArgs a)
 
     const size_t plane = (size_t)g.W * g.H;
     const int nslots = 2 * r + 1;
-    for (int i = tid; i < nslots * TX * Dw; i += COST_THREADS) ring[i] = 0;
+    for (int i = tid; i < nslots * TX * Dw; i += nthr) ring[i] = 0;
 
-    uint32_t crun[COST_NIT];
+    // phase C ownership: word w of columns xg*XPT .. xg*XPT+XPT-1
+    const int w = tid % Dw, xg = tid / Dw;
+    uint32_t crun[XPT];
 #pragma unroll
-    for (int n = 0; n < COST_NIT; n++) crun[n] = 0;
-    const int nitems = TX * Dw;
+    for (int n = 0; n < XPT; n++) crun[n] = 0;
     const uint32_t KK = COST_K * 0x10001u;
+    const uint32_t KSUB = (COST_K + COST_K / 4) * 0x10001u;
+    const int planeStrideW = 2 * NQh;                    // words between right-side planes
 
     const int nsteps = (yend - yb) + 2 * r;
     for (int k = 0; k < nsteps; k++) {
@@ -120,85 +126,87 @@ __global__ void __launch_bounds__(COST_THREADS) k_cost(CostArgs a)
         // ---- A: stage this source row --------------------------------------------------------
         for (int c = 0; c < cn; c++) {
             const uint8_t *pl = a.planes + (size_t)(0 * cn + c) * 6 * plane + (size_t)ysrc * g.W;
-            const uint8_t *pr = a.planes + (size_t)(1 * cn + c) * 6 * plane + (size_t)ysrc * g.W;
-            for (int i = tid; i < 6 * TXH; i += COST_THREADS) {
-                int p = i / TXH, xx = i % TXH;
-                int x = g.minX1 + min(max(x0 - r + xx, 0), g.W1 - 1);
-                lv[(c * 6 + p) * TXH + xx] = pl[(size_t)p * plane + x];
+            const uint8_t *pr = a.planes + (size_t)(1 * cn + c) * 6 * plane + (size_t)ysrc * g.W + q0;
+            for (int xx = tid; xx < TXH; xx += nthr) {
+                const int x = g.minX1 + min(max(x0 - r + xx, 0), g.W1 - 1);
+#pragma unroll
+                for (int p = 0; p < 6; p++) lv[(c * 6 + p) * TXH + xx] = pl[(size_t)p * plane + x];
             }
-            for (int i = tid; i < 6 * NQ; i += COST_THREADS) {
-                int p = i / NQ, qi = i % NQ;
-                int q = q0 + qi;                                      // 0 <= q, q+1 <= W-1 (A.2 range)
-                const uint8_t *src = pr + (size_t)p * plane + q;
-                uint32_t v = (uint32_t)src[1] | ((uint32_t)src[0] << 16);   // lo = v(q+1), hi = v(q)
-                rp[((c * 6 + p) * 2 + (qi & 1)) * NQh + (qi >> 1)] = v;
+            for (int qi = tid; qi < NQ; qi += nthr) {                       // 0 <= q, q+1 <= W-1 (A.2 range)
+                uint32_t *dst = rp + (size_t)(c * 6) * planeStrideW + (qi & 1) * NQh + (qi >> 1);
+#pragma unroll
+                for (int p = 0; p < 6; p++) {
+                    const uint8_t *src = pr + (size_t)p * plane + qi;
+                    dst[p * planeStrideW] = (uint32_t)src[1] | ((uint32_t)src[0] << 16);   // lo = v(q+1), hi = v(q)
+                }
             }
         }
         __syncthreads();
         // ---- B: pixel costs for the TXH columns ----------------------------------------------
-        for (int xx = warp; xx < TXH; xx += nwarp) {
-            const int x = g.minX1 + min(max(x0 - r + xx, 0), g.W1 - 1);
-            const int qtop = x - g.minD - 1 - q0;            // pair entry index for dr = 0
-            const int par = qtop & 1;
-            const int itop = qtop >> 1;
-            for (int pi = lane; pi < D / 2; pi += 32) {
-                uint32_t acc = 0;
-                for (int c = 0; c < cn; c++) {
-                    const uint8_t *lc = lv + (c * 6) * TXH + xx;
-                    const uint32_t *rc = rp + (size_t)(c * 6) * 2 * NQh + par * NQh + (itop - pi);
+        for (int c = 0; c < cn; c++) {
+            for (int xx = warp; xx < TXH; xx += nwarp) {
+                const int x = g.minX1 + min(max(x0 - r + xx, 0), g.W1 - 1);
+                const int qtop = x - g.minD - 1 - q0;            // pair entry index for dr = 0
+                const uint8_t *lc = lv + (c * 6) * TXH + xx;
+                uint32_t uK[2], Ku[2], KmUhi[2], UloK[2];
+#pragma unroll
+                for (int p = 0; p < 2; p++) {
+                    const uint32_t u = lc[(3 * p + 0) * TXH], ulo = lc[(3 * p + 1) * TXH], uhi = lc[(3 * p + 2) * TXH];
+                    uK[p] = (u + COST_K) * 0x10001u; Ku[p] = (COST_K - u) * 0x10001u;
+                    KmUhi[p] = (COST_K - uhi) * 0x10001u; UloK[p] = (ulo + COST_K) * 0x10001u;
+                }
+                const uint32_t *rc = rp + (size_t)(c * 6) * planeStrideW + (qtop & 1) * NQh + (qtop >> 1) - lane;
+                uint32_t *pcol = pixbuf + (size_t)xx * Dw;
+                for (int pi = lane; pi < HP; pi += 32, rc -= 32) {
                     uint32_t bt[2];
 #pragma unroll
                     for (int p = 0; p < 2; p++) {
-                        uint32_t u = lc[(3 * p + 0) * TXH], ulo = lc[(3 * p + 1) * TXH], uhi = lc[(3 * p + 2) * TXH];
-                        uint32_t v2 = rc[(size_t)(3 * p + 0) * 2 * NQh];
-                        uint32_t vlo2 = rc[(size_t)(3 * p + 1) * 2 * NQh];
-                        uint32_t vhi2 = rc[(size_t)(3 * p + 2) * 2 * NQh];
-                        uint32_t A = (u + COST_K) * 0x10001u - vhi2;          // u - vhi + K
-                        uint32_t B = vlo2 + (COST_K - u) * 0x10001u;          // vlo - u + K
-                        uint32_t c1 = __vimax3_u16x2(A, B, KK);
-                        uint32_t A2 = v2 + (COST_K - uhi) * 0x10001u;         // v - uhi + K
-                        uint32_t B2 = (ulo + COST_K) * 0x10001u - v2;         // ulo - v + K
-                        uint32_t c2 = __vimax3_u16x2(A2, B2, KK);
-                        bt[p] = __vminu2(c1, c2);                             // bt + K
+                        const uint32_t v2 = rc[(3 * p + 0) * planeStrideW];
+                        const uint32_t vlo2 = rc[(3 * p + 1) * planeStrideW];
+                        const uint32_t vhi2 = rc[(3 * p + 2) * planeStrideW];
+                        const uint32_t c1 = __vimax3_u16x2(uK[p] - vhi2, vlo2 + Ku[p], KK);      // max(u-vhi, vlo-u, 0) + K
+                        const uint32_t c2 = __vimax3_u16x2(v2 + KmUhi[p], UloK[p] - v2, KK);     // max(v-uhi, ulo-v, 0) + K
+                        bt[p] = __vminu2(c1, c2);
                     }
                     // (bt_g + K) + ((bt_t + K) >> 2) - (K + K/4)
-                    acc += bt[0] + ((bt[1] >> 2) & 0x3FFF3FFFu) - (COST_K + COST_K / 4) * 0x10001u;
+                    const uint32_t val = bt[0] + ((bt[1] >> 2) & 0x3FFF3FFFu) - KSUB;
+                    const int l = pi / NREG, m = pi - l * NREG;
+                    uint32_t *dst = pcol + 4 * (g.lpc * (m >> 2) + l) + (m & 3);
+                    if (c == 0) *dst = val; else *dst += val;
                 }
-                const int l = pi / g.nreg, m = pi % g.nreg;
-                pixbuf[(size_t)xx * Dw + 4 * (g.lpc * (m >> 2) + l) + (m & 3)] = acc;
             }
         }
         __syncthreads();
-        // ---- C: horizontal sum, ring, running vertical sum, store ------------------------------
-        const int slot = k % nslots;
-        const int yout = yb + k - 2 * r;
-        const bool emit = (k >= 2 * r);
-        const bool zero = a.zeroTail && r > 0 && yout >= g.H - r;
-        uint32_t *orow32 = reinterpret_cast<uint32_t *>(a.out) +
-                           (emit ? ((size_t)(yout - a.y0) * g.rowStride + (size_t)x0 * Dp) / 2 : 0);
+        // ---- C: sliding horizontal sum, ring, running vertical sum, store ----------------------
+        if (xg < a.NXG) {
+            const int slot = k % nslots;
+            const int yout = yb + k - 2 * r;
+            const bool emit = (k >= 2 * r);
+            const bool zero = a.zeroTail && r > 0 && yout >= g.H - r;
+            const int xbase = xg * XPT;
+            const uint32_t *pb = pixbuf + (size_t)xbase * Dw + w;            // column xbase-r of the tile (halo offset r)
+            uint32_t *rg = ring + ((size_t)slot * TX + xbase) * Dw + w;
+            uint32_t *orow32 = reinterpret_cast<uint32_t *>(a.out) +
+                               (emit ? ((size_t)(yout - a.y0) * g.rowStride + (size_t)(x0 + xbase) * g.Dp) / 2 + w : 0);
+            uint32_t hs = 0;
+            for (int i = 0; i <= 2 * r; i++) hs += pb[(size_t)i * Dw];
 #pragma unroll
-        for (int n = 0; n < COST_NIT; n++) {
-            int it = tid + n * COST_THREADS;
-            if (it < nitems) {
-                int x = it / Dw, w = it - x * Dw;
-                const uint32_t *pb = pixbuf + (size_t)x * Dw + w;
-                uint32_t hs = 0;
-                for (int i = 0; i <= 2 * r; i++) hs += pb[(size_t)i * Dw];
-                uint32_t *rg = ring + ((size_t)slot * TX + x) * Dw + w;
-                uint32_t old = *rg;
-                *rg = hs;
+            for (int n = 0; n < XPT; n++) {
+                if (n > 0) hs += pb[(size_t)(n + 2 * r) * Dw] - pb[(size_t)(n - 1) * Dw];
+                const uint32_t old = rg[(size_t)n * Dw];
+                rg[(size_t)n * Dw] = hs;
                 crun[n] = crun[n] + hs - old;
-                if (emit && x0 + x < g.W1) orow32[it] = zero ? 0u : crun[n];
+                if (emit && x0 + xbase + n < g.W1) orow32[(size_t)n * Dw] = zero ? 0u : crun[n];
             }
         }
         // the next iteration's first __syncthreads orders ring/pixbuf reuse
     }
 }
 
-size_t sgbm_cost_smem_bytes(const Geo &g, int TX)
+static size_t cost_smem_bytes(const Geo &g, int TX)
 {
     int r = g.r, TXH = TX + 2 * r, Dw = g.Dp / 2;
-    int NQ = TXH + g.D, NQh = (NQ + 1) / 2 + 1;
+    int NQh = (TXH + g.D) / 2 + 2;
     size_t b = (size_t)(2 * r + 1) * TX * Dw * 4 + (size_t)TXH * Dw * 4 + (size_t)g.cn * 6 * 2 * NQh * 4 +
                (size_t)g.cn * 6 * TXH;
     return (b + 15) & ~(size_t)15;
@@ -214,6 +222,20 @@ int sgbm_launch_prefilter(const Geo &g, const uint8_t *left, const uint8_t *righ
     return 0;
 }
 
+template <int NREG, int XPT>
+static int launch_cost_t(CostArgs &a, int threads, size_t smem, dim3 grid, int maxSmem, cudaStream_t st)
+{
+    static bool attrDone = false;
+    if (!attrDone) {
+        SGBM_CUDA_CHECK(cudaFuncSetAttribute(k_cost<NREG, XPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        attrDone = true;
+    }
+    k_cost<NREG, XPT><<<grid, threads, smem, st>>>(a);
+    sgbm_count_launch(1);
+    SGBM_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
 // Rows [y0, y0+nrows) of the cost volume with vertical clamp floor ylo, written at out (row y0 first).
 int sgbm_launch_cost(const Geo &g, const uint8_t *planes, uint16_t *out, int y0, int nrows, int ylo,
                      int zeroTail, cudaStream_t st)
@@ -224,20 +246,30 @@ int sgbm_launch_cost(const Geo &g, const uint8_t *planes, uint16_t *out, int y0,
         int dev = 0;
         SGBM_CUDA_CHECK(cudaGetDevice(&dev));
         SGBM_CUDA_CHECK(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        SGBM_CUDA_CHECK(cudaFuncSetAttribute(k_cost, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
     }
-    int TX = 32;
-    while (TX > 1 && (sgbm_cost_smem_bytes(g, TX) > (size_t)maxSmem / 2 || TX * (g.Dp / 2) > COST_THREADS * COST_NIT))
-        TX >>= 1;
-    if (sgbm_cost_smem_bytes(g, TX) > (size_t)maxSmem || TX * (g.Dp / 2) > COST_THREADS * COST_NIT)
+    const int Dw = g.Dp / 2;
+    if (Dw > 512) return sgbm_fail(-3, "cost kernel: numDisparities too large (Dp=%d)", g.Dp);
+    // threads = Dw * NXG (<= 512, >= 128 when possible); TX = NXG * XPT
+    int NXG = 1;
+    while (Dw * NXG * 2 <= 256) NXG *= 2;
+    int threads = ((Dw * NXG + 31) / 32) * 32;
+    int XPT = 16;
+    while (XPT > 4 && cost_smem_bytes(g, NXG * XPT) > (size_t)maxSmem / 2) XPT >>= 1;
+    while (NXG > 1 && cost_smem_bytes(g, NXG * XPT) > (size_t)maxSmem) { NXG >>= 1; threads = ((Dw * NXG + 31) / 32) * 32; }
+    if (cost_smem_bytes(g, NXG * XPT) > (size_t)maxSmem)
         return sgbm_fail(-3, "cost kernel: blockSize/numDisparities too large for shared memory (r=%d, Dp=%d)", g.r, g.Dp);
+    const int TX = NXG * XPT;
     CostArgs a;
-    a.g = g; a.planes = planes; a.out = out; a.y0 = y0; a.nrows = nrows; a.ylo = ylo; a.TX = TX;
+    a.g = g; a.planes = planes; a.out = out; a.y0 = y0; a.nrows = nrows; a.ylo = ylo; a.NXG = NXG;
     a.RB = nrows < 64 ? nrows : 64;
     a.zeroTail = zeroTail;
     dim3 grid((g.W1 + TX - 1) / TX, (nrows + a.RB - 1) / a.RB);
-    k_cost<<<grid, COST_THREADS, sgbm_cost_smem_bytes(g, TX), st>>>(a);
-    sgbm_count_launch(1);
-    SGBM_CUDA_CHECK(cudaGetLastError());
-    return 0;
+    const size_t smem = cost_smem_bytes(g, TX);
+#define COST_CASE(NR, XP) if (g.nreg == NR && XPT == XP) return launch_cost_t<NR, XP>(a, threads, smem, grid, maxSmem, st);
+    COST_CASE(4, 16) COST_CASE(4, 8) COST_CASE(4, 4)
+    COST_CASE(8, 16) COST_CASE(8, 8) COST_CASE(8, 4)
+    COST_CASE(12, 16) COST_CASE(12, 8) COST_CASE(12, 4)
+    COST_CASE(16, 16) COST_CASE(16, 8) COST_CASE(16, 4)
+#undef COST_CASE
+    return sgbm_fail(-3, "cost kernel: no instantiation for nreg=%d xpt=%d", g.nreg, XPT);
 }
