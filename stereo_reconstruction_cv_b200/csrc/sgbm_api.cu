@@ -174,8 +174,9 @@ static void ws_layout(const Geo &g, const sgbm_params &p, int numSMs, int keep, 
     L.med = take((size_t)g.W * g.H * 2);
     L.speck = take((size_t)g.W * g.H * 8);
     int maxStrips = g.W1 < numSMs ? g.W1 : numSMs;
-    L.haloA = take((size_t)maxStrips * 2 * (g.Dp + 8) * 2);
-    L.haloC = take((size_t)maxStrips * 2 * (g.Dp + 8) * 2);
+    const int maxR = 16;
+    L.haloA = take((size_t)maxStrips * 2 * maxR * (g.Dp + 8) * 2);
+    L.haloC = take((size_t)maxStrips * 2 * maxR * (g.Dp + 8) * 2);
     L.flags = take((size_t)2 * maxStrips * 4);
     L.sdbg = take(keep ? vol : 16);
     L.total = off;
@@ -316,6 +317,7 @@ static int compute_frame(sgbm_handle *h, const Geo &g, const WsLayout &L, const 
     a.haloA = (uint16_t *)(base + L.haloA); a.haloC = (uint16_t *)(base + L.haloC);
     a.flagA = (unsigned int *)(base + L.flags); a.flagC = a.flagA + (g.W1 < h->numSMs ? g.W1 : h->numSMs);
     a.ss = ss; a.ov = ov;
+    a.dbgNoSync = getenv("SGBM_DBG_NOSYNC") ? 1 : 0;
     a.sdbg = h->keep ? (uint16_t *)(base + L.sdbg) : nullptr;
     switch (p.mode) {
     case SGBM_MODE_SGBM:

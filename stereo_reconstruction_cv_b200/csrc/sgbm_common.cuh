@@ -142,14 +142,16 @@ struct VertArgs {
     uint16_t *sdbg;           // test hook: also store the final S of WTA rows here (or null)
     int16_t *raw;             // WTA output, dense H x W int16 (pre-filled with INV)
     unsigned int *d2key;      // WTA disp2 splat keys, dense H x W, pre-filled with 0xFFFFFFFF
-    int SW, nstrips;          // columns per strip, number of strips
+    int SW, nstrips;          // max columns per strip (slots), number of strips
+    int R;                    // rows per super-step between halo exchanges (NDIR = 3)
     int backward;             // 0: rows 0..H-1, 1: rows H-1..0
     int threeway;             // MODE_SGBM_3WAY rules (stripes via blockIdx.y, tie-break, uniqueness)
     int ss, ov;               // 3WAY stripe height and overlap
-    uint16_t *haloA;          // [nstrips][2][Dp + 8]  last column's (x-1)-path state of each strip
-    uint16_t *haloC;          // [nstrips][2][Dp + 8]  first column's (x+1)-path state of each strip
-    unsigned int *flagA;      // [nstrips] rows published
-    unsigned int *flagC;
+    uint16_t *haloA;          // [nstrips][2][R][Dp + 8]  (x-1)-path state of each strip's last R columns
+    uint16_t *haloC;          // [nstrips][2][R][Dp + 8]  (x+1)-path state of each strip's first R columns
+    unsigned int *flagA;      // [nstrips] super-steps published
+    unsigned int *flagC;      // unused
+    int dbgNoSync;            // experiment only: skip neighbour-strip waits (results invalid)
 };
 
 #define SGBM_CUDA_CHECK(call)                                                              \

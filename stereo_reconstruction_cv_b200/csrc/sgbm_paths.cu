@@ -10,6 +10,7 @@
 // Recurrence and saturation rules: SURVEY.md Appendix A.4; packed u16x2 DPX arithmetic
 // (VIMNMX3 / VIADDMNMX) as described in sgbm_common.cuh.
 #include "sgbm_common.cuh"
+#include <stdlib.h>
 
 // =================================================================================================
 // Horizontal paths
@@ -90,6 +91,15 @@ __device__ __forceinline__ void load_vec_cg(uint32_t (&v)[NREG], const uint16_t 
 }
 
 // NDIR = 3: vertical + both diagonals (MODE_SGBM / MODE_HH sweeps);  NDIR = 1: vertical only.
+//
+// Row blocking (NDIR = 3).  A diagonal path moves one column per row, so during R consecutive rows
+// a strip is only influenced by the R columns next to each of its borders.  Strips therefore
+// exchange state once per super-step of R rows: at its end every strip publishes the (x-1)-path
+// state of its last R columns and the (x+1)-path state of its first R columns; during the next
+// super-step the neighbour recomputes the incoming chains itself with R-1 "halo groups" per side
+// (one direction only, a shrinking triangle of (R-1)R/2 cells).  The release/acquire flag round
+// trip and the fence are paid once per R rows instead of every row.
+//
 // Register budget: ~5*NREG live packed registers + 3*NREG prefetch => cap the CTA size per NREG.
 template <int NREG> struct VertMaxThreads { static const int value = NREG >= 16 ? 384 : (NREG >= 12 ? 512 : (NREG >= 8 ? 640 : 1024)); };
 
@@ -99,15 +109,32 @@ __global__ void __launch_bounds__(VertMaxThreads<NREG>::value, 1) k_vertical(Ver
     extern __shared__ __align__(16) uint8_t smem[];
     const Geo &g = a.g;
     const int Dp = g.Dp, W1 = g.W1, lastLane = g.lanesUsed - 1;
-    const int SW = a.SW, strip = blockIdx.x;
-    const int xs = strip * SW;
-    const int ncols = min(SW, W1 - xs);
-    const int ngroups = blockDim.x / LPC;
-    const int grp = threadIdx.x / LPC, lg = threadIdx.x % LPC;
-    const bool act = grp < ncols;
-    const int c = act ? grp : ncols - 1;                 // inactive groups mirror the last column
-    const int x1 = xs + c;
+    const int R = (NDIR == 3) ? a.R : 1, HG = R - 1;
+    const int strip = blockIdx.x;
+    const int SWmax = a.SW;
+    int xs, xe;
+    if (NDIR == 3) {
+        xs = (int)((long long)strip * W1 / a.nstrips);
+        xe = (int)((long long)(strip + 1) * W1 / a.nstrips);
+    } else {
+        xs = strip * SWmax;
+        xe = min(xs + SWmax, W1);
+    }
+    const int SW = xe - xs;
+    const int gi = threadIdx.x / LPC, lg = threadIdx.x % LPC;
     const uint32_t P1p = (uint32_t)g.P1 * 0x10001u, P2mP1p = (uint32_t)(g.P2 - g.P1) * 0x10001u;
+
+    // ---- role of this lane group ---------------------------------------------------------------
+    bool own = false, haloL = false, haloR = false;
+    int hj = 0, xcol;
+    if (gi < HG) { haloL = strip > 0; hj = HG - 1 - gi; xcol = xs - 1 - hj; }
+    else if (gi < HG + SWmax) { own = (gi - HG) < SW; xcol = xs + (gi - HG); }
+    else if (gi < 2 * HG + SWmax) { haloR = strip < a.nstrips - 1; hj = gi - HG - SWmax; xcol = xe + hj; }
+    else xcol = xs;
+    if (xcol < 0 || xcol >= W1) { haloL = haloR = false; }
+    const bool anyRole = own || haloL || haloR;
+    const int slot = anyRole ? xcol - xs + R : R;        // shared-memory slot of this column
+    const int x1 = anyRole ? xcol : xs;                  // safe column for the loads of idle groups
 
     // ---- row program ----------------------------------------------------------------------------
     int yBegin, nRows, yStep, tOut;
@@ -125,24 +152,25 @@ __global__ void __launch_bounds__(VertMaxThreads<NREG>::value, 1) k_vertical(Ver
     }
 
     // ---- shared memory --------------------------------------------------------------------------
-    // exA/exC [2][SW+2][Dp] u16 : previous-row state of the (x-1)/(x+1) paths, slot s <-> column xs+s-1
-    // exm     [2][2][SW+2] u32  : their packed minima
-    // ssm     [ngroups][Dp] u16 : WTA scratch
+    // exA/exC [2][NS][Dp] u16 : previous-row state of the (x-1)/(x+1) paths, slot s <-> column xs-R+s
+    // exm     [2][2][NS] u32  : their packed minima          (NS = SWmax + 2R slots)
+    // ssm     [groups][Dp] u16: WTA scratch, one vector per lane group
+    const int NS = SWmax + 2 * R;
     uint16_t *exA = reinterpret_cast<uint16_t *>(smem);
-    uint16_t *exC = exA + (size_t)2 * (SW + 2) * Dp;
-    uint32_t *exm = reinterpret_cast<uint32_t *>(exC + (size_t)2 * (SW + 2) * Dp);
-    uint16_t *ssm = reinterpret_cast<uint16_t *>(exm + 2 * 2 * (SW + 2)) + (size_t)grp * Dp;
+    uint16_t *exC = exA + (size_t)2 * NS * Dp;
+    uint32_t *exm = reinterpret_cast<uint32_t *>(exC + (size_t)2 * NS * Dp);
+    uint16_t *ssm = reinterpret_cast<uint16_t *>(exm + 2 * 2 * NS) + (size_t)gi * Dp;   // private per lane group
     if (NDIR == 3) {
         uint32_t *z = reinterpret_cast<uint32_t *>(smem);
-        const int nz = (int)((2 * 2 * (size_t)(SW + 2) * Dp * 2 + 2 * 2 * (SW + 2) * 4) / 4);
+        const int nz = (int)((2 * 2 * (size_t)NS * Dp * 2 + 2 * 2 * NS * 4) / 4);
         for (int i = threadIdx.x; i < nz; i += blockDim.x) z[i] = 0;
         __syncthreads();
     }
-    const bool needLeft = (NDIR == 3) && act && c == 0 && strip > 0;                    // reads haloA[strip-1]
-    const bool needRight = (NDIR == 3) && act && c == ncols - 1 && strip < a.nstrips - 1;  // reads haloC[strip+1]
-    const bool pubA = needRight;     // the last column's (x-1)-path state feeds strip+1
-    const bool pubC = needLeft;      // the first column's (x+1)-path state feeds strip-1
-    const size_t haloStride = (size_t)Dp + 8;
+    const size_t haloStride = (size_t)Dp + 8;            // u16 elements per published column (vector + min)
+    const bool pubA = (NDIR == 3) && own && strip < a.nstrips - 1 && xcol >= xe - R;   // feeds strip+1
+    const bool pubC = (NDIR == 3) && own && strip > 0 && xcol < xs + R;                // feeds strip-1
+    const bool rcvL = (NDIR == 3) && gi < R && strip > 0;                              // copies column xs-R+gi
+    const bool rcvR = (NDIR == 3) && gi >= R && gi < 2 * R && strip < a.nstrips - 1;   // copies column xe+(gi-R)
 
     uint32_t LB[NREG], mB = 0;
 #pragma unroll
@@ -156,13 +184,40 @@ __global__ void __launch_bounds__(VertMaxThreads<NREG>::value, 1) k_vertical(Ver
                              : a.C + (size_t)y * g.rowStride + (size_t)x1 * Dp;
     };
     load_vec_nc<NREG, LPC>(Cn, crow_ptr(0), lg);
-    if (0 >= tOut) {
+    if (0 >= tOut && own) {
         load_vec<NREG, LPC>(An, a.inA + (size_t)yBegin * g.rowStride + (size_t)x1 * Dp, lg);
         if (hasB) load_vec<NREG, LPC>(Bn, a.inB + (size_t)yBegin * g.rowStride + (size_t)x1 * Dp, lg);
     }
 
+    int k = 0, sidx = 0;                                  // row inside the super-step, super-step index
     for (int t = 0; t < nRows; t++) {
         const int y = yBegin + t * yStep;
+        const int pp = (t + 1) & 1, pc = t & 1;          // previous / current row parity
+        // ---- super-step start: receive the neighbours' published columns ------------------------
+        if (NDIR == 3 && k == 0 && t > 0) {
+            if (!a.dbgNoSync) {
+                if (rcvL && lg == 0) while (ld_acquire(a.flagA + strip - 1) < (unsigned)sidx) { }
+                if (rcvR && lg == 0) while (ld_acquire(a.flagA + strip + 1) < (unsigned)sidx) { }
+            }
+            __syncwarp();
+            if (rcvL || rcvR) {
+                const int i = rcvL ? gi : gi - R;
+                const uint16_t *h = (rcvL ? a.haloA + ((size_t)(strip - 1) * 2 + ((sidx - 1) & 1)) * R * haloStride
+                                          : a.haloC + ((size_t)(strip + 1) * 2 + ((sidx - 1) & 1)) * R * haloStride) +
+                                    (size_t)i * haloStride;
+                uint32_t v[NREG];
+                load_vec_cg<NREG, LPC>(v, h, lg);
+                const int sl = rcvL ? i : R + SW + i;
+                store_vec<NREG, LPC>(v, (rcvL ? exA : exC) + ((size_t)pp * NS + sl) * Dp, lg);
+                if (lg == 0) exm[((rcvL ? 0 : 1) * 2 + pp) * NS + sl] = __ldcg(reinterpret_cast<const unsigned int *>(h + Dp));
+            }
+            __syncthreads();
+        }
+        const bool haloAct = (haloL || haloR) && k <= HG - 1 - hj;     // chain still needed this row
+        const bool doA = own || (haloL && haloAct), doC = own || (haloR && haloAct);
+        const int kn = (k + 1 == R) ? 0 : k + 1;
+        const bool nextAct = own || ((haloL || haloR) && kn <= HG - 1 - hj);
+
         uint32_t Cc[NREG], S[NREG];
 #pragma unroll
         for (int j = 0; j < NREG; j++) Cc[j] = Cn[j];
@@ -171,90 +226,76 @@ __global__ void __launch_bounds__(VertMaxThreads<NREG>::value, 1) k_vertical(Ver
 #pragma unroll
             for (int j = 0; j < NREG; j++) S[j] = hasB ? paddmin(An[j], Bn[j], SGBM_MAX_S) : An[j];
         }
-        if (t + 1 < nRows) {                              // prefetch the next row of this column
+        if (t + 1 < nRows && nextAct) {                   // prefetch the next row of this column
             load_vec_nc<NREG, LPC>(Cn, crow_ptr(t + 1), lg);
-            if (t + 1 >= tOut) {
+            if (t + 1 >= tOut && own) {
                 const size_t off = (size_t)(y + yStep) * g.rowStride + (size_t)x1 * Dp;
                 load_vec<NREG, LPC>(An, a.inA + off, lg);
                 if (hasB) load_vec<NREG, LPC>(Bn, a.inB + off, lg);
             }
         }
         uint32_t Ln[NREG];
+        const bool warpOwn = __any_sync(0xFFFFFFFFu, own);
         // ---- vertical path: predecessor (x, previous row), state in registers -------------------
-        mB = path_step<NREG, LPC>(Ln, LB, mB, Cc, P1p, P2mP1p, lg, lastLane);
+        if (warpOwn) {
+            mB = path_step<NREG, LPC>(Ln, LB, mB, Cc, P1p, P2mP1p, lg, lastLane);
 #pragma unroll
-        for (int j = 0; j < NREG; j++) LB[j] = Ln[j];
-        if (outRow) {
+            for (int j = 0; j < NREG; j++) LB[j] = Ln[j];
+            if (outRow) {
 #pragma unroll
-            for (int j = 0; j < NREG; j++) S[j] = paddmin(S[j], Ln[j], SGBM_MAX_S);
+                for (int j = 0; j < NREG; j++) S[j] = paddmin(S[j], Ln[j], SGBM_MAX_S);
+            }
         }
         if (NDIR == 3) {
-            const int pp = (t + 1) & 1, pc = t & 1;      // previous / current parity
-            if (t > 0) {                                  // wait for the neighbour strips' row t-1
-                if (needLeft && lg == 0) while (ld_acquire(a.flagA + strip - 1) < (unsigned)t) { }
-                if (needRight && lg == 0) while (ld_acquire(a.flagC + strip + 1) < (unsigned)t) { }
-                __syncwarp();
-            }
+            const bool lastOfStep = (k == R - 1) && (t + 1 < nRows);   // publish after this row
             uint32_t Lp[NREG], mp;
             // ---- path with predecessor (x-1, previous row) --------------------------------------
-            if (needLeft && t > 0) {
-                const uint16_t *h = a.haloA + ((size_t)(strip - 1) * 2 + pp) * haloStride;
-                load_vec_cg<NREG, LPC>(Lp, h, lg);
-                mp = __ldcg(reinterpret_cast<const unsigned int *>(h + Dp));
-            } else {
-                load_vec<NREG, LPC>(Lp, exA + ((size_t)pp * (SW + 2) + c) * Dp, lg);
-                mp = exm[(0 * 2 + pp) * (SW + 2) + c];
-            }
-            uint32_t mA = path_step<NREG, LPC>(Ln, Lp, mp, Cc, P1p, P2mP1p, lg, lastLane);
-            if (act) {
-                store_vec<NREG, LPC>(Ln, exA + ((size_t)pc * (SW + 2) + c + 1) * Dp, lg);
-                if (lg == 0) exm[(0 * 2 + pc) * (SW + 2) + c + 1] = mA;
-                if (pubA) {
-                    uint16_t *h = a.haloA + ((size_t)strip * 2 + pc) * haloStride;
-                    store_vec<NREG, LPC>(Ln, h, lg);
-                    if (lg == 0) *reinterpret_cast<unsigned int *>(h + Dp) = mA;
+            if (__any_sync(0xFFFFFFFFu, doA)) {
+                load_vec<NREG, LPC>(Lp, exA + ((size_t)pp * NS + slot - 1) * Dp, lg);
+                mp = exm[(0 * 2 + pp) * NS + slot - 1];
+                const uint32_t mA = path_step<NREG, LPC>(Ln, Lp, mp, Cc, P1p, P2mP1p, lg, lastLane);
+                if (doA) {
+                    store_vec<NREG, LPC>(Ln, exA + ((size_t)pc * NS + slot) * Dp, lg);
+                    if (lg == 0) exm[(0 * 2 + pc) * NS + slot] = mA;
+                    if (pubA && lastOfStep) {
+                        uint16_t *h = a.haloA + (((size_t)strip * 2 + (sidx & 1)) * R + (xcol - (xe - R))) * haloStride;
+                        store_vec<NREG, LPC>(Ln, h, lg);
+                        if (lg == 0) *reinterpret_cast<unsigned int *>(h + Dp) = mA;
+                    }
                 }
-            }
-            if (outRow) {
+                if (outRow && own) {
 #pragma unroll
-                for (int j = 0; j < NREG; j++) S[j] = paddmin(S[j], Ln[j], SGBM_MAX_S);
+                    for (int j = 0; j < NREG; j++) S[j] = paddmin(S[j], Ln[j], SGBM_MAX_S);
+                }
             }
             // ---- path with predecessor (x+1, previous row) --------------------------------------
-            if (needRight && t > 0) {
-                const uint16_t *h = a.haloC + ((size_t)(strip + 1) * 2 + pp) * haloStride;
-                load_vec_cg<NREG, LPC>(Lp, h, lg);
-                mp = __ldcg(reinterpret_cast<const unsigned int *>(h + Dp));
-            } else {
-                load_vec<NREG, LPC>(Lp, exC + ((size_t)pp * (SW + 2) + c + 2) * Dp, lg);
-                mp = exm[(1 * 2 + pp) * (SW + 2) + c + 2];
-            }
-            uint32_t mC = path_step<NREG, LPC>(Ln, Lp, mp, Cc, P1p, P2mP1p, lg, lastLane);
-            if (act) {
-                store_vec<NREG, LPC>(Ln, exC + ((size_t)pc * (SW + 2) + c + 1) * Dp, lg);
-                if (lg == 0) exm[(1 * 2 + pc) * (SW + 2) + c + 1] = mC;
-                if (pubC) {
-                    uint16_t *h = a.haloC + ((size_t)strip * 2 + pc) * haloStride;
-                    store_vec<NREG, LPC>(Ln, h, lg);
-                    if (lg == 0) *reinterpret_cast<unsigned int *>(h + Dp) = mC;
+            if (__any_sync(0xFFFFFFFFu, doC)) {
+                load_vec<NREG, LPC>(Lp, exC + ((size_t)pp * NS + slot + 1) * Dp, lg);
+                mp = exm[(1 * 2 + pp) * NS + slot + 1];
+                const uint32_t mC = path_step<NREG, LPC>(Ln, Lp, mp, Cc, P1p, P2mP1p, lg, lastLane);
+                if (doC) {
+                    store_vec<NREG, LPC>(Ln, exC + ((size_t)pc * NS + slot) * Dp, lg);
+                    if (lg == 0) exm[(1 * 2 + pc) * NS + slot] = mC;
+                    if (pubC && lastOfStep) {
+                        uint16_t *h = a.haloC + (((size_t)strip * 2 + (sidx & 1)) * R + (xcol - xs)) * haloStride;
+                        store_vec<NREG, LPC>(Ln, h, lg);
+                        if (lg == 0) *reinterpret_cast<unsigned int *>(h + Dp) = mC;
+                    }
+                }
+                if (outRow && own) {
+#pragma unroll
+                    for (int j = 0; j < NREG; j++) S[j] = paddmin(S[j], Ln[j], SGBM_MAX_S);
                 }
             }
-            if (outRow) {
-#pragma unroll
-                for (int j = 0; j < NREG; j++) S[j] = paddmin(S[j], Ln[j], SGBM_MAX_S);
-            }
-            // ---- publish row t to the neighbour strips ------------------------------------------
-            if (pubA || pubC) __threadfence();
-            __syncwarp();
-            if (pubA && lg == 0) st_release(a.flagA + strip, (unsigned)(t + 1));
-            if (pubC && lg == 0) st_release(a.flagC + strip, (unsigned)(t + 1));
+            if (lastOfStep && (pubA || pubC)) __threadfence();
         }
 
-        if (outRow) {
+        if (outRow && warpOwn) {
             if (a.sout) {
-                if (act) store_vec<NREG, LPC>(S, a.sout + (size_t)y * g.rowStride + (size_t)x1 * Dp, lg);
+                if (own) store_vec<NREG, LPC>(S, a.sout + (size_t)y * g.rowStride + (size_t)x1 * Dp, lg);
             } else {
                 // ---- winner-take-all (A.5 / A.6) --------------------------------------------------
-                if (a.sdbg && act) store_vec<NREG, LPC>(S, a.sdbg + (size_t)y * g.rowStride + (size_t)x1 * Dp, lg);
+                if (a.sdbg && own) store_vec<NREG, LPC>(S, a.sdbg + (size_t)y * g.rowStride + (size_t)x1 * Dp, lg);
                 uint32_t tm = local_min<NREG>(S);
                 if (lg > lastLane) tm = SGBM_INF2;
                 const uint32_t mS2 = group_min<LPC>(tm);
@@ -333,7 +374,7 @@ __global__ void __launch_bounds__(VertMaxThreads<NREG>::value, 1) k_vertical(Ver
                     const int m2 = (int)(group_min<LPC>(t2) & 0xFFFFu);
                     reject = m2 < T;
                 }
-                if (lg == 0 && act) {
+                if (lg == 0 && own) {
                     const int x = x1 + g.minX1;
                     int out = g.INV;
                     if (!reject) {
@@ -351,16 +392,21 @@ __global__ void __launch_bounds__(VertMaxThreads<NREG>::value, 1) k_vertical(Ver
                 }
             }
         }
-        if (NDIR == 3) __syncthreads();
+        if (NDIR == 3) {
+            __syncthreads();
+            if (k == R - 1 && t + 1 < nRows && threadIdx.x == 0) st_release(a.flagA + strip, (unsigned)(sidx + 1));
+            if (++k == R) { k = 0; sidx++; }
+        }
     }
 }
 
 // =================================================================================================
 // Host side: template dispatch and launch configuration
 // =================================================================================================
-size_t sgbm_vertical_smem_bytes(const Geo &g, int SW, int threads)
+static size_t vertical_smem_bytes(const Geo &g, int SWmax, int R, int threads)
 {
-    size_t ex = (size_t)2 * 2 * (SW + 2) * g.Dp * 2 + (size_t)2 * 2 * (SW + 2) * 4;
+    const int NS = SWmax + 2 * R;
+    size_t ex = (size_t)2 * 2 * NS * g.Dp * 2 + (size_t)2 * 2 * NS * 4;
     size_t ss = (size_t)(threads / g.lpc) * g.Dp * 2;
     return (ex + ss + 15) & ~(size_t)15;
 }
@@ -397,29 +443,40 @@ static int launch_vertical_t(VertArgs &a, int numSMs, cudaStream_t st)
         // independent columns: ordinary grid, 128 threads per CTA
         const int threads = 128;
         a.SW = threads / LPC;
+        a.R = 1;
         a.nstrips = (g.W1 + a.SW - 1) / a.SW;
-        const size_t smem = sgbm_vertical_smem_bytes(g, a.SW, threads);
+        const size_t smem = vertical_smem_bytes(g, a.SW, 1, threads);
         dim3 grid(a.nstrips, a.threeway ? 4 : 1);
         kern<<<grid, threads, smem, st>>>(a);
         sgbm_count_launch(1);
         SGBM_CUDA_CHECK(cudaGetLastError());
         return 0;
     }
-    // NDIR == 3: all strips must be co-resident (neighbour flags) -> cooperative launch, <= 1 CTA per SM
-    int SW = (g.W1 + numSMs - 1) / numSMs;
-    if (SW < 1) SW = 1;
-    if (SW * LPC > VertMaxThreads<NREG>::value)
-        return sgbm_fail(-3, "image too wide for the vertical sweep (W1=%d, lanes/column=%d, SMs=%d)", g.W1, LPC, numSMs);
-    int threads = ((SW * LPC + 31) / 32) * 32;
-    size_t smem = sgbm_vertical_smem_bytes(g, SW, threads);
-    if (smem > (size_t)maxSmem) return sgbm_fail(-3, "vertical sweep needs %zu bytes of shared memory (max %d)", smem, maxSmem);
-    a.SW = SW;
-    a.nstrips = (g.W1 + SW - 1) / SW;
+    // NDIR == 3: all strips must be co-resident (neighbour flags) -> cooperative launch, <= 1 CTA per SM.
+    // R rows per super-step (env SGBM_VR overrides); every strip must own >= R columns.
+    const int maxThreads = VertMaxThreads<NREG>::value;
+    int R = 9;
+    if (const char *e = getenv("SGBM_VR")) R = atoi(e) > 0 ? atoi(e) : 1;
+    if (R > 16) R = 16;
+    int nstrips = numSMs, SWmax = 1;
+    for (;; R--) {
+        if (R < 1) return sgbm_fail(-3, "image too wide for the vertical sweep (W1=%d, lanes/column=%d, SMs=%d)", g.W1, LPC, numSMs);
+        nstrips = numSMs;
+        const int minCols = R > 2 ? R : 2;                // every strip owns >= R (and >= 2) columns
+        if (nstrips > g.W1 / minCols) nstrips = g.W1 / minCols;
+        if (nstrips < 1) nstrips = 1;
+        if (nstrips == 1 && R > 1) continue;              // a single strip has no halos
+        SWmax = (g.W1 + nstrips - 1) / nstrips;
+        const int thr = (((SWmax + 2 * (R - 1)) * LPC + 31) / 32) * 32;
+        if (thr <= maxThreads && vertical_smem_bytes(g, SWmax, R, thr) <= (size_t)maxSmem) break;
+    }
+    const int threads = (((SWmax + 2 * (R - 1)) * LPC + 31) / 32) * 32;
+    const size_t smem = vertical_smem_bytes(g, SWmax, R, threads);
+    a.SW = SWmax; a.R = R; a.nstrips = nstrips;
     int occ = 0;
     SGBM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
     if (occ * numSMs < a.nstrips) return sgbm_fail(-3, "vertical sweep cannot be made co-resident (%d strips, %d x %d slots)", a.nstrips, occ, numSMs);
     SGBM_CUDA_CHECK(cudaMemsetAsync(a.flagA, 0, sizeof(unsigned int) * a.nstrips, st));
-    SGBM_CUDA_CHECK(cudaMemsetAsync(a.flagC, 0, sizeof(unsigned int) * a.nstrips, st));
     void *args[] = {&a};
     SGBM_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)kern, dim3(a.nstrips), dim3(threads), args, smem, st));
     sgbm_count_launch(1);
