@@ -1,5 +1,10 @@
 cd /root/repo
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -15
-for r in 1 5 9 13; do SGBM_VR=$r python bench.py --workload cfg3 --steps 3 --warmup 3 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('R=$r', d['value'], d['ms_per_step'], d['stages_ms'])"; done
-SGBM_VR=9 python bench.py --workload cfg2 --steps 3 --warmup 3 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('cfg2 R=9', d['value'], d['ms_per_step'], d['stages_ms'])"
-SGBM_VR=9 python bench.py --workload cfg4 --steps 3 --warmup 3 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('cfg4 R=9', d['value'], d['ms_per_step'], d['stages_ms'])"
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -15
+run() { timeout 300 python bench.py --workload $1 --steps 3 --warmup 3 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$2', d['value'], d['ms_per_step'], d['stages_ms'])"; }
+run cfg3 "cfg3 default"
+SGBM_VR=7 run cfg3 "cfg3 R7"
+SGBM_VR=5 run cfg3 "cfg3 R5"
+SGBM_VR=5 SGBM_NSTG=4 run cfg3 "cfg3 R5 nstg4"
+run cfg5 cfg5
+run cfg4 cfg4
+run cfg2 cfg2

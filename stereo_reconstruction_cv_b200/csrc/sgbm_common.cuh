@@ -89,6 +89,43 @@ __device__ __forceinline__ void store_vec(const uint32_t (&v)[NREG], uint16_t *c
         p[LPC * k] = make_uint4(v[4 * k + 0], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
 }
 
+
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers ------------------------------
+// One elected lane arms an mbarrier with the byte count and issues global->shared bulk copies; the
+// consumers wait on the barrier's phase parity.  Waits are bounded: a protocol error traps instead
+// of hanging the GPU.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t n = 0;
+    while (!mbar_try_wait(bar, parity)) { if (++n > (1u << 26)) __trap(); }
+}
+
 // One step of the SGM recurrence (A.4) for one column, distributed over a group of LPC lanes:
 //   Ln(d) = C(d) + min(Lp(d), Lp(d-1)+P1, Lp(d+1)+P1, m+P2) - m,   m = min_k Lp(k)
 // Lp / mp : predecessor's path costs and their (packed, broadcast) minimum.
@@ -144,6 +181,8 @@ struct VertArgs {
     unsigned int *d2key;      // WTA disp2 splat keys, dense H x W, pre-filled with 0xFFFFFFFF
     int SW, nstrips;          // max columns per strip (slots), number of strips
     int R;                    // rows per super-step between halo exchanges (NDIR = 3)
+    int nslots, nstg, nAB;    // exchange slots, TMA staging depth, staged input volumes (1 or 2)
+    unsigned int ssmOff, stgCOff, stgABOff, barOff;   // shared-memory layout (bytes)
     int backward;             // 0: rows 0..H-1, 1: rows H-1..0
     int threeway;             // MODE_SGBM_3WAY rules (stripes via blockIdx.y, tie-break, uniqueness)
     int ss, ov;               // 3WAY stripe height and overlap

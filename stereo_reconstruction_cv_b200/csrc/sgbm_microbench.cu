@@ -21,6 +21,9 @@ __global__ void __launch_bounds__(256) k_microbench(uint32_t *out, uint32_t a, u
             else if (WHICH == 3) x[i] = __byte_perm(x[i], a, 0x5432);
             else if (WHICH == 4) x[i] = __shfl_xor_sync(0xFFFFFFFFu, x[i], 1);
             else if (WHICH == 5) x[i] = __vminu2(x[i], a);
+            else if (WHICH == 7) x[i] = __funnelshift_r(x[i], a, 16);
+            else if (WHICH == 8) x[i] = (x[i] >> 16) | (a << 16);
+            else if (WHICH == 9) x[i] = __vmaxu2(x[i], a) ^ b;
             else {   // 6: the path-step mix per packed register: PRMT, VIMNMX3, VIADDMNMX, IADD3, VIADDMNMX(S), VIMNMX
                 uint32_t s = __byte_perm(x[i], a, 0x5432);
                 uint32_t m3 = __vimin3_u16x2(s, x[(i + 1) % MB_CHAINS], b);
@@ -77,6 +80,9 @@ int sgbm_run_microbench(int which, double *out)
     case 4: return run_one<4>(1, out);
     case 5: return run_one<5>(1, out);
     case 6: return run_one<6>(6, out);
+    case 7: return run_one<7>(1, out);
+    case 8: return run_one<8>(1, out);
+    case 9: return run_one<9>(2, out);
     }
     return sgbm_fail(-1, "unknown microbenchmark %d", which);
 }

@@ -16,51 +16,80 @@
 // Horizontal paths
 // =================================================================================================
 #define HZ_THREADS 128
-#define HZ_PF 4                      // prefetch depth (columns in flight per lane group)
+#define HZ_K 4                       // columns per staging chunk
+#define HZ_NS 3                      // chunks in flight per warp
 
+// One lane group per image row and direction.  The cost rows are streamed through a per-warp ring
+// of HZ_NS shared-memory stages filled by TMA bulk copies (one contiguous K-column segment per
+// row), so HBM latency is covered by data in flight instead of registers.
 template <int NREG, int LPC>
 __global__ void __launch_bounds__(HZ_THREADS) k_horizontal(Geo g, const uint16_t *__restrict__ C,
                                                            uint16_t *__restrict__ LhA,
                                                            uint16_t *__restrict__ LhB, int y0, int nrows)
 {
-    const int gpb = HZ_THREADS / LPC;
-    const int grp = threadIdx.x / LPC, lg = threadIdx.x % LPC;
-    int row = y0 + blockIdx.x * gpb + grp;
-    const bool act = row < y0 + nrows;
-    if (!act) row = y0 + nrows - 1;                       // keep the warp convergent, no stores
-    const int dir = blockIdx.y;                           // 0: predecessor (-1,0), 1: predecessor (+1,0)
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int GPW = 32 / LPC;                         // lane groups (rows) per warp
+    constexpr int NW = HZ_THREADS / 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane / LPC, lg = lane % LPC;
     const int W1 = g.W1, Dp = g.Dp, lastLane = g.lanesUsed - 1;
-    const uint16_t *crow = C + (size_t)row * g.rowStride;
+    const int rowBase = y0 + (blockIdx.x * NW + warp) * GPW;
+    const int rowEnd = y0 + nrows;
+    if (rowBase >= rowEnd) return;                        // whole warp idle (warp-uniform)
+    int row = rowBase + grp;
+    const bool act = row < rowEnd;
+    if (!act) row = rowEnd - 1;                           // keep the warp convergent, no stores
+    const int dir = blockIdx.y;                           // 0: predecessor (-1,0), 1: predecessor (+1,0)
     uint16_t *orow = (dir ? LhB : LhA) + (size_t)row * g.rowStride;
     const uint32_t P1p = (uint32_t)g.P1 * 0x10001u, P2mP1p = (uint32_t)(g.P2 - g.P1) * 0x10001u;
+
+    const size_t stageElems = (size_t)GPW * HZ_K * Dp;
+    uint16_t *wbuf = reinterpret_cast<uint16_t *>(smem) + (size_t)warp * HZ_NS * stageElems;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)NW * HZ_NS * stageElems * 2) + warp * HZ_NS;
+    if (lane == 0) {
+        for (int i = 0; i < HZ_NS; i++) mbar_init(&bars[i], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    const int nchunks = (W1 + HZ_K - 1) / HZ_K;
+    auto fill = [&](int ci) {                             // lane 0: chunk ci -> stage ci % HZ_NS
+        const int st = ci % HZ_NS;
+        const int s0 = ci * HZ_K, kc = min(HZ_K, W1 - s0);
+        const int xlo = dir ? (W1 - s0 - kc) : s0;        // first (lowest) column of the chunk
+        const uint32_t bytes = (uint32_t)kc * Dp * 2;
+        mbar_expect_tx(&bars[st], bytes * GPW);
+        for (int q = 0; q < GPW; q++) {
+            const int r = min(rowBase + q, rowEnd - 1);
+            bulk_g2s(wbuf + st * stageElems + (size_t)q * HZ_K * Dp, C + (size_t)r * g.rowStride + (size_t)xlo * Dp,
+                     bytes, &bars[st]);
+        }
+    };
+    if (lane == 0)
+        for (int ci = 0; ci < HZ_NS && ci < nchunks; ci++) fill(ci);
 
     uint32_t L[NREG], m = 0;
 #pragma unroll
     for (int j = 0; j < NREG; j++) L[j] = 0;              // "predecessor outside" == L = 0, m = 0 (A.4)
-    uint32_t cb[HZ_PF][NREG];
+    for (int ci = 0; ci < nchunks; ci++) {
+        const int st = ci % HZ_NS;
+        mbar_wait(&bars[st], (uint32_t)(ci / HZ_NS) & 1u);
+        const int s0 = ci * HZ_K, kc = min(HZ_K, W1 - s0);
+        const uint16_t *sb = wbuf + st * stageElems + (size_t)grp * HZ_K * Dp;
 #pragma unroll
-    for (int i = 0; i < HZ_PF; i++) {
-        int s = i < W1 ? i : W1 - 1;
-        load_vec_nc<NREG, LPC>(cb[i], crow + (size_t)(dir ? W1 - 1 - s : s) * Dp, lg);
-    }
-    for (int s0 = 0; s0 < W1; s0 += HZ_PF) {
-#pragma unroll
-        for (int i = 0; i < HZ_PF; i++) {
-            const int s = s0 + i;
-            if (s < W1) {
+        for (int i = 0; i < HZ_K; i++) {
+            if (i < kc) {
+                const int s = s0 + i;
+                const int x = dir ? W1 - 1 - s : s;
                 uint32_t Cc[NREG], Ln[NREG];
-#pragma unroll
-                for (int j = 0; j < NREG; j++) Cc[j] = cb[i][j];
-                if (s + HZ_PF < W1) {
-                    int sn = s + HZ_PF;
-                    load_vec_nc<NREG, LPC>(cb[i], crow + (size_t)(dir ? W1 - 1 - sn : sn) * Dp, lg);
-                }
+                load_vec<NREG, LPC>(Cc, sb + (size_t)(dir ? kc - 1 - i : i) * Dp, lg);
                 m = path_step<NREG, LPC>(Ln, L, m, Cc, P1p, P2mP1p, lg, lastLane);
 #pragma unroll
                 for (int j = 0; j < NREG; j++) L[j] = Ln[j];
-                if (act) store_vec<NREG, LPC>(Ln, orow + (size_t)(dir ? W1 - 1 - s : s) * Dp, lg);
+                if (act) store_vec<NREG, LPC>(Ln, orow + (size_t)x * Dp, lg);
             }
         }
+        __syncwarp();
+        if (lane == 0 && ci + HZ_NS < nchunks) fill(ci + HZ_NS);
     }
 }
 
@@ -124,17 +153,15 @@ __global__ void __launch_bounds__(VertMaxThreads<NREG>::value, 1) k_vertical(Ver
     const int gi = threadIdx.x / LPC, lg = threadIdx.x % LPC;
     const uint32_t P1p = (uint32_t)g.P1 * 0x10001u, P2mP1p = (uint32_t)(g.P2 - g.P1) * 0x10001u;
 
-    // ---- role of this lane group ---------------------------------------------------------------
-    bool own = false, haloL = false, haloR = false;
-    int hj = 0, xcol;
-    if (gi < HG) { haloL = strip > 0; hj = HG - 1 - gi; xcol = xs - 1 - hj; }
-    else if (gi < HG + SWmax) { own = (gi - HG) < SW; xcol = xs + (gi - HG); }
-    else if (gi < 2 * HG + SWmax) { haloR = strip < a.nstrips - 1; hj = gi - HG - SWmax; xcol = xe + hj; }
-    else xcol = xs;
-    if (xcol < 0 || xcol >= W1) { haloL = haloR = false; }
-    const bool anyRole = own || haloL || haloR;
-    const int slot = anyRole ? xcol - xs + R : R;        // shared-memory slot of this column
-    const int x1 = anyRole ? xcol : xs;                  // safe column for the loads of idle groups
+    // ---- role of this lane group: group gi <-> column xs - HG + gi (contiguous) --------------------
+    const int xcol = xs - HG + gi;
+    const bool inImg = xcol >= 0 && xcol < W1;
+    const bool own = inImg && gi >= HG && gi < HG + SW;
+    const bool haloL = (NDIR == 3) && inImg && gi < HG && strip > 0;
+    const bool haloR = (NDIR == 3) && inImg && gi >= HG + SW && gi < 2 * HG + SW && strip < a.nstrips - 1;
+    const int hj = haloL ? HG - 1 - gi : gi - HG - SW;   // distance-1 of a halo column from the strip
+    const int slot = gi + 1;                             // slot 0 <-> column xs - R
+    const int x1 = inImg ? xcol : min(max(xcol, 0), W1 - 1);
 
     // ---- row program ----------------------------------------------------------------------------
     int yBegin, nRows, yStep, tOut;
@@ -151,19 +178,32 @@ __global__ void __launch_bounds__(VertMaxThreads<NREG>::value, 1) k_vertical(Ver
         yBegin = a.backward ? g.H - 1 : 0; nRows = g.H; yStep = a.backward ? -1 : 1; tOut = 0;
     }
 
-    // ---- shared memory --------------------------------------------------------------------------
+    // ---- shared memory (layout computed on the host, see vertical_layout) ------------------------
     // exA/exC [2][NS][Dp] u16 : previous-row state of the (x-1)/(x+1) paths, slot s <-> column xs-R+s
-    // exm     [2][2][NS] u32  : their packed minima          (NS = SWmax + 2R slots)
-    // ssm     [groups][Dp] u16: WTA scratch, one vector per lane group
-    const int NS = SWmax + 2 * R;
+    // exm     [2][2][NS] u32  : their packed minima
+    // ssm     [own warps][GPW][Dp] u16 : WTA scratch, one vector per lane group
+    // stgC    [warps][nstg][GPW][Dp]      : TMA-staged cost rows of the warp's columns
+    // stgAB   [own warps][nstg][2][GPW][Dp] : TMA-staged input volumes (L_h / S_fwd)
+    constexpr int GPW = 32 / LPC;
+    const int NS = a.nslots;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, grpw = lane / LPC;
+    const int nstg = a.nstg, ngroups = blockDim.x / LPC;
     uint16_t *exA = reinterpret_cast<uint16_t *>(smem);
     uint16_t *exC = exA + (size_t)2 * NS * Dp;
     uint32_t *exm = reinterpret_cast<uint32_t *>(exC + (size_t)2 * NS * Dp);
-    uint16_t *ssm = reinterpret_cast<uint16_t *>(exm + 2 * 2 * NS) + (size_t)gi * Dp;   // private per lane group
+    uint16_t *ssm = reinterpret_cast<uint16_t *>(smem + a.ssmOff) + (size_t)gi * Dp;
+    uint16_t *stgC = reinterpret_cast<uint16_t *>(smem + a.stgCOff);       // [nstg][ngroups][Dp]
+    uint16_t *stgAB = reinterpret_cast<uint16_t *>(smem + a.stgABOff);     // [nstg][nAB][SWmax][Dp]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + a.barOff);
+    (void)warp; (void)grpw; (void)ngroups;
     if (NDIR == 3) {
         uint32_t *z = reinterpret_cast<uint32_t *>(smem);
         const int nz = (int)((2 * 2 * (size_t)NS * Dp * 2 + 2 * 2 * NS * 4) / 4);
         for (int i = threadIdx.x; i < nz; i += blockDim.x) z[i] = 0;
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < nstg; i++) mbar_init(&bars[i], 1);
+            mbar_fence_init();
+        }
         __syncthreads();
     }
     const size_t haloStride = (size_t)Dp + 8;            // u16 elements per published column (vector + min)
@@ -177,16 +217,39 @@ __global__ void __launch_bounds__(VertMaxThreads<NREG>::value, 1) k_vertical(Ver
     for (int j = 0; j < NREG; j++) LB[j] = 0;
 
     const bool hasB = a.inB != nullptr;
-    uint32_t Cn[NREG], An[NREG], Bn[NREG];               // prefetched next-row operands
+    // NDIR = 3: the strip's columns (own + halo) are contiguous in memory, so one thread stages a
+    // whole row with one TMA bulk copy per volume into a ring of nstg shared-memory stages.
+    const int scol0 = xs - HG;                            // column of group 0
+    const int clo = max(scol0, 0), chi = min(scol0 + ngroups, W1);
+    auto fill = [&](int t) {                              // thread 0: stage row t of the row program
+        const int sg = t % nstg;
+        const int y = yBegin + t * yStep;
+        const uint32_t bytesC = (uint32_t)(chi - clo) * Dp * 2, bytesAB = (uint32_t)SW * Dp * 2;
+        mbar_expect_tx(&bars[sg], bytesC + bytesAB * (hasB ? 2u : 1u));
+        bulk_g2s(stgC + ((size_t)sg * ngroups + (clo - scol0)) * Dp, a.C + (size_t)y * g.rowStride + (size_t)clo * Dp, bytesC, &bars[sg]);
+        const size_t off = (size_t)y * g.rowStride + (size_t)xs * Dp;
+        bulk_g2s(stgAB + (size_t)(sg * a.nAB + 0) * SWmax * Dp, a.inA + off, bytesAB, &bars[sg]);
+        if (hasB) bulk_g2s(stgAB + (size_t)(sg * a.nAB + 1) * SWmax * Dp, a.inB + off, bytesAB, &bars[sg]);
+    };
+    // NDIR = 1: independent columns, operands of the next row are prefetched into registers.
+    uint32_t Cn[NREG], An[NREG], Bn[NREG];
     auto crow_ptr = [&](int t) -> const uint16_t * {
         const int y = yBegin + t * yStep;
         return (t < altRows) ? calt + (size_t)t * g.rowStride + (size_t)x1 * Dp
                              : a.C + (size_t)y * g.rowStride + (size_t)x1 * Dp;
     };
-    load_vec_nc<NREG, LPC>(Cn, crow_ptr(0), lg);
-    if (0 >= tOut && own) {
-        load_vec<NREG, LPC>(An, a.inA + (size_t)yBegin * g.rowStride + (size_t)x1 * Dp, lg);
-        if (hasB) load_vec<NREG, LPC>(Bn, a.inB + (size_t)yBegin * g.rowStride + (size_t)x1 * Dp, lg);
+    if (NDIR == 3) {
+        if (threadIdx.x == 0) {
+            for (int t = 0; t < nstg && t < nRows; t++) fill(t);
+            mbar_wait(&bars[0], 0u);
+        }
+        __syncthreads();
+    } else {
+        load_vec_nc<NREG, LPC>(Cn, crow_ptr(0), lg);
+        if (0 >= tOut && own) {
+            load_vec<NREG, LPC>(An, a.inA + (size_t)yBegin * g.rowStride + (size_t)x1 * Dp, lg);
+            if (hasB) load_vec<NREG, LPC>(Bn, a.inB + (size_t)yBegin * g.rowStride + (size_t)x1 * Dp, lg);
+        }
     }
 
     int k = 0, sidx = 0;                                  // row inside the super-step, super-step index
@@ -215,27 +278,40 @@ __global__ void __launch_bounds__(VertMaxThreads<NREG>::value, 1) k_vertical(Ver
         }
         const bool haloAct = (haloL || haloR) && k <= HG - 1 - hj;     // chain still needed this row
         const bool doA = own || (haloL && haloAct), doC = own || (haloR && haloAct);
-        const int kn = (k + 1 == R) ? 0 : k + 1;
-        const bool nextAct = own || ((haloL || haloR) && kn <= HG - 1 - hj);
 
         uint32_t Cc[NREG], S[NREG];
-#pragma unroll
-        for (int j = 0; j < NREG; j++) Cc[j] = Cn[j];
         const bool outRow = t >= tOut;
-        if (outRow) {
+        const bool warpOwn = __any_sync(0xFFFFFFFFu, own);
+        if (NDIR == 3) {
+            const int sg = t % nstg;                      // stage t was waited for before the last barrier
+            load_vec<NREG, LPC>(Cc, stgC + ((size_t)sg * ngroups + gi) * Dp, lg);
+            if (warpOwn) {
+                const int oi = own ? gi - HG : 0;
+                load_vec<NREG, LPC>(S, stgAB + ((size_t)(sg * a.nAB + 0) * SWmax + oi) * Dp, lg);
+                if (hasB) {
+                    uint32_t Bv[NREG];
+                    load_vec<NREG, LPC>(Bv, stgAB + ((size_t)(sg * a.nAB + 1) * SWmax + oi) * Dp, lg);
 #pragma unroll
-            for (int j = 0; j < NREG; j++) S[j] = hasB ? paddmin(An[j], Bn[j], SGBM_MAX_S) : An[j];
-        }
-        if (t + 1 < nRows && nextAct) {                   // prefetch the next row of this column
-            load_vec_nc<NREG, LPC>(Cn, crow_ptr(t + 1), lg);
-            if (t + 1 >= tOut && own) {
-                const size_t off = (size_t)(y + yStep) * g.rowStride + (size_t)x1 * Dp;
-                load_vec<NREG, LPC>(An, a.inA + off, lg);
-                if (hasB) load_vec<NREG, LPC>(Bn, a.inB + off, lg);
+                    for (int j = 0; j < NREG; j++) S[j] = paddmin(S[j], Bv[j], SGBM_MAX_S);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NREG; j++) Cc[j] = Cn[j];
+            if (outRow) {
+#pragma unroll
+                for (int j = 0; j < NREG; j++) S[j] = hasB ? paddmin(An[j], Bn[j], SGBM_MAX_S) : An[j];
+            }
+            if (t + 1 < nRows) {                          // prefetch the next row of this column
+                load_vec_nc<NREG, LPC>(Cn, crow_ptr(t + 1), lg);
+                if (t + 1 >= tOut && own) {
+                    const size_t off = (size_t)(y + yStep) * g.rowStride + (size_t)x1 * Dp;
+                    load_vec<NREG, LPC>(An, a.inA + off, lg);
+                    if (hasB) load_vec<NREG, LPC>(Bn, a.inB + off, lg);
+                }
             }
         }
         uint32_t Ln[NREG];
-        const bool warpOwn = __any_sync(0xFFFFFFFFu, own);
         // ---- vertical path: predecessor (x, previous row), state in registers -------------------
         if (warpOwn) {
             mB = path_step<NREG, LPC>(Ln, LB, mB, Cc, P1p, P2mP1p, lg, lastLane);
@@ -393,8 +469,12 @@ __global__ void __launch_bounds__(VertMaxThreads<NREG>::value, 1) k_vertical(Ver
             }
         }
         if (NDIR == 3) {
+            if (threadIdx.x == 0 && t + 1 < nRows) mbar_wait(&bars[(t + 1) % nstg], (uint32_t)((t + 1) / nstg) & 1u);
             __syncthreads();
-            if (k == R - 1 && t + 1 < nRows && threadIdx.x == 0) st_release(a.flagA + strip, (unsigned)(sidx + 1));
+            if (threadIdx.x == 0) {
+                if (k == R - 1 && t + 1 < nRows) st_release(a.flagA + strip, (unsigned)(sidx + 1));
+                if (t + nstg < nRows) fill(t + nstg);     // stage t % nstg is free now
+            }
             if (++k == R) { k = 0; sidx++; }
         }
     }
@@ -403,21 +483,42 @@ __global__ void __launch_bounds__(VertMaxThreads<NREG>::value, 1) k_vertical(Ver
 // =================================================================================================
 // Host side: template dispatch and launch configuration
 // =================================================================================================
-static size_t vertical_smem_bytes(const Geo &g, int SWmax, int R, int threads)
+// Shared-memory layout of k_vertical (must match the carve-up in the kernel).
+static size_t vertical_layout(VertArgs &a, int SWmax, int R, int threads, int ndir, int nstg)
 {
-    const int NS = SWmax + 2 * R;
-    size_t ex = (size_t)2 * 2 * NS * g.Dp * 2 + (size_t)2 * 2 * NS * 4;
-    size_t ss = (size_t)(threads / g.lpc) * g.Dp * 2;
-    return (ex + ss + 15) & ~(size_t)15;
+    const Geo &g = a.g;
+    const int ngroups = threads / g.lpc;
+    (void)R;
+    a.nslots = ngroups + 2;
+    a.nstg = nstg;
+    a.nAB = a.inB ? 2 : 1;
+    size_t off = (ndir == 3) ? (size_t)2 * 2 * a.nslots * g.Dp * 2 + (size_t)2 * 2 * a.nslots * 4 : 0;
+    off = (off + 127) & ~(size_t)127;
+    a.ssmOff = (unsigned)off;
+    if (!a.sout) off += (size_t)ngroups * g.Dp * 2;
+    a.stgCOff = (unsigned)off;
+    if (ndir == 3) off += (size_t)nstg * ngroups * g.Dp * 2;
+    a.stgABOff = (unsigned)off;
+    if (ndir == 3) off += (size_t)nstg * a.nAB * SWmax * g.Dp * 2;
+    a.barOff = (unsigned)off;
+    off += 8 * 8;
+    return off;
 }
 
 template <int NREG, int LPC>
-static int launch_horizontal_t(const Geo &g, const uint16_t *C, uint16_t *LhA, uint16_t *LhB, int y0,
-                               int nrows, cudaStream_t st)
+static int launch_horizontal_t(const Geo &g, const uint16_t *C, uint16_t *LhA, uint16_t *LhB, int y0, int nrows,
+                               cudaStream_t st)
 {
-    const int gpb = HZ_THREADS / LPC;
-    dim3 grid((nrows + gpb - 1) / gpb, 2);
-    k_horizontal<NREG, LPC><<<grid, HZ_THREADS, 0, st>>>(g, C, LhA, LhB, y0, nrows);
+    constexpr int GPW = 32 / LPC, NW = HZ_THREADS / 32;
+    const size_t smem = (size_t)NW * HZ_NS * GPW * HZ_K * g.Dp * 2 + (size_t)NW * HZ_NS * 8;
+    static bool attrDone = false;
+    if (!attrDone) {
+        SGBM_CUDA_CHECK(cudaFuncSetAttribute(k_horizontal<NREG, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attrDone = true;
+    }
+    const int rowsPerCta = NW * GPW;
+    dim3 grid((nrows + rowsPerCta - 1) / rowsPerCta, 2);
+    k_horizontal<NREG, LPC><<<grid, HZ_THREADS, smem, st>>>(g, C, LhA, LhB, y0, nrows);
     sgbm_count_launch(1);
     SGBM_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -439,13 +540,16 @@ static int launch_vertical_t(VertArgs &a, int numSMs, cudaStream_t st)
         SGBM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
         attrDone = true;
     }
+    int nstgWant = 3;
+    if (const char *e = getenv("SGBM_NSTG")) nstgWant = atoi(e) >= 2 && atoi(e) <= 4 ? atoi(e) : 3;
     if (NDIR == 1) {
         // independent columns: ordinary grid, 128 threads per CTA
         const int threads = 128;
         a.SW = threads / LPC;
         a.R = 1;
         a.nstrips = (g.W1 + a.SW - 1) / a.SW;
-        const size_t smem = vertical_smem_bytes(g, a.SW, 1, threads);
+        const size_t smem = vertical_layout(a, a.SW, 1, threads, 1, 2);
+        if (smem > (size_t)maxSmem) return sgbm_fail(-3, "vertical sweep needs %zu bytes of shared memory (max %d)", smem, maxSmem);
         dim3 grid(a.nstrips, a.threeway ? 4 : 1);
         kern<<<grid, threads, smem, st>>>(a);
         sgbm_count_launch(1);
@@ -458,7 +562,8 @@ static int launch_vertical_t(VertArgs &a, int numSMs, cudaStream_t st)
     int R = 9;
     if (const char *e = getenv("SGBM_VR")) R = atoi(e) > 0 ? atoi(e) : 1;
     if (R > 16) R = 16;
-    int nstrips = numSMs, SWmax = 1;
+    int nstrips = numSMs, SWmax = 1, threads = 32, nstg = 2;
+    size_t smem = 0;
     for (;; R--) {
         if (R < 1) return sgbm_fail(-3, "image too wide for the vertical sweep (W1=%d, lanes/column=%d, SMs=%d)", g.W1, LPC, numSMs);
         nstrips = numSMs;
@@ -467,12 +572,17 @@ static int launch_vertical_t(VertArgs &a, int numSMs, cudaStream_t st)
         if (nstrips < 1) nstrips = 1;
         if (nstrips == 1 && R > 1) continue;              // a single strip has no halos
         SWmax = (g.W1 + nstrips - 1) / nstrips;
-        const int thr = (((SWmax + 2 * (R - 1)) * LPC + 31) / 32) * 32;
-        if (thr <= maxThreads && vertical_smem_bytes(g, SWmax, R, thr) <= (size_t)maxSmem) break;
+        threads = (((SWmax + 2 * (R - 1)) * LPC + 31) / 32) * 32;
+        if (threads > maxThreads) continue;
+        bool fits = false;
+        for (nstg = nstgWant; nstg >= 2; nstg--) {
+            smem = vertical_layout(a, SWmax, R, threads, 3, nstg);
+            if (smem <= (size_t)maxSmem) { fits = true; break; }
+        }
+        if (fits) break;
     }
-    const int threads = (((SWmax + 2 * (R - 1)) * LPC + 31) / 32) * 32;
-    const size_t smem = vertical_smem_bytes(g, SWmax, R, threads);
     a.SW = SWmax; a.R = R; a.nstrips = nstrips;
+    smem = vertical_layout(a, SWmax, R, threads, 3, nstg);
     int occ = 0;
     SGBM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
     if (occ * numSMs < a.nstrips) return sgbm_fail(-3, "vertical sweep cannot be made co-resident (%d strips, %d x %d slots)", a.nstrips, occ, numSMs);
