@@ -78,39 +78,96 @@ __device__ __forceinline__ void uf_union(int *L, int a, int b)
     } while (!done);
 }
 
-__global__ void k_cc_init(const int16_t *img, int *label, int *size, int n, int newVal)
+// Run-based labelling.  A "run" is a maximal horizontal segment of connected pixels; every pixel
+// is labelled with the index of its run's first pixel (no atomics: segmented max-scan per row),
+// so the union-find only has to merge runs of adjacent rows, and sizes are added per run.
+#define CC_THREADS 256
+__device__ __forceinline__ bool cc_link(int a, int b, int newVal, int maxDiff)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    label[i] = (img[i] != newVal) ? i : -1;
-    size[i] = 0;
+    return a != newVal && b != newVal && abs(a - b) <= maxDiff;
 }
+
+// one CTA per row: label[i] = first pixel of the run containing i (or -1), size[i] = 0
+__global__ void __launch_bounds__(CC_THREADS) k_cc_runs(const int16_t *img, int *label, int *size, int W, int newVal, int maxDiff)
+{
+    __shared__ int wmax[CC_THREADS / 32];
+    __shared__ int carry;
+    const int y = blockIdx.x;
+    const int16_t *row = img + (size_t)y * W;
+    if (threadIdx.x == 0) carry = -1;
+    __syncthreads();
+    for (int x0 = 0; x0 < W; x0 += CC_THREADS) {
+        const int x = x0 + threadIdx.x;
+        int start = -1, v = newVal;
+        if (x < W) {
+            v = row[x];
+            const bool linked = x > 0 && cc_link(row[x - 1], v, newVal, maxDiff);
+            if (!linked) start = x;                       // run starts here (also for invalid pixels)
+        }
+        int m = start;                                    // inclusive max-scan of run starts
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xFFFFFFFFu, m, o);
+            if ((threadIdx.x & 31) >= o) m = max(m, t);
+        }
+        if ((threadIdx.x & 31) == 31) wmax[threadIdx.x >> 5] = m;
+        __syncthreads();
+        int pre = carry;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) pre = max(pre, wmax[w]);
+        m = max(m, pre);
+        if (x < W) {
+            const size_t i = (size_t)y * W + x;
+            label[i] = (v != newVal) ? y * W + m : -1;
+            size[i] = 0;
+        }
+        __syncthreads();
+        if (threadIdx.x == CC_THREADS - 1) carry = m;
+        __syncthreads();
+    }
+}
+
+// vertical merges: one union per contact between a run of row y and a run of row y+1
 __global__ void k_cc_merge(const int16_t *img, int *label, int W, int H, int newVal, int maxDiff)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y;
-    if (x >= W) return;
-    int i = y * W + x;
-    int v = img[i];
-    if (v == newVal) return;
-    if (x + 1 < W) { int w = img[i + 1]; if (w != newVal && abs(v - w) <= maxDiff) uf_union(label, i, i + 1); }
-    if (y + 1 < H) { int w = img[i + W]; if (w != newVal && abs(v - w) <= maxDiff) uf_union(label, i, i + W); }
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= W || y + 1 >= H) return;
+    const int i = y * W + x;
+    const int a = img[i], b = img[i + W];
+    if (!cc_link(a, b, newVal, maxDiff)) return;
+    if (x > 0) {                                          // the same two runs already touched at x-1?
+        const int a0 = img[i - 1], b0 = img[i + W - 1];
+        if (cc_link(a0, a, newVal, maxDiff) && cc_link(b0, b, newVal, maxDiff) && cc_link(a0, b0, newVal, maxDiff)) return;
+    }
+    uf_union(label, label[i], label[i + W]);
 }
-__global__ void k_cc_count(int *label, int *size, int n)
+
+// run ends add their run length to the root's size and flatten the run start's label
+__global__ void k_cc_count(const int16_t *img, int *label, int *size, int W, int H, int newVal, int maxDiff)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (label[i] < 0) return;
-    int r = uf_find(label, i);
-    label[i] = r;                       // path flattening; racing readers still see an ancestor
-    atomicAdd(&size[r], 1);
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= W) return;
+    const int i = y * W + x;
+    const int v = img[i];
+    if (v == newVal) return;
+    const bool runEnd = (x + 1 >= W) || !cc_link(v, img[i + 1], newVal, maxDiff);
+    if (!runEnd) return;
+    const bool runStart = (x == 0) || !cc_link(img[i - 1], v, newVal, maxDiff);
+    const int s = runStart ? i : label[i];               // non-start pixels keep pointing at their run start
+    const int r = uf_find(label, s);
+    atomicAdd(&size[r], i - s + 1);
 }
+
 __global__ void k_cc_apply(int16_t *img, const int *label, const int *size, int n, int newVal, int maxSize)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int r = label[i];
-    if (r >= 0 && size[r] <= maxSize) img[i] = (int16_t)newVal;
+    const int s = label[i];
+    if (s < 0) return;
+    int r = s, p = label[r];
+    while (p != r) { r = p; p = label[r]; }               // labels are final here
+    if (size[r] <= maxSize) img[i] = (int16_t)newVal;
 }
 
 // ---- float conversion + reprojection --------------------------------------------------------------
@@ -299,10 +356,10 @@ int sgbm_launch_speckles(int16_t *img, int W, int H, int newVal, int maxSize, in
 {
     int n = W * H;
     int *label = (int *)scratch, *size = label + n;
-    k_cc_init<<<(n + 255) / 256, 256, 0, st>>>(img, label, size, n, newVal);
+    k_cc_runs<<<H, CC_THREADS, 0, st>>>(img, label, size, W, newVal, maxDiff);
     dim3 grid((W + 255) / 256, H);
     k_cc_merge<<<grid, 256, 0, st>>>(img, label, W, H, newVal, maxDiff);
-    k_cc_count<<<(n + 255) / 256, 256, 0, st>>>(label, size, n);
+    k_cc_count<<<grid, 256, 0, st>>>(img, label, size, W, H, newVal, maxDiff);
     k_cc_apply<<<(n + 255) / 256, 256, 0, st>>>(img, label, size, n, newVal, maxSize);
     sgbm_count_launch(4);
     SGBM_CUDA_CHECK(cudaGetLastError());
