@@ -1,5 +1,7 @@
 cd /root/repo
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -15
-run() { timeout 300 python bench.py --workload $1 --steps 3 --warmup 3 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$2', d['value'], d['ms_per_step'], d['stages_ms'])"; }
-run cfg3 cfg3
+run() { timeout 120 python bench.py --workload $1 --steps 5 --warmup 3 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$2', round(d['value']), round(d['ms_per_step'],2), d['e2e']['matches_device_path'], d['stages_ms'])"; }
+timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "stages_vs_oracle" 2>&1 | tail -15
 run cfg2 cfg2
+run cfg3 cfg3
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+run cfg4 cfg4

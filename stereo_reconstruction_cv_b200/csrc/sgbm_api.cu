@@ -175,9 +175,9 @@ static void ws_layout(const Geo &g, const sgbm_params &p, int numSMs, int keep, 
     L.speck = take((size_t)g.W * g.H * 8);
     int maxStrips = g.W1 < numSMs ? g.W1 : numSMs;
     const int maxR = 16;
-    L.haloA = take((size_t)maxStrips * 2 * maxR * (g.Dp + 8) * 2);
-    L.haloC = take((size_t)maxStrips * 2 * maxR * (g.Dp + 8) * 2);
-    L.flags = take((size_t)2 * maxStrips * 4);
+    L.haloA = take((size_t)maxStrips * 4 * maxR * (g.Dp + 8) * 2);    // 4 super-step slots (sgbm_sweep.cu)
+    L.haloC = take((size_t)maxStrips * 4 * maxR * (g.Dp + 8) * 2);
+    L.flags = take((size_t)2 * maxStrips * maxR * 4);                 // one flag per published column
     L.sdbg = take(keep ? vol : 16);
     L.total = off;
 }

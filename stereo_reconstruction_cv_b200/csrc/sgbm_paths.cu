@@ -613,10 +613,19 @@ int sgbm_launch_horizontal(const Geo &g, const uint16_t *C, uint16_t *LhA, uint1
     return sgbm_fail(-3, "no kernel for lane mapping nreg=%d lpc=%d", g.nreg, g.lpc);
 }
 
+int sgbm_launch_sweep(const VertArgs &a, int numSMs, cudaStream_t st);   // sgbm_sweep.cu
+
 int sgbm_launch_vertical(VertArgs &a, int ndir, int numSMs, cudaStream_t st)
 {
     const Geo &g = a.g;
     if (ndir == 3) {
+        // role-specialised sweep (sgbm_sweep.cu); the lock-step kernel below remains as the fallback for
+        // geometries it cannot hold (and for A/B runs with SGBM_SWEEP=0)
+        const char *e = getenv("SGBM_SWEEP");
+        if (!e || atoi(e) != 0) {
+            const int rc = sgbm_launch_sweep(a, numSMs, st);
+            if (rc <= 0) return rc;
+        }
         SGBM_DISPATCH_ALL((launch_vertical_t<NREG, LPC, 3>(a, numSMs, st)))
     } else {
         SGBM_DISPATCH_ALL((launch_vertical_t<NREG, LPC, 1>(a, numSMs, st)))

@@ -1,0 +1,500 @@
+// sgbm_sweep.cu -- the 3-direction sweep of StereoSGBM.compute (main.ipynb:668) for sm_100a:
+// one top-down (or bottom-up) pass that advances the vertical path (0,-1) and the two diagonal
+// paths (-1,-1), (+1,-1) for every column, accumulates S and either spills it once (MODE_HH
+// forward sweep) or runs the fused winner-take-all.
+//
+// Design (replaces the lock-step k_vertical<.,.,3>, which spent its time in a per-row block
+// barrier): one persistent CTA per column strip, warp-specialised into three path roles that each
+// keep their path state in REGISTERS and never exchange it inside the CTA:
+//   role V : one lane group per column, fixed column              -> vertical path
+//   role A : lane groups that move one column to the right per row -> path with predecessor (x-1)
+//   role C : lane groups that move one column to the left per row  -> path with predecessor (x+1)
+// A lane group of role A/C follows "its" diagonal through the strip, so the predecessor state is
+// simply what the group computed on the previous row.  What flows between the roles is the partial
+// sum S, through a ring of K shared-memory row slots:  V writes L_h + L_v, A adds its path,
+// C adds its path and finishes the pixel (spill or WTA).  Cost rows (and the L_h / S_fwd input
+// rows) are staged by a producer warp with TMA bulk copies into multi-stage rings.  All hand-offs
+// are mbarrier full/empty pairs, so the roles drift apart by up to K rows and no warp ever waits at
+// a block-wide barrier.
+//
+// Strips exchange diagonal state every R rows (a "super-step"): at its end, role A publishes the
+// state of the strip's last R columns, role C that of its first R columns (global memory, one
+// release flag per column).  At the next super-step R chains per role restart from the
+// neighbour's published columns, R-1 of them in halo columns outside the strip (the redundant
+// triangle that pays for syncing every R rows instead of every row).  Group (b, i) -- batch b,
+// index i -- restarts at super-steps n == b (mod NB) at halo position i, so at every row each
+// column of the strip is covered by exactly one chain.
+#include "sgbm_common.cuh"
+#include <stdlib.h>
+#include <string.h>
+
+struct SweepArgs {
+    Geo g;
+    const uint16_t *C, *inA, *inB;
+    uint16_t *sout, *sdbg;
+    int16_t *raw;
+    unsigned int *d2key;
+    int SW, nstrips, R, NB;          // max columns per strip, strips, rows per super-step, batches
+    int nwA, nwV;                    // warps of each diagonal role / of the vertical role
+    int NSC, NSI, K, nAB;            // ring depths (cost rows, input rows, S slots), input volumes
+    unsigned int stgCOff, stgIOff, pOff, ssmOff, barOff;
+    int backward;
+    uint16_t *haloA, *haloC;         // [nstrips][4][R][Dp + 8]
+    unsigned int *flagA, *flagC;     // [nstrips][R] super-steps published per column
+    int dbgNoSync;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+template <int NREG, int LPC>
+__device__ __forceinline__ void load_vec_l2(uint32_t (&v)[NREG], const uint16_t *col, int lg)
+{
+    const uint4 *p = reinterpret_cast<const uint4 *>(col) + lg;
+#pragma unroll
+    for (int k = 0; k < NREG / 4; k++) {
+        uint4 q = __ldcg(p + LPC * k);
+        v[4 * k + 0] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+    }
+}
+
+struct SweepSmem {
+    uint16_t *stgC, *stgI, *P, *ssm;
+    uint64_t *fullC, *emptyC, *fullI, *emptyI, *fullV, *fullA, *freeP;
+};
+__device__ __forceinline__ SweepSmem sweep_carve(const SweepArgs &a, uint8_t *smem)
+{
+    SweepSmem s;
+    s.stgC = reinterpret_cast<uint16_t *>(smem + a.stgCOff);     // [NSC][SW + 2(R-1)][Dp]
+    s.stgI = reinterpret_cast<uint16_t *>(smem + a.stgIOff);     // [NSI][nAB][SW][Dp]
+    s.P = reinterpret_cast<uint16_t *>(smem + a.pOff);           // [K][SW][Dp]
+    s.ssm = reinterpret_cast<uint16_t *>(smem + a.ssmOff);       // [groups of role C][Dp]  (WTA scratch)
+    uint64_t *b = reinterpret_cast<uint64_t *>(smem + a.barOff);
+    s.fullC = b; b += a.NSC;
+    s.emptyC = b; b += a.NSC;
+    s.fullI = b; b += a.NSI;
+    s.emptyI = b; b += a.NSI;
+    s.fullV = b; b += a.K;
+    s.fullA = b; b += a.K;
+    s.freeP = b;
+    return s;
+}
+
+// ---- producer: TMA bulk copies of the cost row and the input rows of every sweep row ---------------
+__device__ __forceinline__ void sweep_producer(const SweepArgs &a, const SweepSmem &s, int xs, int xe, int yBegin,
+                                               int yStep, int nRows)
+{
+    const Geo &g = a.g;
+    const int Dp = g.Dp, HG = a.R - 1, ngC = a.SW + 2 * HG;
+    const int scol0 = xs - HG;
+    const int clo = max(scol0, 0), chi = min(xe + HG, g.W1);
+    const uint32_t bytesC = (uint32_t)(chi - clo) * Dp * 2, bytesI = (uint32_t)(xe - xs) * Dp * 2;
+    int sc = 0, si = 0;
+    uint32_t pc = 0, pi = 0;
+    for (int t = 0; t < nRows; t++) {
+        const int y = yBegin + t * yStep;
+        if (t >= a.NSC) mbar_wait(&s.emptyC[sc], pc ^ 1u);
+        mbar_expect_tx(&s.fullC[sc], bytesC);
+        bulk_g2s(s.stgC + ((size_t)sc * ngC + (clo - scol0)) * Dp, a.C + (size_t)y * g.rowStride + (size_t)clo * Dp, bytesC,
+                 &s.fullC[sc]);
+        if (t >= a.NSI) mbar_wait(&s.emptyI[si], pi ^ 1u);
+        const size_t off = (size_t)y * g.rowStride + (size_t)xs * Dp;
+        mbar_expect_tx(&s.fullI[si], bytesI * (uint32_t)a.nAB);
+        bulk_g2s(s.stgI + (size_t)(si * a.nAB + 0) * a.SW * Dp, a.inA + off, bytesI, &s.fullI[si]);
+        if (a.nAB > 1) bulk_g2s(s.stgI + (size_t)(si * a.nAB + 1) * a.SW * Dp, a.inB + off, bytesI, &s.fullI[si]);
+        if (++sc == a.NSC) { sc = 0; pc ^= 1u; }
+        if (++si == a.NSI) { si = 0; pi ^= 1u; }
+    }
+}
+
+// ---- role V: vertical path, starts the S slot of every row ------------------------------------------
+template <int NREG, int LPC>
+__device__ __forceinline__ void sweep_role_v(const SweepArgs &a, const SweepSmem &s, int rwarp, int SW, int nRows)
+{
+    constexpr int GPW = 32 / LPC;
+    const Geo &g = a.g;
+    const int lane = threadIdx.x & 31, lg = lane % LPC;
+    const int Dp = g.Dp, lastLane = g.lanesUsed - 1, HG = a.R - 1, ngC = a.SW + 2 * HG;
+    const int gi = rwarp * GPW + lane / LPC;
+    const bool own = gi < SW;
+    const int ci = own ? gi : SW - 1;
+    const uint32_t P1p = (uint32_t)g.P1 * 0x10001u, P2mP1p = (uint32_t)(g.P2 - g.P1) * 0x10001u;
+    const bool hasB = a.nAB > 1;
+    uint32_t LB[NREG], mB = 0;
+#pragma unroll
+    for (int j = 0; j < NREG; j++) LB[j] = 0;
+    int sc = 0, si = 0, k = 0;
+    uint32_t pc = 0, pi = 0, pk = 0;
+    for (int t = 0; t < nRows; t++) {
+        uint32_t S[NREG];
+        mbar_wait(&s.fullC[sc], pc);
+        {
+            uint32_t Cc[NREG];
+            load_vec<NREG, LPC>(Cc, s.stgC + ((size_t)sc * ngC + HG + ci) * Dp, lg);
+            mB = path_step<NREG, LPC>(LB, LB, mB, Cc, P1p, P2mP1p, lg, lastLane);   // in place (reads run ahead of writes)
+        }
+        mbar_wait(&s.fullI[si], pi);
+        load_vec<NREG, LPC>(S, s.stgI + ((size_t)(si * a.nAB + 0) * a.SW + ci) * Dp, lg);
+#pragma unroll
+        for (int j = 0; j < NREG; j++) S[j] = paddmin(S[j], LB[j], SGBM_MAX_S);
+        if (hasB) {
+            uint32_t Bv[NREG];
+            load_vec<NREG, LPC>(Bv, s.stgI + ((size_t)(si * a.nAB + 1) * a.SW + ci) * Dp, lg);
+#pragma unroll
+            for (int j = 0; j < NREG; j++) S[j] = paddmin(S[j], Bv[j], SGBM_MAX_S);
+        }
+        if (t >= a.K) mbar_wait(&s.freeP[k], pk ^ 1u);
+        if (own) store_vec<NREG, LPC>(S, s.P + ((size_t)k * a.SW + gi) * Dp, lg);
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&s.fullV[k]);
+            mbar_arrive(&s.emptyC[sc]);
+            mbar_arrive(&s.emptyI[si]);
+        }
+        if (++sc == a.NSC) { sc = 0; pc ^= 1u; }
+        if (++si == a.NSI) { si = 0; pi ^= 1u; }
+        if (++k == a.K) { k = 0; pk ^= 1u; }
+    }
+}
+
+// ---- winner-take-all of one pixel (A.5), S distributed over the lane group --------------------------
+template <int NREG, int LPC>
+__device__ __forceinline__ void sweep_wta(const SweepArgs &a, const uint32_t (&S)[NREG], uint16_t *ssm, int lg, bool own,
+                                          int x1, int y)
+{
+    const Geo &g = a.g;
+    const int lastLane = g.lanesUsed - 1;
+    uint32_t tm = local_min<NREG>(S);
+    if (lg > lastLane) tm = SGBM_INF2;
+    const uint32_t mS2 = group_min<LPC>(tm);
+    const int minS = (int)(mS2 & 0xFFFFu);
+    int idx = 0x7FFF;
+#pragma unroll
+    for (int j = NREG - 1; j >= 0; j--) {
+        const uint32_t e = S[j] ^ mS2;
+        if ((e >> 16) == 0) idx = 2 * j + 1;
+        if ((e & 0xFFFFu) == 0) idx = 2 * j;
+    }
+    int dl = (lg <= lastLane && idx != 0x7FFF) ? lg * 2 * NREG + idx : 0x7FFF;
+#pragma unroll
+    for (int off = LPC / 2; off >= 1; off >>= 1) dl = min(dl, __shfl_xor_sync(0xFFFFFFFFu, dl, off, LPC));
+    const int best = (minS == 32767) ? -1 : dl;                         // first minimum (A.5)
+    // S to shared scratch: sub-pixel neighbours and the masked uniqueness scan
+    __syncwarp();
+    store_vec<NREG, LPC>(S, ssm, lg);
+    __syncwarp();
+    int Sm = 0, Sp = 0;
+    const bool interior = best > 0 && best < g.D - 1;
+    if (lg == 0 && interior) {
+        Sm = ssm[sgbm_pos(best - 1, NREG, LPC)];
+        Sp = ssm[sgbm_pos(best + 1, NREG, LPC)];
+    }
+    bool reject = false;
+    if (g.UR > 0) {
+        const int av = 100 - g.UR;                                       // S(d)*(100-UR) < minS*100  <=>  S(d) < T
+        const int T = av > 0 ? min((100 * minS + av - 1) / av, 32768) : (minS > 0 ? 32768 : 0);
+        __syncwarp();
+        if (lg == 0) {
+#pragma unroll
+            for (int dd = -1; dd <= 1; dd++) {
+                const int d = best + dd;
+                if (d >= 0 && d < g.D) ssm[sgbm_pos(d, NREG, LPC)] = 0xFFFFu;
+            }
+        }
+        __syncwarp();
+        uint32_t S2[NREG];
+        load_vec<NREG, LPC>(S2, ssm, lg);
+        uint32_t t2 = local_min<NREG>(S2);
+        if (lg > lastLane) t2 = SGBM_INF2;
+        const int m2 = (int)(group_min<LPC>(t2) & 0xFFFFu);
+        reject = m2 < T;
+    }
+    if (lg == 0 && own) {
+        const int x = x1 + g.minX1;
+        int out = g.INV;
+        if (!reject) {
+            const int x2 = x - best - g.minD;
+            if (minS < 32767 && x2 >= 0 && x2 < g.W)
+                atomicMin(a.d2key + (size_t)y * g.W + x2, ((unsigned)minS << 16) | (0xFFFFu - (unsigned)x1));
+            int dq = best * 16;
+            if (interior) {
+                const int den = max(Sm + Sp - 2 * minS, 1);
+                dq += ((Sm - Sp) * 16 + den) / (2 * den);
+            }
+            out = dq + g.minD * 16;
+        }
+        a.raw[(size_t)y * g.W + x] = (int16_t)out;
+    }
+}
+
+// ---- roles A (DIR = +1) and C (DIR = -1, finishes the pixel) -----------------------------------------
+template <int NREG, int LPC, int DIR>
+__device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepSmem &s, int rwarp, int strip, int xs,
+                                                int xe, int yBegin, int yStep, int nRows)
+{
+    constexpr int GPW = 32 / LPC;
+    constexpr bool FINAL = DIR < 0;
+    const Geo &g = a.g;
+    const int lane = threadIdx.x & 31, lg = lane % LPC;
+    const int Dp = g.Dp, lastLane = g.lanesUsed - 1, R = a.R, HG = R - 1, ngC = a.SW + 2 * HG, NB = a.NB;
+    const uint32_t P1p = (uint32_t)g.P1 * 0x10001u, P2mP1p = (uint32_t)(g.P2 - g.P1) * 0x10001u;
+    const int gg = rwarp * GPW + lane / LPC;
+    const int b = gg / R, i = gg - b * R;
+    const bool exists = b < NB;
+    int p = i + ((NB - b) % NB) * R;                      // position at row 0 (chains "started" before the image)
+    const bool hasNbr = DIR > 0 ? strip > 0 : strip < a.nstrips - 1;
+    const bool canPub = DIR > 0 ? strip < a.nstrips - 1 : strip > 0;
+    const size_t haloStride = (size_t)Dp + 8;
+    uint16_t *haloOut = (DIR > 0 ? a.haloA : a.haloC) + (size_t)strip * 4 * R * haloStride;
+    unsigned int *flagOut = (DIR > 0 ? a.flagA : a.flagC) + (size_t)strip * R;
+    const int nbr = DIR > 0 ? strip - 1 : strip + 1;
+    const int hidx = DIR > 0 ? i : R - 1 - i;             // which published column chain i continues
+    const uint16_t *haloIn = (DIR > 0 ? a.haloA : a.haloC) + ((size_t)nbr * 4 * R + hidx) * haloStride;
+    const unsigned int *flagIn = (DIR > 0 ? a.flagA : a.flagC) + (size_t)nbr * R + hidx;
+    uint16_t *ssm = s.ssm + (size_t)gg * Dp;
+    uint64_t *waitBar = DIR > 0 ? s.fullV : s.fullA, *doneBar = DIR > 0 ? s.fullA : s.freeP;
+
+    uint32_t L[NREG], m = 0;
+#pragma unroll
+    for (int j = 0; j < NREG; j++) L[j] = 0;              // "predecessor outside" == L = 0, m = 0 (A.4)
+    int sc = 0, k = 0, kk = 0, n = 0, nm = 0;
+    uint32_t pc = 0, pk = 0;
+    for (int t = 0; t < nRows; t++) {
+        // ---- super-step start: batch nm restarts from the neighbour's published columns -------------
+        if (kk == 0 && t > 0) {
+            const bool restart = exists && nm == b;
+            if (restart) p = i;
+            if (hasNbr) {
+                if (restart && lg == 0 && !a.dbgNoSync) {
+                    unsigned int spins = 0;
+                    while (ld_acquire_u32(flagIn) < (unsigned)n) {
+                        __nanosleep(32);
+                        if (++spins > (1u << 24)) __trap();
+                    }
+                }
+                __syncwarp();
+                if (restart) {
+                    const uint16_t *h = haloIn + (size_t)((n - 1) & 3) * R * haloStride;
+                    load_vec_l2<NREG, LPC>(L, h, lg);
+                    m = __ldcg(reinterpret_cast<const unsigned int *>(h + Dp));
+                }
+            } else if (restart) {
+#pragma unroll
+                for (int j = 0; j < NREG; j++) L[j] = 0;
+                m = 0;
+            }
+        }
+        const int col = DIR > 0 ? xs - HG + p : xe - 1 + HG - p;
+        const bool active = exists && (DIR > 0 ? col < xe : col >= xs) && col >= 0 && col < g.W1;
+        const bool own = active && col >= xs && col < xe;
+        const int sidx = active ? col - (xs - HG) : HG;
+        if (!hasNbr && (DIR > 0 ? col <= 0 : col >= g.W1 - 1)) {   // chain enters the image: predecessor outside
+#pragma unroll
+            for (int j = 0; j < NREG; j++) L[j] = 0;
+            m = 0;
+        }
+        mbar_wait(&s.fullC[sc], pc);
+        if (__any_sync(0xFFFFFFFFu, active)) {           // inactive groups compute garbage that is never used
+            uint32_t Cc[NREG];
+            load_vec<NREG, LPC>(Cc, s.stgC + ((size_t)sc * ngC + sidx) * Dp, lg);
+            m = path_step<NREG, LPC>(L, L, m, Cc, P1p, P2mP1p, lg, lastLane);
+        }
+        const uint32_t mN = m;
+        const uint32_t (&Ln)[NREG] = L;
+        // ---- super-step end: publish the columns the neighbour continues ----------------------------
+        if (kk == R - 1 && canPub && t + 1 < nRows) {
+            const int pi = DIR > 0 ? col - (xe - R) : col - xs;
+            const bool pub = own && pi >= 0 && pi < R;
+            if (pub) {
+                uint16_t *h = haloOut + ((size_t)(n & 3) * R + pi) * haloStride;
+                store_vec<NREG, LPC>(Ln, h, lg);
+                if (lg == 0) *reinterpret_cast<unsigned int *>(h + Dp) = mN;
+            }
+            __syncwarp();
+            if (pub && lg == 0) {
+                __threadfence();
+                st_release_u32(flagOut + pi, (unsigned)(n + 1));
+            }
+        }
+        // ---- S slot of this row ---------------------------------------------------------------------
+        mbar_wait(&waitBar[k], pk);
+        uint32_t S[NREG];
+        if (own) {
+            uint16_t *ps = s.P + ((size_t)k * a.SW + (col - xs)) * Dp;
+            load_vec<NREG, LPC>(S, ps, lg);
+#pragma unroll
+            for (int j = 0; j < NREG; j++) S[j] = paddmin(S[j], Ln[j], SGBM_MAX_S);
+            if (!FINAL) store_vec<NREG, LPC>(S, ps, lg);
+        } else if (FINAL) {
+#pragma unroll
+            for (int j = 0; j < NREG; j++) S[j] = SGBM_MAX_S;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&doneBar[k]);
+            mbar_arrive(&s.emptyC[sc]);
+        }
+        if (FINAL && __any_sync(0xFFFFFFFFu, own)) {
+            const int y = yBegin + t * yStep;
+            const int x1 = own ? col : xs;
+            if (a.sout) {
+                if (own) store_vec<NREG, LPC>(S, a.sout + (size_t)y * g.rowStride + (size_t)x1 * Dp, lg);
+            } else {
+                if (a.sdbg && own) store_vec<NREG, LPC>(S, a.sdbg + (size_t)y * g.rowStride + (size_t)x1 * Dp, lg);
+                sweep_wta<NREG, LPC>(a, S, ssm, lg, own, x1, y);
+            }
+        }
+        p++;
+        if (++sc == a.NSC) { sc = 0; pc ^= 1u; }
+        if (++k == a.K) { k = 0; pk ^= 1u; }
+        if (++kk == R) {
+            kk = 0; n++;
+            if (++nm == NB) nm = 0;
+        }
+    }
+}
+
+template <int NREG> struct SweepMaxThreads { static const int value = NREG >= 12 ? 768 : 1024; };
+
+template <int NREG, int LPC>
+__global__ void __launch_bounds__(SweepMaxThreads<NREG>::value, 1) k_sweep(SweepArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const Geo &g = a.g;
+    const int strip = blockIdx.x;
+    const int xs = (int)((long long)strip * g.W1 / a.nstrips);
+    const int xe = (int)((long long)(strip + 1) * g.W1 / a.nstrips);
+    const int nRows = g.H, yBegin = a.backward ? g.H - 1 : 0, yStep = a.backward ? -1 : 1;
+    const SweepSmem s = sweep_carve(a, smem);
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        const int nCons = a.nwV + 2 * a.nwA;
+        for (int q = 0; q < a.NSC; q++) { mbar_init(&s.fullC[q], 1); mbar_init(&s.emptyC[q], nCons); }
+        for (int q = 0; q < a.NSI; q++) { mbar_init(&s.fullI[q], 1); mbar_init(&s.emptyI[q], a.nwV); }
+        for (int q = 0; q < a.K; q++) { mbar_init(&s.fullV[q], a.nwV); mbar_init(&s.fullA[q], a.nwA); mbar_init(&s.freeP[q], a.nwA); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (warp < a.nwV) {
+        sweep_role_v<NREG, LPC>(a, s, warp, xe - xs, nRows);
+    } else if (warp < a.nwV + a.nwA) {
+        sweep_role_diag<NREG, LPC, +1>(a, s, warp - a.nwV, strip, xs, xe, yBegin, yStep, nRows);
+    } else if (warp < a.nwV + 2 * a.nwA) {
+        sweep_role_diag<NREG, LPC, -1>(a, s, warp - a.nwV - a.nwA, strip, xs, xe, yBegin, yStep, nRows);
+    } else if ((threadIdx.x & 31) == 0) {
+        sweep_producer(a, s, xs, xe, yBegin, yStep, nRows);
+    }
+}
+
+// =================================================================================================
+// Host side
+// =================================================================================================
+static size_t sweep_layout(SweepArgs &a, int groupsC, bool wta)
+{
+    const Geo &g = a.g;
+    const size_t col = (size_t)g.Dp * 2;
+    size_t off = 0;
+    a.stgCOff = (unsigned)off; off += (size_t)a.NSC * (a.SW + 2 * (a.R - 1)) * col;
+    a.stgIOff = (unsigned)off; off += (size_t)a.NSI * a.nAB * a.SW * col;
+    a.pOff = (unsigned)off; off += (size_t)a.K * a.SW * col;
+    a.ssmOff = (unsigned)off; if (wta) off += (size_t)groupsC * col;
+    off = (off + 15) & ~(size_t)15;
+    a.barOff = (unsigned)off; off += (size_t)(2 * a.NSC + 2 * a.NSI + 3 * a.K) * 8;
+    return off;
+}
+
+// Returns 0 on success, 1 if this geometry does not fit the role-specialised sweep (the caller falls
+// back to k_vertical), negative on error.
+template <int NREG, int LPC>
+static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
+{
+    constexpr int GPW = 32 / LPC;
+    const Geo &g = va.g;
+    auto kern = k_sweep<NREG, LPC>;
+    static bool attrDone = false;
+    static int maxSmem = 0;
+    if (!attrDone) {
+        int dev = 0;
+        SGBM_CUDA_CHECK(cudaGetDevice(&dev));
+        SGBM_CUDA_CHECK(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        SGBM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        attrDone = true;
+    }
+    SweepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = g; a.C = va.C; a.inA = va.inA; a.inB = va.inB; a.sout = va.sout; a.sdbg = va.sdbg; a.raw = va.raw;
+    a.d2key = va.d2key; a.backward = va.backward; a.haloA = va.haloA; a.haloC = va.haloC; a.flagA = va.flagA;
+    a.flagC = va.flagC; a.dbgNoSync = va.dbgNoSync;
+    a.nAB = va.inB ? 2 : 1;
+    const bool wta = va.sout == nullptr;
+    const int maxThreads = SweepMaxThreads<NREG>::value;
+    int R = 8;
+    if (const char *e = getenv("SGBM_VR")) R = atoi(e) > 0 ? atoi(e) : 1;
+    if (R > 16) R = 16;
+    int Kwant = 3, NSCwant = 5, NSIwant = 3;
+    if (const char *e = getenv("SGBM_SWEEP_K")) Kwant = atoi(e) >= 1 && atoi(e) <= 8 ? atoi(e) : Kwant;
+    if (const char *e = getenv("SGBM_SWEEP_NSC")) NSCwant = atoi(e) >= 2 && atoi(e) <= 8 ? atoi(e) : NSCwant;
+    if (const char *e = getenv("SGBM_SWEEP_NSI")) NSIwant = atoi(e) >= 2 && atoi(e) <= 8 ? atoi(e) : NSIwant;
+    int threads = 0;
+    size_t smem = 0;
+    bool found = false;
+    for (; R >= 1 && !found; R--) {
+        int nstrips = numSMs;
+        const int minCols = R > 2 ? R : 2;                // every strip owns >= R (and >= 2) columns
+        if (nstrips > g.W1 / minCols) nstrips = g.W1 / minCols;
+        if (nstrips < 1) nstrips = 1;
+        if (nstrips == 1 && R > 1) continue;              // a single strip has no halos
+        const int SWmax = (g.W1 + nstrips - 1) / nstrips;
+        const int NB = (SWmax + R - 1 + R - 1) / R;       // ceil((SW + HG) / R)
+        const int groupsA = NB * R;
+        a.nwA = (groupsA + GPW - 1) / GPW;
+        a.nwV = (SWmax + GPW - 1) / GPW;
+        threads = (a.nwV + 2 * a.nwA + 1) * 32;
+        if (threads > maxThreads) continue;
+        a.SW = SWmax; a.nstrips = nstrips; a.R = R; a.NB = NB;
+        // ring depths: shrink until the layout fits
+        static const int tries[][3] = {{0, 0, 0}, {0, 0, -1}, {0, -1, -1}, {-1, -1, -1}, {-1, -2, -1}, {-2, -2, -1}, {-2, -3, -1}};
+        for (const auto &tr : tries) {
+            a.K = Kwant + tr[0]; a.NSC = NSCwant + tr[1]; a.NSI = NSIwant + tr[2];
+            if (a.K < 1) a.K = 1;
+            if (a.NSC < 2) a.NSC = 2;
+            if (a.NSI < 2) a.NSI = 2;
+            smem = sweep_layout(a, a.nwA * GPW, wta);
+            if (smem <= (size_t)maxSmem) { found = true; break; }
+        }
+    }
+    if (!found) return 1;
+    int occ = 0;
+    SGBM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    if (occ * numSMs < a.nstrips) return 1;
+    SGBM_CUDA_CHECK(cudaMemsetAsync(a.flagA, 0, sizeof(unsigned int) * 2 * (size_t)a.nstrips * 16, st));
+    a.flagC = a.flagA + (size_t)a.nstrips * 16;
+    void *args[] = {&a};
+    SGBM_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)kern, dim3(a.nstrips), dim3(threads), args, smem, st));
+    sgbm_count_launch(1);
+    return 0;
+}
+
+#define SWEEP_DISPATCH(NREG_, LPC_) \
+    if (g.nreg == NREG_ && g.lpc == LPC_) return launch_sweep_t<NREG_, LPC_>(a, numSMs, st);
+
+int sgbm_launch_sweep(const VertArgs &a, int numSMs, cudaStream_t st)
+{
+    const Geo &g = a.g;
+    SWEEP_DISPATCH(4, 2) SWEEP_DISPATCH(4, 4) SWEEP_DISPATCH(4, 8) SWEEP_DISPATCH(4, 16) SWEEP_DISPATCH(4, 32)
+    SWEEP_DISPATCH(8, 2) SWEEP_DISPATCH(8, 4) SWEEP_DISPATCH(8, 8) SWEEP_DISPATCH(8, 16) SWEEP_DISPATCH(8, 32)
+    SWEEP_DISPATCH(12, 2) SWEEP_DISPATCH(12, 4) SWEEP_DISPATCH(12, 8) SWEEP_DISPATCH(12, 16) SWEEP_DISPATCH(12, 32)
+    SWEEP_DISPATCH(16, 2) SWEEP_DISPATCH(16, 4) SWEEP_DISPATCH(16, 8) SWEEP_DISPATCH(16, 16) SWEEP_DISPATCH(16, 32)
+    return 1;
+}
