@@ -120,10 +120,33 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// Non-blocking probe: issued early, consumed later, so its latency overlaps independent work.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Blocking wait.  The retry passes a suspend-time hint so that a waiting warp sleeps in hardware
+// instead of burning issue slots in a poll loop; ~5 s without progress traps (protocol error).
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
-    uint32_t n = 0;
-    while (!mbar_try_wait(bar, parity)) { if (++n > (1u << 26)) __trap(); }
+    if (mbar_try_wait(bar, parity)) return;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .u32 n;\n\t"
+        "mov.u32 n, 0;\n"
+        "SGBM_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
+        "@p bra SGBM_DONE;\n\t"
+        "add.u32 n, n, 1;\n\t"
+        "setp.lt.u32 p, n, 512;\n\t"
+        "@p bra SGBM_WAIT;\n\t"
+        "trap;\n"
+        "SGBM_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
 // One step of the SGM recurrence (A.4) for one column, distributed over a group of LPC lanes:

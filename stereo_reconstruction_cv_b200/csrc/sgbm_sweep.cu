@@ -118,8 +118,13 @@ __device__ __forceinline__ void sweep_producer(const SweepArgs &a, const SweepSm
     }
 }
 
+// S accumulation: saturating (A.4) unless the host proved that the sum of all paths fits 16 bits, in
+// which case plain adds are exact and the clamp to 32767 is applied once when the pixel is finished.
+template <bool SAT>
+__device__ __forceinline__ uint32_t sacc(uint32_t s, uint32_t x) { return SAT ? paddmin(s, x, SGBM_MAX_S) : s + x; }
+
 // ---- role V: vertical path, starts the S slot of every row ------------------------------------------
-template <int NREG, int LPC>
+template <int NREG, int LPC, bool SAT>
 __device__ __forceinline__ void sweep_role_v(const SweepArgs &a, const SweepSmem &s, int rwarp, int SW, int nRows)
 {
     constexpr int GPW = 32 / LPC;
@@ -131,40 +136,52 @@ __device__ __forceinline__ void sweep_role_v(const SweepArgs &a, const SweepSmem
     const int ci = own ? gi : SW - 1;
     const uint32_t P1p = (uint32_t)g.P1 * 0x10001u, P2mP1p = (uint32_t)(g.P2 - g.P1) * 0x10001u;
     const bool hasB = a.nAB > 1;
+    const int NSC = a.NSC, NSI = a.NSI, K = a.K;
+    // element offsets of this group's column inside one stage / slot, and the stage strides
+    const int cBase = (HG + ci) * Dp, cStride = ngC * Dp;
+    const int iBase = ci * Dp, iStride = a.nAB * a.SW * Dp, iB = a.SW * Dp;
+    const int pBase = ci * Dp, pStride = a.SW * Dp;
     uint32_t LB[NREG], mB = 0;
 #pragma unroll
     for (int j = 0; j < NREG; j++) LB[j] = 0;
-    int sc = 0, si = 0, k = 0;
+    int sc = 0, si = 0, k = 0, cOff = cBase, iOff = iBase, pOff = pBase;
     uint32_t pc = 0, pi = 0, pk = 0;
+    bool okC = false;                                     // early probe of the next row's cost stage
     for (int t = 0; t < nRows; t++) {
         uint32_t S[NREG];
-        mbar_wait(&s.fullC[sc], pc);
+        if (!okC) mbar_wait(&s.fullC[sc], pc);
+        // probes whose latency hides behind the path step
+        const bool okI = mbar_test_wait(&s.fullI[si], pi);
+        const bool okP = t >= K ? mbar_test_wait(&s.freeP[k], pk ^ 1u) : true;
         {
             uint32_t Cc[NREG];
-            load_vec<NREG, LPC>(Cc, s.stgC + ((size_t)sc * ngC + HG + ci) * Dp, lg);
+            load_vec<NREG, LPC>(Cc, s.stgC + cOff, lg);
+            const int scN = sc + 1 == NSC ? 0 : sc + 1;
+            okC = t + 1 < nRows ? mbar_test_wait(&s.fullC[scN], scN ? pc : pc ^ 1u) : true;
             mB = path_step<NREG, LPC>(LB, LB, mB, Cc, P1p, P2mP1p, lg, lastLane);   // in place (reads run ahead of writes)
         }
-        mbar_wait(&s.fullI[si], pi);
-        load_vec<NREG, LPC>(S, s.stgI + ((size_t)(si * a.nAB + 0) * a.SW + ci) * Dp, lg);
+        if (!okI) mbar_wait(&s.fullI[si], pi);
+        load_vec<NREG, LPC>(S, s.stgI + iOff, lg);
 #pragma unroll
-        for (int j = 0; j < NREG; j++) S[j] = paddmin(S[j], LB[j], SGBM_MAX_S);
+        for (int j = 0; j < NREG; j++) S[j] = sacc<SAT>(S[j], LB[j]);
         if (hasB) {
             uint32_t Bv[NREG];
-            load_vec<NREG, LPC>(Bv, s.stgI + ((size_t)(si * a.nAB + 1) * a.SW + ci) * Dp, lg);
+            load_vec<NREG, LPC>(Bv, s.stgI + iOff + iB, lg);
 #pragma unroll
-            for (int j = 0; j < NREG; j++) S[j] = paddmin(S[j], Bv[j], SGBM_MAX_S);
+            for (int j = 0; j < NREG; j++) S[j] = sacc<SAT>(S[j], Bv[j]);
         }
-        if (t >= a.K) mbar_wait(&s.freeP[k], pk ^ 1u);
-        if (own) store_vec<NREG, LPC>(S, s.P + ((size_t)k * a.SW + gi) * Dp, lg);
+        if (!okP) mbar_wait(&s.freeP[k], pk ^ 1u);
+        if (own) store_vec<NREG, LPC>(S, s.P + pOff, lg);
         __syncwarp();
         if (lane == 0) {
             mbar_arrive(&s.fullV[k]);
             mbar_arrive(&s.emptyC[sc]);
             mbar_arrive(&s.emptyI[si]);
         }
-        if (++sc == a.NSC) { sc = 0; pc ^= 1u; }
-        if (++si == a.NSI) { si = 0; pi ^= 1u; }
-        if (++k == a.K) { k = 0; pk ^= 1u; }
+        cOff += cStride; iOff += iStride; pOff += pStride;
+        if (++sc == NSC) { sc = 0; pc ^= 1u; cOff = cBase; }
+        if (++si == NSI) { si = 0; pi ^= 1u; iOff = iBase; }
+        if (++k == K) { k = 0; pk ^= 1u; pOff = pBase; }
     }
 }
 
@@ -239,7 +256,7 @@ __device__ __forceinline__ void sweep_wta(const SweepArgs &a, const uint32_t (&S
 }
 
 // ---- roles A (DIR = +1) and C (DIR = -1, finishes the pixel) -----------------------------------------
-template <int NREG, int LPC, int DIR>
+template <int NREG, int LPC, int DIR, bool SAT>
 __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepSmem &s, int rwarp, int strip, int xs,
                                                 int xe, int yBegin, int yStep, int nRows)
 {
@@ -268,8 +285,11 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
     uint32_t L[NREG], m = 0;
 #pragma unroll
     for (int j = 0; j < NREG; j++) L[j] = 0;              // "predecessor outside" == L = 0, m = 0 (A.4)
-    int sc = 0, k = 0, kk = 0, n = 0, nm = 0;
+    const int NSC = a.NSC, K = a.K;
+    const int cStride = ngC * Dp, pStride = a.SW * Dp;
+    int sc = 0, k = 0, kk = 0, n = 0, nm = 0, cOff = 0, pOff = 0;
     uint32_t pc = 0, pk = 0;
+    bool okC = false;                                     // early probe of the next row's cost stage
     for (int t = 0; t < nRows; t++) {
         // ---- super-step start: batch nm restarts from the neighbour's published columns -------------
         if (kk == 0 && t > 0) {
@@ -304,10 +324,15 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
             for (int j = 0; j < NREG; j++) L[j] = 0;
             m = 0;
         }
-        mbar_wait(&s.fullC[sc], pc);
+        if (!okC) mbar_wait(&s.fullC[sc], pc);
+        const bool okS = mbar_test_wait(&waitBar[k], pk);  // latency hides behind the path step
+        {
+            const int scN = sc + 1 == NSC ? 0 : sc + 1;
+            okC = t + 1 < nRows ? mbar_test_wait(&s.fullC[scN], scN ? pc : pc ^ 1u) : true;
+        }
         if (__any_sync(0xFFFFFFFFu, active)) {           // inactive groups compute garbage that is never used
             uint32_t Cc[NREG];
-            load_vec<NREG, LPC>(Cc, s.stgC + ((size_t)sc * ngC + sidx) * Dp, lg);
+            load_vec<NREG, LPC>(Cc, s.stgC + cOff + sidx * Dp, lg);
             m = path_step<NREG, LPC>(L, L, m, Cc, P1p, P2mP1p, lg, lastLane);
         }
         const uint32_t mN = m;
@@ -328,13 +353,13 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
             }
         }
         // ---- S slot of this row ---------------------------------------------------------------------
-        mbar_wait(&waitBar[k], pk);
+        if (!okS) mbar_wait(&waitBar[k], pk);
         uint32_t S[NREG];
         if (own) {
-            uint16_t *ps = s.P + ((size_t)k * a.SW + (col - xs)) * Dp;
+            uint16_t *ps = s.P + pOff + (col - xs) * Dp;
             load_vec<NREG, LPC>(S, ps, lg);
 #pragma unroll
-            for (int j = 0; j < NREG; j++) S[j] = paddmin(S[j], Ln[j], SGBM_MAX_S);
+            for (int j = 0; j < NREG; j++) S[j] = sacc<SAT>(S[j], Ln[j]);
             if (!FINAL) store_vec<NREG, LPC>(S, ps, lg);
         } else if (FINAL) {
 #pragma unroll
@@ -351,13 +376,18 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
             if (a.sout) {
                 if (own) store_vec<NREG, LPC>(S, a.sout + (size_t)y * g.rowStride + (size_t)x1 * Dp, lg);
             } else {
+                if (!SAT) {
+#pragma unroll
+                    for (int j = 0; j < NREG; j++) S[j] = pmin(S[j], SGBM_MAX_S);
+                }
                 if (a.sdbg && own) store_vec<NREG, LPC>(S, a.sdbg + (size_t)y * g.rowStride + (size_t)x1 * Dp, lg);
                 sweep_wta<NREG, LPC>(a, S, ssm, lg, own, x1, y);
             }
         }
         p++;
-        if (++sc == a.NSC) { sc = 0; pc ^= 1u; }
-        if (++k == a.K) { k = 0; pk ^= 1u; }
+        cOff += cStride; pOff += pStride;
+        if (++sc == NSC) { sc = 0; pc ^= 1u; cOff = 0; }
+        if (++k == K) { k = 0; pk ^= 1u; pOff = 0; }
         if (++kk == R) {
             kk = 0; n++;
             if (++nm == NB) nm = 0;
@@ -367,7 +397,7 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
 
 template <int NREG> struct SweepMaxThreads { static const int value = NREG >= 12 ? 768 : 1024; };
 
-template <int NREG, int LPC>
+template <int NREG, int LPC, bool SAT>
 __global__ void __launch_bounds__(SweepMaxThreads<NREG>::value, 1) k_sweep(SweepArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -387,11 +417,11 @@ __global__ void __launch_bounds__(SweepMaxThreads<NREG>::value, 1) k_sweep(Sweep
     }
     __syncthreads();
     if (warp < a.nwV) {
-        sweep_role_v<NREG, LPC>(a, s, warp, xe - xs, nRows);
+        sweep_role_v<NREG, LPC, SAT>(a, s, warp, xe - xs, nRows);
     } else if (warp < a.nwV + a.nwA) {
-        sweep_role_diag<NREG, LPC, +1>(a, s, warp - a.nwV, strip, xs, xe, yBegin, yStep, nRows);
+        sweep_role_diag<NREG, LPC, +1, SAT>(a, s, warp - a.nwV, strip, xs, xe, yBegin, yStep, nRows);
     } else if (warp < a.nwV + 2 * a.nwA) {
-        sweep_role_diag<NREG, LPC, -1>(a, s, warp - a.nwV - a.nwA, strip, xs, xe, yBegin, yStep, nRows);
+        sweep_role_diag<NREG, LPC, -1, SAT>(a, s, warp - a.nwV - a.nwA, strip, xs, xe, yBegin, yStep, nRows);
     } else if ((threadIdx.x & 31) == 0) {
         sweep_producer(a, s, xs, xe, yBegin, yStep, nRows);
     }
@@ -416,12 +446,12 @@ static size_t sweep_layout(SweepArgs &a, int groupsC, bool wta)
 
 // Returns 0 on success, 1 if this geometry does not fit the role-specialised sweep (the caller falls
 // back to k_vertical), negative on error.
-template <int NREG, int LPC>
+template <int NREG, int LPC, bool SAT>
 static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
 {
     constexpr int GPW = 32 / LPC;
     const Geo &g = va.g;
-    auto kern = k_sweep<NREG, LPC>;
+    auto kern = k_sweep<NREG, LPC, SAT>;
     static bool attrDone = false;
     static int maxSmem = 0;
     if (!attrDone) {
@@ -486,12 +516,20 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
     return 0;
 }
 
-#define SWEEP_DISPATCH(NREG_, LPC_) \
-    if (g.nreg == NREG_ && g.lpc == LPC_) return launch_sweep_t<NREG_, LPC_>(a, numSMs, st);
+#define SWEEP_DISPATCH(NREG_, LPC_)                                                               \
+    if (g.nreg == NREG_ && g.lpc == LPC_)                                                         \
+        return sat ? launch_sweep_t<NREG_, LPC_, true>(a, numSMs, st) : launch_sweep_t<NREG_, LPC_, false>(a, numSMs, st);
 
 int sgbm_launch_sweep(const VertArgs &a, int numSMs, cudaStream_t st)
 {
     const Geo &g = a.g;
+    // Largest value the sum over all paths of the mode can reach (A.2-A.4): every path cost is
+    // <= C + P2 and C <= cn * (2r+1)^2 * (max BT cost of the gradient plane + (255 >> 2)).
+    const long long pixMax = (long long)(2 * g.ftzero < 255 ? 2 * g.ftzero : 255) + 63;
+    const long long cMax = (long long)g.cn * (2 * g.r + 1) * (2 * g.r + 1) * pixMax;
+    const int npaths = g.mode == 1 ? 8 : 5;
+    bool sat = npaths * (cMax + g.P2) > 65535;
+    if (const char *e = getenv("SGBM_SWEEP_SAT")) sat = sat || atoi(e) != 0;
     SWEEP_DISPATCH(4, 2) SWEEP_DISPATCH(4, 4) SWEEP_DISPATCH(4, 8) SWEEP_DISPATCH(4, 16) SWEEP_DISPATCH(4, 32)
     SWEEP_DISPATCH(8, 2) SWEEP_DISPATCH(8, 4) SWEEP_DISPATCH(8, 8) SWEEP_DISPATCH(8, 16) SWEEP_DISPATCH(8, 32)
     SWEEP_DISPATCH(12, 2) SWEEP_DISPATCH(12, 4) SWEEP_DISPATCH(12, 8) SWEEP_DISPATCH(12, 16) SWEEP_DISPATCH(12, 32)
