@@ -15,6 +15,9 @@
 // ---- launchers implemented in the other translation units -------------------------------------
 int sgbm_launch_prefilter(const Geo &g, const uint8_t *left, const uint8_t *right, long long pitch, uint8_t *planes, cudaStream_t st);
 int sgbm_launch_cost(const Geo &g, const uint8_t *planes, uint16_t *out, int y0, int nrows, int ylo, int zeroTail, cudaStream_t st);
+int sgbm_launch_prefilter2(const Geo &g, const uint8_t *left, const uint8_t *right, long long pitch, uint8_t *planes, cudaStream_t st);
+int sgbm_launch_cost2(const Geo &g, const uint8_t *planes, uint16_t *out, int y0, int nrows, int ylo, int zeroTail, cudaStream_t st);
+size_t sgbm_cost2_planes_bytes(const Geo &g);
 int sgbm_launch_horizontal(const Geo &g, const uint16_t *C, uint16_t *LhA, uint16_t *LhB, int y0, int nrows, cudaStream_t st);
 int sgbm_launch_vertical(VertArgs &a, int ndir, int numSMs, cudaStream_t st);
 int sgbm_launch_fill_i16(int16_t *p, size_t n, int v, cudaStream_t st);
@@ -164,7 +167,10 @@ static void ws_layout(const Geo &g, const sgbm_params &p, int numSMs, int keep, 
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     size_t vol = (size_t)g.rowStride * g.H * 2;
-    L.planes = take((size_t)2 * g.cn * 6 * g.W * g.H);
+    {   // prefilter output: the larger of the two generations' formats (sgbm_cost.cu / sgbm_cost2.cu)
+        const size_t v1 = (size_t)2 * g.cn * 6 * g.W * g.H, v2 = sgbm_cost2_planes_bytes(g);
+        L.planes = take(v1 > v2 ? v1 : v2);
+    }
     L.C = take(vol);
     L.LhA = take(vol);
     L.LhB = take(vol);
@@ -287,9 +293,22 @@ static int compute_frame(sgbm_handle *h, const Geo &g, const WsLayout &L, const 
     unsigned int *d2key = (unsigned int *)(base + L.d2key);
     int rc;
     if ((rc = prof_mark(h, ST_START, st))) return rc;
-    if ((rc = sgbm_launch_prefilter(g, left, right, pitch, planes, st))) return rc;
-    if ((rc = prof_mark(h, ST_PREFILTER, st))) return rc;
-    if ((rc = sgbm_launch_cost(g, planes, C, 0, g.H, 0, p.mode == SGBM_MODE_HH4, st))) return rc;
+    // second-generation prefilter + cost kernels (sgbm_cost2.cu); the first generation stays as the
+    // fallback for geometries the new kernel does not hold (rc == 1) and for A/B runs (SGBM_COST2=0)
+    bool cost2 = true;
+    if (const char *e = getenv("SGBM_COST2")) cost2 = atoi(e) != 0;
+    if (cost2) {
+        if ((rc = sgbm_launch_prefilter2(g, left, right, pitch, planes, st))) return rc;
+        if ((rc = prof_mark(h, ST_PREFILTER, st))) return rc;
+        rc = sgbm_launch_cost2(g, planes, C, 0, g.H, 0, p.mode == SGBM_MODE_HH4, st);
+        if (rc < 0) return rc;
+        if (rc == 1) cost2 = false;
+    }
+    if (!cost2) {
+        if ((rc = sgbm_launch_prefilter(g, left, right, pitch, planes, st))) return rc;
+        if ((rc = prof_mark(h, ST_PREFILTER, st))) return rc;
+        if ((rc = sgbm_launch_cost(g, planes, C, 0, g.H, 0, p.mode == SGBM_MODE_HH4, st))) return rc;
+    }
     if ((rc = prof_mark(h, ST_COST, st))) return rc;
     const int ss = (g.H + 3) / 4;
     int ov = 0;
@@ -301,7 +320,9 @@ static int compute_frame(sgbm_handle *h, const Geo &g, const WsLayout &L, const 
             int s0 = o0 - ov > 0 ? o0 - ov : 0;
             if (s0 == 0) continue;
             int nr = g.r < g.H - s0 ? g.r : g.H - s0;
-            if ((rc = sgbm_launch_cost(g, planes, Calt + (size_t)(n - 1) * g.r * g.rowStride, s0, nr, s0, 0, st))) return rc;
+            uint16_t *dst = Calt + (size_t)(n - 1) * g.r * g.rowStride;
+            rc = cost2 ? sgbm_launch_cost2(g, planes, dst, s0, nr, s0, 0, st) : sgbm_launch_cost(g, planes, dst, s0, nr, s0, 0, st);
+            if (rc) return rc < 0 ? rc : sgbm_fail(SGBM_E_UNSUPPORTED, "cost kernel geometry changed between launches");
         }
     }
     if (p.mode == SGBM_MODE_SGBM_3WAY && (rc = prof_mark(h, ST_COST_ALT, st))) return rc;
