@@ -42,6 +42,7 @@ struct SweepArgs {
     uint16_t *haloA, *haloC;         // [nstrips][4][R][Dp + 8]
     unsigned int *flagA, *flagC;     // [nstrips][R] super-steps published per column
     int dbgNoSync;
+    unsigned int urMagic;            // floor(2^32 / (100 - uniquenessRatio)) + 1
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
@@ -71,7 +72,7 @@ __device__ __forceinline__ void load_vec_l2(uint32_t (&v)[NREG], const uint16_t 
 
 struct SweepSmem {
     uint16_t *stgC, *stgI, *P, *ssm;
-    uint64_t *fullC, *emptyC, *fullI, *emptyI, *fullV, *fullA, *freeP;
+    uint64_t *fullC, *emptyC, *fullI, *emptyI, *fullV, *fullM, *freeP;
 };
 __device__ __forceinline__ SweepSmem sweep_carve(const SweepArgs &a, uint8_t *smem)
 {
@@ -86,7 +87,7 @@ __device__ __forceinline__ SweepSmem sweep_carve(const SweepArgs &a, uint8_t *sm
     s.fullI = b; b += a.NSI;
     s.emptyI = b; b += a.NSI;
     s.fullV = b; b += a.K;
-    s.fullA = b; b += a.K;
+    s.fullM = b; b += a.K;
     s.freeP = b;
     return s;
 }
@@ -186,30 +187,36 @@ __device__ __forceinline__ void sweep_role_v(const SweepArgs &a, const SweepSmem
 }
 
 // ---- winner-take-all of one pixel (A.5), S distributed over the lane group --------------------------
+// Minimum and first arg-minimum come out of ONE reduction over 32-bit keys (S << 16 | d): the key
+// order is the order "(cost, disparity)", so the smallest key is the first minimum.  The
+// uniqueness scan re-reads S from shared scratch with the window around the winner masked and
+// combines the lanes' verdicts with one ballot.
 template <int NREG, int LPC>
 __device__ __forceinline__ void sweep_wta(const SweepArgs &a, const uint32_t (&S)[NREG], uint16_t *ssm, int lg, bool own,
                                           int x1, int y)
 {
     const Geo &g = a.g;
     const int lastLane = g.lanesUsed - 1;
-    uint32_t tm = local_min<NREG>(S);
-    if (lg > lastLane) tm = SGBM_INF2;
-    const uint32_t mS2 = group_min<LPC>(tm);
-    const int minS = (int)(mS2 & 0xFFFFu);
-    int idx = 0x7FFF;
-#pragma unroll
-    for (int j = NREG - 1; j >= 0; j--) {
-        const uint32_t e = S[j] ^ mS2;
-        if ((e >> 16) == 0) idx = 2 * j + 1;
-        if ((e & 0xFFFFu) == 0) idx = 2 * j;
-    }
-    int dl = (lg <= lastLane && idx != 0x7FFF) ? lg * 2 * NREG + idx : 0x7FFF;
-#pragma unroll
-    for (int off = LPC / 2; off >= 1; off >>= 1) dl = min(dl, __shfl_xor_sync(0xFFFFFFFFu, dl, off, LPC));
-    const int best = (minS == 32767) ? -1 : dl;                         // first minimum (A.5)
-    // S to shared scratch: sub-pixel neighbours and the masked uniqueness scan
     __syncwarp();
-    store_vec<NREG, LPC>(S, ssm, lg);
+    store_vec<NREG, LPC>(S, ssm, lg);                     // scratch for the sub-pixel neighbours / masked re-scan
+    uint32_t km[NREG];
+#pragma unroll
+    for (int j = 0; j < NREG; j++) {
+        const uint32_t idx2 = (uint32_t)(2 * j) | ((uint32_t)(2 * j + 1) << 16);
+        const uint32_t klo = __byte_perm(S[j], idx2, 0x1054);           // S(2j)   << 16 | 2j
+        const uint32_t khi = __byte_perm(S[j], idx2, 0x3276);           // S(2j+1) << 16 | 2j+1
+        km[j] = min(klo, khi);
+    }
+    uint32_t key = km[0];
+#pragma unroll
+    for (int j = 1; j + 1 < NREG; j += 2) key = __vimin3_u32(key, km[j], km[j + 1]);
+    if ((NREG & 1) == 0) key = min(key, km[NREG - 1]);
+    key += (uint32_t)(lg * 2 * NREG);                                   // lane-local index -> disparity
+    if (lg > lastLane) key = 0xFFFFFFFFu;
+#pragma unroll
+    for (int off = LPC / 2; off >= 1; off >>= 1) key = min(key, __shfl_xor_sync(0xFFFFFFFFu, key, off, LPC));
+    const int minS = (int)(key >> 16);
+    const int best = (minS == 32767) ? -1 : (int)(key & 0xFFFFu);       // first minimum (A.5)
     __syncwarp();
     int Sm = 0, Sp = 0;
     const bool interior = best > 0 && best < g.D - 1;
@@ -220,8 +227,9 @@ __device__ __forceinline__ void sweep_wta(const SweepArgs &a, const uint32_t (&S
     bool reject = false;
     if (g.UR > 0) {
         const int av = 100 - g.UR;                                       // S(d)*(100-UR) < minS*100  <=>  S(d) < T
-        const int T = av > 0 ? min((100 * minS + av - 1) / av, 32768) : (minS > 0 ? 32768 : 0);
-        __syncwarp();
+        // ceil(100*minS / av) by multiply-high with M = floor(2^32/av)+1: exact for numerators < 2^22
+        const unsigned num = (unsigned)(100 * minS + av - 1);
+        const int T = av > 0 ? min((int)(av == 1 ? num : __umulhi(num, a.urMagic)), 32768) : (minS > 0 ? 32768 : 0);
         if (lg == 0) {
 #pragma unroll
             for (int dd = -1; dd <= 1; dd++) {
@@ -232,10 +240,12 @@ __device__ __forceinline__ void sweep_wta(const SweepArgs &a, const uint32_t (&S
         __syncwarp();
         uint32_t S2[NREG];
         load_vec<NREG, LPC>(S2, ssm, lg);
-        uint32_t t2 = local_min<NREG>(S2);
-        if (lg > lastLane) t2 = SGBM_INF2;
-        const int m2 = (int)(group_min<LPC>(t2) & 0xFFFFu);
-        reject = m2 < T;
+        const uint32_t t2 = local_min<NREG>(S2);
+        const bool viol = lg <= lastLane && (int)(t2 & 0xFFFFu) < T;
+        const unsigned ball = __ballot_sync(0xFFFFFFFFu, viol);
+        const int lane = threadIdx.x & 31;
+        const unsigned gmask = (LPC == 32 ? 0xFFFFFFFFu : ((1u << LPC) - 1u)) << (lane & ~(LPC - 1));
+        reject = (ball & gmask) != 0u;
     }
     if (lg == 0 && own) {
         const int x = x1 + g.minX1;
@@ -247,7 +257,9 @@ __device__ __forceinline__ void sweep_wta(const SweepArgs &a, const uint32_t (&S
             int dq = best * 16;
             if (interior) {
                 const int den = max(Sm + Sp - 2 * minS, 1);
-                dq += ((Sm - Sp) * 16 + den) / (2 * den);
+                // C division (toward zero) through one IEEE float division: |num| < 2^20 and 2*den < 2^18 are
+                // exact floats and the rounded quotient cannot reach the next integer (error < 1/(2*den))
+                dq += (int)((float)((Sm - Sp) * 16 + den) / (float)(2 * den));
             }
             out = dq + g.minD * 16;
         }
@@ -261,6 +273,8 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
                                                 int xe, int yBegin, int yStep, int nRows)
 {
     constexpr int GPW = 32 / LPC;
+    // Fixed order V -> A -> C.  (Letting A and C take turns in finishing rows was measured and is slower:
+    // the alternation chains the two roles' rows into one serial sequence and destroys their pipelining.)
     constexpr bool FINAL = DIR < 0;
     const Geo &g = a.g;
     const int lane = threadIdx.x & 31, lg = lane % LPC;
@@ -280,7 +294,6 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
     const uint16_t *haloIn = (DIR > 0 ? a.haloA : a.haloC) + ((size_t)nbr * 4 * R + hidx) * haloStride;
     const unsigned int *flagIn = (DIR > 0 ? a.flagA : a.flagC) + (size_t)nbr * R + hidx;
     uint16_t *ssm = s.ssm + (size_t)gg * Dp;
-    uint64_t *waitBar = DIR > 0 ? s.fullV : s.fullA, *doneBar = DIR > 0 ? s.fullA : s.freeP;
 
     uint32_t L[NREG], m = 0;
 #pragma unroll
@@ -324,6 +337,7 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
             for (int j = 0; j < NREG; j++) L[j] = 0;
             m = 0;
         }
+        uint64_t *waitBar = FINAL ? s.fullM : s.fullV, *doneBar = FINAL ? s.freeP : s.fullM;
         if (!okC) mbar_wait(&s.fullC[sc], pc);
         const bool okS = mbar_test_wait(&waitBar[k], pk);  // latency hides behind the path step
         {
@@ -412,7 +426,7 @@ __global__ void __launch_bounds__(SweepMaxThreads<NREG>::value, 1) k_sweep(Sweep
         const int nCons = a.nwV + 2 * a.nwA;
         for (int q = 0; q < a.NSC; q++) { mbar_init(&s.fullC[q], 1); mbar_init(&s.emptyC[q], nCons); }
         for (int q = 0; q < a.NSI; q++) { mbar_init(&s.fullI[q], 1); mbar_init(&s.emptyI[q], a.nwV); }
-        for (int q = 0; q < a.K; q++) { mbar_init(&s.fullV[q], a.nwV); mbar_init(&s.fullA[q], a.nwA); mbar_init(&s.freeP[q], a.nwA); }
+        for (int q = 0; q < a.K; q++) { mbar_init(&s.fullV[q], a.nwV); mbar_init(&s.fullM[q], a.nwA); mbar_init(&s.freeP[q], a.nwA); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -467,6 +481,7 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
     a.d2key = va.d2key; a.backward = va.backward; a.haloA = va.haloA; a.haloC = va.haloC; a.flagA = va.flagA;
     a.flagC = va.flagC; a.dbgNoSync = va.dbgNoSync;
     a.nAB = va.inB ? 2 : 1;
+    a.urMagic = g.UR < 99 ? 0xFFFFFFFFu / (unsigned)(100 - g.UR) + 1u : 0u;
     const bool wta = va.sout == nullptr;
     const int maxThreads = SweepMaxThreads<NREG>::value;
     int R = 8;
