@@ -13,7 +13,8 @@ SYMBOLS = [
     "sgbm_set_params", "sgbm_get_params", "sgbm_workspace_bytes", "sgbm_compute", "sgbm_compute_host",
     "sgbm_disp_to_float", "sgbm_reproject_f32", "sgbm_reproject_i16", "sgbm_reproject_compact",
     "sgbm_reproject_compact_scratch_bytes", "sgbm_filter_speckles", "sgbm_median3x3",
-    "sgbm_debug_keep", "sgbm_debug_fetch", "sgbm_microbench_int16",
+    "sgbm_debug_keep", "sgbm_debug_fetch", "sgbm_microbench_int16", "sgbm_kernel_launches",
+    "sgbm_profile_enable", "sgbm_profile_read",
 ]
 
 

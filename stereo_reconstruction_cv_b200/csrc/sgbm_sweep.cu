@@ -25,6 +25,7 @@
 // index i -- restarts at super-steps n == b (mod NB) at halo position i, so at every row each
 // column of the strip is covered by exactly one chain.
 #include "sgbm_common.cuh"
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -43,7 +44,16 @@ struct SweepArgs {
     unsigned int *flagA, *flagC;     // [nstrips][R] super-steps published per column
     int dbgNoSync;
     unsigned int urMagic;            // floor(2^32 / (100 - uniquenessRatio)) + 1
+    unsigned long long *trace;       // debug: clock64 time stamps of one strip [row][role 4][8] (or null)
+    int traceStrip;
 };
+
+#define SWEEP_TR(ROLE, IDX, COND)                                                                          \
+    do {                                                                                                   \
+        if (a.trace && (COND) && (threadIdx.x & 31) == 0 && (int)blockIdx.x == a.traceStrip)                \
+            a.trace[((size_t)t * 4 + (ROLE)) * 8 + (IDX)] = (unsigned long long)clock64();                 \
+    } while (0)
+
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
@@ -105,7 +115,9 @@ __device__ __forceinline__ void sweep_producer(const SweepArgs &a, const SweepSm
     uint32_t pc = 0, pi = 0;
     for (int t = 0; t < nRows; t++) {
         const int y = yBegin + t * yStep;
+        SWEEP_TR(3, 0, true);
         if (t >= a.NSC) mbar_wait(&s.emptyC[sc], pc ^ 1u);
+        SWEEP_TR(3, 1, true);
         mbar_expect_tx(&s.fullC[sc], bytesC);
         bulk_g2s(s.stgC + ((size_t)sc * ngC + (clo - scol0)) * Dp, a.C + (size_t)y * g.rowStride + (size_t)clo * Dp, bytesC,
                  &s.fullC[sc]);
@@ -114,6 +126,7 @@ __device__ __forceinline__ void sweep_producer(const SweepArgs &a, const SweepSm
         mbar_expect_tx(&s.fullI[si], bytesI * (uint32_t)a.nAB);
         bulk_g2s(s.stgI + (size_t)(si * a.nAB + 0) * a.SW * Dp, a.inA + off, bytesI, &s.fullI[si]);
         if (a.nAB > 1) bulk_g2s(s.stgI + (size_t)(si * a.nAB + 1) * a.SW * Dp, a.inB + off, bytesI, &s.fullI[si]);
+        SWEEP_TR(3, 2, true);
         if (++sc == a.NSC) { sc = 0; pc ^= 1u; }
         if (++si == a.NSI) { si = 0; pi ^= 1u; }
     }
@@ -150,7 +163,9 @@ __device__ __forceinline__ void sweep_role_v(const SweepArgs &a, const SweepSmem
     bool okC = false;                                     // early probe of the next row's cost stage
     for (int t = 0; t < nRows; t++) {
         uint32_t S[NREG];
+        SWEEP_TR(0, 0, rwarp == 0);
         if (!okC) mbar_wait(&s.fullC[sc], pc);
+        SWEEP_TR(0, 1, rwarp == 0);
         // probes whose latency hides behind the path step
         const bool okI = mbar_test_wait(&s.fullI[si], pi);
         const bool okP = t >= K ? mbar_test_wait(&s.freeP[k], pk ^ 1u) : true;
@@ -161,6 +176,7 @@ __device__ __forceinline__ void sweep_role_v(const SweepArgs &a, const SweepSmem
             okC = t + 1 < nRows ? mbar_test_wait(&s.fullC[scN], scN ? pc : pc ^ 1u) : true;
             mB = path_step<NREG, LPC>(LB, LB, mB, Cc, P1p, P2mP1p, lg, lastLane);   // in place (reads run ahead of writes)
         }
+        SWEEP_TR(0, 2, rwarp == 0);
         if (!okI) mbar_wait(&s.fullI[si], pi);
         load_vec<NREG, LPC>(S, s.stgI + iOff, lg);
 #pragma unroll
@@ -171,7 +187,9 @@ __device__ __forceinline__ void sweep_role_v(const SweepArgs &a, const SweepSmem
 #pragma unroll
             for (int j = 0; j < NREG; j++) S[j] = sacc<SAT>(S[j], Bv[j]);
         }
+        SWEEP_TR(0, 3, rwarp == 0);
         if (!okP) mbar_wait(&s.freeP[k], pk ^ 1u);
+        SWEEP_TR(0, 4, rwarp == 0);
         if (own) store_vec<NREG, LPC>(S, s.P + pOff, lg);
         __syncwarp();
         if (lane == 0) {
@@ -179,6 +197,7 @@ __device__ __forceinline__ void sweep_role_v(const SweepArgs &a, const SweepSmem
             mbar_arrive(&s.emptyC[sc]);
             mbar_arrive(&s.emptyI[si]);
         }
+        SWEEP_TR(0, 5, rwarp == 0);
         cOff += cStride; iOff += iStride; pOff += pStride;
         if (++sc == NSC) { sc = 0; pc ^= 1u; cOff = cBase; }
         if (++si == NSI) { si = 0; pi ^= 1u; iOff = iBase; }
@@ -338,7 +357,9 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
             m = 0;
         }
         uint64_t *waitBar = FINAL ? s.fullM : s.fullV, *doneBar = FINAL ? s.freeP : s.fullM;
+        SWEEP_TR(DIR > 0 ? 1 : 2, 0, rwarp == a.nwA / 2);
         if (!okC) mbar_wait(&s.fullC[sc], pc);
+        SWEEP_TR(DIR > 0 ? 1 : 2, 1, rwarp == a.nwA / 2);
         const bool okS = mbar_test_wait(&waitBar[k], pk);  // latency hides behind the path step
         {
             const int scN = sc + 1 == NSC ? 0 : sc + 1;
@@ -367,7 +388,9 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
             }
         }
         // ---- S slot of this row ---------------------------------------------------------------------
+        SWEEP_TR(DIR > 0 ? 1 : 2, 2, rwarp == a.nwA / 2);
         if (!okS) mbar_wait(&waitBar[k], pk);
+        SWEEP_TR(DIR > 0 ? 1 : 2, 3, rwarp == a.nwA / 2);
         uint32_t S[NREG];
         if (own) {
             uint16_t *ps = s.P + pOff + (col - xs) * Dp;
@@ -384,6 +407,7 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
             mbar_arrive(&doneBar[k]);
             mbar_arrive(&s.emptyC[sc]);
         }
+        SWEEP_TR(DIR > 0 ? 1 : 2, 4, rwarp == a.nwA / 2);
         if (FINAL && __any_sync(0xFFFFFFFFu, own)) {
             const int y = yBegin + t * yStep;
             const int x1 = own ? col : xs;
@@ -398,6 +422,7 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
                 sweep_wta<NREG, LPC>(a, S, ssm, lg, own, x1, y);
             }
         }
+        SWEEP_TR(DIR > 0 ? 1 : 2, 5, rwarp == a.nwA / 2);
         p++;
         cOff += cStride; pOff += pStride;
         if (++sc == NSC) { sc = 0; pc ^= 1u; cOff = 0; }
@@ -525,9 +550,26 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
     if (occ * numSMs < a.nstrips) return 1;
     SGBM_CUDA_CHECK(cudaMemsetAsync(a.flagA, 0, sizeof(unsigned int) * 2 * (size_t)a.nstrips * 16, st));
     a.flagC = a.flagA + (size_t)a.nstrips * 16;
+    const char *tracePath = getenv("SGBM_SWEEP_TRACE");       // debug: dump one strip's time stamps to a file
+    const size_t traceBytes = (size_t)g.H * 4 * 8 * sizeof(unsigned long long);
+    if (tracePath) {
+        SGBM_CUDA_CHECK(cudaMalloc(&a.trace, traceBytes));
+        SGBM_CUDA_CHECK(cudaMemsetAsync(a.trace, 0, traceBytes, st));
+        a.traceStrip = a.nstrips / 2;
+    }
     void *args[] = {&a};
     SGBM_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)kern, dim3(a.nstrips), dim3(threads), args, smem, st));
     sgbm_count_launch(1);
+    if (tracePath) {
+        SGBM_CUDA_CHECK(cudaStreamSynchronize(st));
+        void *hbuf = malloc(traceBytes);
+        SGBM_CUDA_CHECK(cudaMemcpy(hbuf, a.trace, traceBytes, cudaMemcpyDeviceToHost));
+        if (FILE *f = fopen(tracePath, "wb")) { fwrite(hbuf, 1, traceBytes, f); fclose(f); }
+        free(hbuf);
+        cudaFree(a.trace);
+        fprintf(stderr, "sweep trace: H=%d strips=%d R=%d NB=%d nwV=%d nwA=%d K=%d NSC=%d NSI=%d threads=%d smem=%zu\n", g.H,
+                a.nstrips, a.R, a.NB, a.nwV, a.nwA, a.K, a.NSC, a.NSI, threads, smem);
+    }
     return 0;
 }
 

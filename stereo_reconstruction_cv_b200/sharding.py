@@ -1,0 +1,70 @@
+"""Frame sharding of a batch of stereo pairs over the GPUs of one box.
+
+The dense-stereo path shards by stereo pair / video frame only: vertical and diagonal SGM paths
+span the whole image, so there is nothing to exchange between GPUs while a frame is computed.
+One process per GPU (torchrun), a contiguous block of the batch per rank, NO collective on the
+data path.  The only optional exchange is the gather of the compacted point clouds (or the
+disparity maps) to one rank at the end: counts first, then a variable-length gather.
+
+The helpers take any torch.distributed backend: NCCL over NVLink on the GPU box, gloo in the CPU
+tests (tests/test_sharding.py, world_size 2).
+"""
+import numpy as np
+
+
+def shard_range(n_frames, world_size, rank):
+    """Contiguous block partition frames[g*B/G : (g+1)*B/G] of SURVEY.md 8(e) -> (start, stop)."""
+    if world_size < 1 or not (0 <= rank < world_size) or n_frames < 0:
+        raise ValueError("bad shard request: n_frames=%r world_size=%r rank=%r" % (n_frames, world_size, rank))
+    return (rank * n_frames) // world_size, ((rank + 1) * n_frames) // world_size
+
+
+def shard_ranges(n_frames, world_size):
+    return [shard_range(n_frames, world_size, r) for r in range(world_size)]
+
+
+def compute_shard(stereo, lefts, rights, world_size=1, rank=0, out=None):
+    """Disparity of this rank's block of a batch.
+
+    lefts / rights: sequences (or (B,H,W) arrays / CUDA tensors) indexed by global frame number.
+    Returns (start, stop, list_or_tensor_of_disparities).  CUDA tensors stay on the device."""
+    start, stop = shard_range(len(lefts), world_size, rank)
+    if hasattr(lefts, "is_cuda") and lefts.is_cuda and lefts.dim() >= 3:
+        return start, stop, stereo.compute(lefts[start:stop], rights[start:stop], out)
+    return start, stop, [stereo.compute(lefts[i], rights[i]) for i in range(start, stop)]
+
+
+def gather_varlen(t, dst=0, group=None):
+    """Gather first-dimension-ragged tensors (e.g. per-rank point clouds, N_r x 3) to rank `dst`.
+
+    Two steps: all-gather of the per-rank lengths (8 bytes each), then a gather
+    of buffers padded to the maximum length.  Returns the list of per-rank tensors on `dst` and
+    None elsewhere.  Without an initialised process group it degenerates to [t]."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return [t]
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c.item()) for c in counts]
+    nmax = max(counts) if counts else 0
+    pad = torch.zeros((nmax,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[: t.shape[0]] = t
+    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return [b[:c] for b, c in zip(bufs, counts)]
+
+
+def gather_point_cloud(xyz, rgb=None, dst=0, group=None):
+    """Concatenate the ranks' compacted clouds (reprojectCompact output) on rank `dst` in rank order,
+    i.e. in global frame order for block-sharded batches.  Returns (xyz, rgb) on dst, (None, None) elsewhere."""
+    import torch
+    px = gather_varlen(xyz, dst, group)
+    pc = gather_varlen(rgb, dst, group) if rgb is not None else None
+    if px is None:
+        return None, None
+    return torch.cat(px, 0), (torch.cat(pc, 0) if pc is not None else None)

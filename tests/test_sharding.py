@@ -1,0 +1,105 @@
+"""CPU tests of the multi-GPU host logic: block partition of a batch and the
+variable-length gather of point clouds, run with torch.distributed/gloo at world_size 2, plus the
+PLY writer of 8(f) n2."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from stereo_reconstruction_cv_b200 import pointcloud, sharding
+
+
+def test_shard_ranges_cover_batch():
+    for n in (0, 1, 7, 8, 512, 513):
+        for world in (1, 2, 3, 4, 8):
+            r = sharding.shard_ranges(n, world)
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:]))                # contiguous, ordered, no overlap
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
+    assert sharding.shard_ranges(512, 8) == [(64 * g, 64 * (g + 1)) for g in range(8)]
+    with pytest.raises(ValueError):
+        sharding.shard_range(4, 2, 2)
+
+
+class _FakeStereo:
+    """Stands in for StereoSGBM on the CPU: 'disparity' = left - right, so the test sees which frames ran."""
+
+    def compute(self, l, r, out=None):
+        return l.astype(np.int16) - r.astype(np.int16)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(0)
+        lefts = [rng.integers(0, 255, (4, 6), dtype=np.uint8) for _ in range(5)]
+        rights = [rng.integers(0, 255, (4, 6), dtype=np.uint8) for _ in range(5)]
+        start, stop, disps = sharding.compute_shard(_FakeStereo(), lefts, rights, world, rank)
+        assert (start, stop) == sharding.shard_range(5, world, rank) and len(disps) == stop - start
+        # ragged "point clouds": one point per frame pixel with positive fake disparity
+        pts = [np.argwhere(d > 0).astype(np.float32) for d in disps]
+        xyz = torch.from_numpy(np.concatenate([np.c_[p, np.full(len(p), start + i, np.float32)] for i, p in enumerate(pts)]))
+        rgb = torch.full((xyz.shape[0], 3), rank + 1, dtype=torch.uint8)
+        gx, gc = sharding.gather_point_cloud(xyz, rgb, dst=0)
+        if rank == 0:
+            ref = []
+            for i in range(5):
+                d = lefts[i].astype(np.int16) - rights[i].astype(np.int16)
+                p = np.argwhere(d > 0).astype(np.float32)
+                ref.append(np.c_[p, np.full(len(p), i, np.float32)])
+            ref = np.concatenate(ref)
+            assert np.array_equal(gx.numpy(), ref), "gathered cloud differs from the single-process result"
+            assert gc.shape[0] == ref.shape[0] and set(np.unique(gc.numpy())) <= {1, 2}
+            open(os.path.join(tmp, "ok"), "w").write("%d" % ref.shape[0])
+        else:
+            assert gx is None and gc is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_shard_and_gather(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert int(open(tmp_path / "ok").read()) > 0
+
+
+def test_gather_without_process_group():
+    t = torch.arange(6, dtype=torch.float32).reshape(2, 3)
+    assert sharding.gather_varlen(t)[0] is t
+
+
+def test_ply_round_trip(tmp_path):
+    rng = np.random.default_rng(1)
+    xyz = rng.normal(size=(4, 5, 3)).astype(np.float32)
+    xyz[0, 0, 0] = np.inf
+    xyz[1, 2, 2] = -np.inf
+    rgb = rng.integers(0, 256, (4, 5, 3), dtype=np.uint8)
+    n = pointcloud.write_ply(tmp_path / "a.ply", xyz, rgb)
+    assert n == 18
+    x, c = pointcloud.read_ply(tmp_path / "a.ply")
+    ok = np.isfinite(xyz.reshape(-1, 3)).all(1)
+    assert x.dtype == np.float64 and np.array_equal(x, xyz.reshape(-1, 3)[ok].astype(np.float64))
+    assert np.array_equal(c, rgb.reshape(-1, 3)[ok])
+    # the reference's second call site writes every pixel, non-finite included (main.ipynb:796)
+    assert pointcloud.write_ply(tmp_path / "b.ply", xyz, keep_nonfinite=True, dtype=np.float32) == 20
+    x2, c2 = pointcloud.read_ply(tmp_path / "b.ply")
+    assert c2 is None and x2.dtype == np.float32 and np.array_equal(np.isfinite(x2), np.isfinite(xyz.reshape(-1, 3)))
+    pts, col = pointcloud.open3d_arrays(xyz, rgb)
+    assert pts.dtype == np.float64 and col.dtype == np.float64 and col.max() <= 1.0
+    hdr = open(tmp_path / "a.ply", "rb").read(200).decode("ascii", "ignore")
+    assert hdr.startswith("ply\nformat binary_little_endian 1.0") and "property double x" in hdr
