@@ -217,14 +217,22 @@ def run_product(args, W, H, D, mode, modename):
     dev = torch.device("cuda", local)
     L = _lib.lib()
 
-    l, r = make_inputs(W, H, D, seed=rank)                      # every rank owns its own frame
-    lt, rt = torch.from_numpy(l).to(dev), torch.from_numpy(r).to(dev)
+    # Every rank owns its own frames (block sharding of the batch, sharding.shard_range): a pool of
+    # `pool` distinct synthetic pairs per rank, resident in HBM, visited round-robin by the steps.
+    pool = max(1, min(args.pool, args.steps + max(args.warmup, 3)))
+    frames = [make_inputs(W, H, D, seed=rank * pool + i) for i in range(pool)]
+    l, r = frames[0]
+    lts = [torch.from_numpy(f[0]).to(dev) for f in frames]
+    rts = [torch.from_numpy(f[1]).to(dev) for f in frames]
     st = sg.StereoSGBM_create(numDisparities=D, mode=mode, **PARAMS)
     out = torch.empty((H, W), dtype=torch.int16, device=dev)
     with_reproject = args.workload == "cfg5"
+    counter = [0]
 
     def step_device():
-        st.compute(lt, rt, out)
+        i = counter[0] % pool
+        counter[0] += 1
+        st.compute(lts[i], rts[i], out)
         if with_reproject:
             return sg.reprojectCompact(out, NOTEBOOK_Q)
         return None
@@ -289,6 +297,7 @@ def run_product(args, W, H, D, mode, modename):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = evals_step * e2e_steps * world / float(t.item()) / 1e6
+    st.compute(lts[0], rts[0], out)
     same = bool((torch.from_numpy(res).to(dev) == out).all().item())
 
     if rank == 0:
@@ -301,13 +310,24 @@ def run_product(args, W, H, D, mode, modename):
                "vertical_wta": 4 if mode in (1, 3) else 6}.get(dom, 0)
         roof = None
         alu = None
+        traffic = None
+        try:                                                 # dram bytes per launch from the committed `ncu --set full` capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tj.get(args.workload, {}).get(dom)
+        except Exception:
+            pass
         if dom:
             dom_ms = stages[dom]["ms"]
             ach = bpe * elems / (dom_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
+                    "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
                     "kernel_ms": dom_ms, "share_of_step": dom_ms / (ms / args.steps),
                     "algorithmic_bytes_per_launch": bpe * elems}
+            # whole pipeline: sum of the stages' algorithmic bytes over the step time
+            pipe_bpe = {0: 16, 1: 22, 2: 16, 3: 22}[mode]
+            roof["pipeline"] = {"algorithmic_bytes_per_step": pipe_bpe * elems,
+                                "achieved": pipe_bpe * elems / (ms / args.steps * 1e-3) / 1e9,
+                                "frac": pipe_bpe * elems / (ms / args.steps * 1e-3) / 1e9 / peaks["hbm_gbs"]}
             try:
                 mix = sg.microbench_int16(6)               # G lane-ops/s of the path-step instruction mix
                 ops_per_elem = {"horizontal": 2 * 3.3, "vertical_fwd": 3 * 3.3, "vertical_wta": 3 * 3.3 + 1.5,
@@ -330,6 +350,7 @@ def run_product(args, W, H, D, mode, modename):
                            "frames_per_s": args.steps * world / (ms_max * 1e-3),
                            "l2": "no flush: each step streams the %.1f GB cost/path volumes (>> 126 MB L2)"
                                  % (3 * elems * 2 / 1e9),
+                           "frame_pool": "%d distinct synthetic pairs per GPU (seeds rank*%d..), resident in HBM, round-robin" % (pool, pool),
                            "parallelism": "frames sharded over %d GPU(s), no collective" % world},
                 "e2e": {"value": e2e_value, "unit": "MDE/s", "h2d_bytes_per_step": int(2 * W * H),
                         "d2h_bytes_per_step": int(2 * W * H), "steps": e2e_steps, "matches_device_path": same},
@@ -353,6 +374,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--pool", type=int, default=4, help="distinct synthetic pairs per GPU visited round-robin")
     args = ap.parse_args()
     W, H, D, mode, modename, _ = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -129,7 +129,8 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity)
     return ok != 0;
 }
 // Blocking wait.  The retry passes a suspend-time hint so that a waiting warp sleeps in hardware
-// instead of burning issue slots in a poll loop; ~5 s without progress traps (protocol error).
+// instead of burning issue slots in a poll loop; ~80 s without progress traps (protocol error; the
+// bound is generous because profilers that patch the kernel slow it down by orders of magnitude).
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     if (mbar_try_wait(bar, parity)) return;
@@ -142,7 +143,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
         "@p bra SGBM_DONE;\n\t"
         "add.u32 n, n, 1;\n\t"
-        "setp.lt.u32 p, n, 512;\n\t"
+        "setp.lt.u32 p, n, 8192;\n\t"
         "@p bra SGBM_WAIT;\n\t"
         "trap;\n"
         "SGBM_DONE:\n\t"

@@ -332,7 +332,7 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
                     unsigned int spins = 0;
                     while (ld_acquire_u32(flagIn) < (unsigned)n) {
                         __nanosleep(32);
-                        if (++spins > (1u << 24)) __trap();
+                        if (++spins > (1u << 28)) __trap();
                     }
                 }
                 __syncwarp();

@@ -13,4 +13,4 @@ for r,(nm,npts) in enumerate(zip(names,[6,6,6,3])):
 x=a[lo:hi]-t0
 print('lag V.arrive->A.slotwait done', (x[:,1,3]-x[:,0,5]).mean(), ' A.arrive->C.slot done',(x[:,2,3]-x[:,1,4]).mean(), ' C.arrive->V.freeP(row+K)?')
 for K in (1,2,3,4): print('  K=%d: V.t4(row+K)-C.t4(row): %.0f'%(K,(x[K:,0,4]-x[:-K,2,4]).mean()))
-print('total cycles/row', (a[hi,2,5]-a[lo,2,5])/(hi-lo))
+print("total cycles/row", (a[hi-1,2,5]-a[lo,2,5])/(hi-1-lo))
