@@ -1,3 +1,3 @@
 cd /root/repo
-timeout 300 python bench.py --workload cfg3 --steps 1 --warmup 3 > gpurun_out/plain.log 2>&1 && timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_sweep' -s 2 -c 2 -o gpurun_out/prof_r1e_sweep -f python bench.py --workload cfg3 --steps 1 --warmup 3 > gpurun_out/ncu_fs.log 2>&1
-grep -E "Profiling|ERROR" gpurun_out/ncu_fs.log
+SGBM_SWEEP_TRACE=gpurun_out/trace_cfg2.bin timeout 120 python bench.py --workload cfg2 --steps 1 --warmup 3 2>&1 | grep "sweep trace" | tail -1
+SGBM_SWEEP_TRACE=gpurun_out/trace_cfg3.bin timeout 120 python bench.py --workload cfg3 --steps 1 --warmup 3 2>&1 | grep "sweep trace" | tail -2

@@ -292,8 +292,11 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
                                                 int xe, int yBegin, int yStep, int nRows)
 {
     constexpr int GPW = 32 / LPC;
-    // Fixed order V -> A -> C.  (Letting A and C take turns in finishing rows was measured and is slower:
-    // the alternation chains the two roles' rows into one serial sequence and destroys their pipelining.)
+    // Fixed order V -> A -> C, role C finishes the pixel.  Two alternatives were built and measured
+    // (4K, D=256, WTA sweep 4.1 ms) and are slower: letting A and C take turns in finishing rows chains
+    // the two roles' rows into one serial sequence (5.5 ms); moving the winner-take-all tail onto roles
+    // V / A (even / odd rows) couples V and A row by row through the slot release and the SM's ALU pipe
+    // is already 55 % busy, so the freed time of role C cannot be used (7.0 ms).
     constexpr bool FINAL = DIR < 0;
     const Geo &g = a.g;
     const int lane = threadIdx.x & 31, lg = lane % LPC;
