@@ -64,10 +64,12 @@ struct sgbm_handle {
     // device workspace (grown on demand)
     void *ws = nullptr;
     size_t wsBytes = 0;
-    // pinned + device staging for the _host entry point
-    void *hostIn = nullptr, *hostOut = nullptr, *devIn = nullptr, *devOut = nullptr;
-    size_t hostInBytes = 0, hostOutBytes = 0, devInBytes = 0, devOutBytes = 0;
-    cudaStream_t ownStream = nullptr;
+    // pinned + device staging for the _host entry point: two slots so that the host copies and the
+    // PCIe transfers of frame b+1 / b-1 overlap the kernels of frame b
+    void *hostIn[2] = {nullptr, nullptr}, *hostOut[2] = {nullptr, nullptr}, *devIn[2] = {nullptr, nullptr}, *devOut[2] = {nullptr, nullptr};
+    size_t hostInBytes[2] = {0, 0}, hostOutBytes[2] = {0, 0}, devInBytes[2] = {0, 0}, devOutBytes[2] = {0, 0};
+    cudaStream_t ownStream = nullptr, inStream = nullptr, outStream = nullptr;
+    cudaEvent_t evIn[2] = {nullptr, nullptr}, evComp[2] = {nullptr, nullptr}, evOut[2] = {nullptr, nullptr};
     // debug
     int keep = 0;
     Geo lastGeo{};
@@ -226,11 +228,18 @@ extern "C" int sgbm_destroy(sgbm_handle *h)
 {
     if (!h) return 0;
     if (h->ws) cudaFree(h->ws);
-    if (h->devIn) cudaFree(h->devIn);
-    if (h->devOut) cudaFree(h->devOut);
-    if (h->hostIn) cudaFreeHost(h->hostIn);
-    if (h->hostOut) cudaFreeHost(h->hostOut);
+    for (int i = 0; i < 2; i++) {
+        if (h->devIn[i]) cudaFree(h->devIn[i]);
+        if (h->devOut[i]) cudaFree(h->devOut[i]);
+        if (h->hostIn[i]) cudaFreeHost(h->hostIn[i]);
+        if (h->hostOut[i]) cudaFreeHost(h->hostOut[i]);
+        if (h->evIn[i]) cudaEventDestroy(h->evIn[i]);
+        if (h->evComp[i]) cudaEventDestroy(h->evComp[i]);
+        if (h->evOut[i]) cudaEventDestroy(h->evOut[i]);
+    }
     if (h->ownStream) cudaStreamDestroy(h->ownStream);
+    if (h->inStream) cudaStreamDestroy(h->inStream);
+    if (h->outStream) cudaStreamDestroy(h->outStream);
     for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
     delete h;
     return 0;
@@ -427,33 +436,67 @@ extern "C" int sgbm_compute_host(sgbm_handle *h, const uint8_t *left, const uint
     Geo g;
     int rc = make_geo(h->p, W, H, channels, g);
     if (rc) return rc;
-    if (!h->ownStream) SGBM_CUDA_CHECK(cudaStreamCreateWithFlags(&h->ownStream, cudaStreamNonBlocking));
+    if (!h->ownStream) {
+        SGBM_CUDA_CHECK(cudaStreamCreateWithFlags(&h->ownStream, cudaStreamNonBlocking));
+        SGBM_CUDA_CHECK(cudaStreamCreateWithFlags(&h->inStream, cudaStreamNonBlocking));
+        SGBM_CUDA_CHECK(cudaStreamCreateWithFlags(&h->outStream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            SGBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->evIn[i], cudaEventDisableTiming));
+            SGBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->evComp[i], cudaEventDisableTiming));
+            SGBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->evOut[i], cudaEventDisableTiming));
+        }
+    }
     cudaStream_t st = h->ownStream;
     const size_t rowIn = (size_t)W * channels, frameIn = rowIn * H, frameOut = (size_t)W * H * 2;
-    // frames are staged one pair at a time through pinned memory (dense rows)
-    if ((rc = ensure_buf(&h->hostIn, &h->hostInBytes, 2 * frameIn, true))) return rc;
-    if ((rc = ensure_buf(&h->hostOut, &h->hostOutBytes, frameOut, true))) return rc;
-    if ((rc = ensure_buf(&h->devIn, &h->devInBytes, 2 * frameIn, false))) return rc;
-    if ((rc = ensure_buf(&h->devOut, &h->devOutBytes, frameOut, false))) return rc;
+    const int nslots = batch > 1 ? 2 : 1;
+    for (int i = 0; i < nslots; i++) {
+        if ((rc = ensure_buf(&h->hostIn[i], &h->hostInBytes[i], 2 * frameIn, true))) return rc;
+        if ((rc = ensure_buf(&h->hostOut[i], &h->hostOutBytes[i], frameOut, true))) return rc;
+        if ((rc = ensure_buf(&h->devIn[i], &h->devInBytes[i], 2 * frameIn, false))) return rc;
+        if ((rc = ensure_buf(&h->devOut[i], &h->devOutBytes[i], frameOut, false))) return rc;
+    }
     WsLayout L;
     ws_layout(g, h->p, h->numSMs, h->keep, L);
     if ((rc = ensure_ws(h, L.total, st))) return rc;
-    for (int b = 0; b < batch; b++) {
-        const uint8_t *l = left + (size_t)b * pitch_bytes * H, *r = right + (size_t)b * pitch_bytes * H;
-        uint8_t *hi = (uint8_t *)h->hostIn;
-        for (int y = 0; y < H; y++) {
-            memcpy(hi + (size_t)y * rowIn, l + (size_t)y * pitch_bytes, rowIn);
-            memcpy(hi + frameIn + (size_t)y * rowIn, r + (size_t)y * pitch_bytes, rowIn);
-        }
-        SGBM_CUDA_CHECK(cudaMemcpyAsync(h->devIn, h->hostIn, 2 * frameIn, cudaMemcpyHostToDevice, st));
-        rc = compute_frame(h, g, L, (const uint8_t *)h->devIn, (const uint8_t *)h->devIn + frameIn, (long long)rowIn,
-                           (int16_t *)h->devOut, W, st);
-        if (rc) return rc;
-        SGBM_CUDA_CHECK(cudaMemcpyAsync(h->hostOut, h->devOut, frameOut, cudaMemcpyDeviceToHost, st));
-        SGBM_CUDA_CHECK(cudaStreamSynchronize(st));
+    // Frames are staged through pinned memory (dense rows).  Three streams: H2D, kernels, D2H; while the
+    // kernels of frame b run, the host copies frame b+1 into the other slot and frame b-1 out of it.
+    auto drain = [&](int b) -> int {                      // wait for frame b's D2H and hand the rows to the caller
+        const int sl = b & 1;
+        SGBM_CUDA_CHECK(cudaEventSynchronize(h->evOut[sl]));
         uint8_t *o = (uint8_t *)disp_out + (size_t)b * out_pitch_bytes * H;
-        for (int y = 0; y < H; y++) memcpy(o + (size_t)y * out_pitch_bytes, (uint8_t *)h->hostOut + (size_t)y * W * 2, (size_t)W * 2);
+        if ((size_t)out_pitch_bytes == (size_t)W * 2) memcpy(o, h->hostOut[sl], frameOut);
+        else
+            for (int y = 0; y < H; y++) memcpy(o + (size_t)y * out_pitch_bytes, (uint8_t *)h->hostOut[sl] + (size_t)y * W * 2, (size_t)W * 2);
+        return 0;
+    };
+    for (int b = 0; b < batch; b++) {
+        const int sl = nslots == 2 ? (b & 1) : 0;
+        if (b >= 2 && (rc = drain(b - 2))) return rc;     // frees slot sl (its kernels and D2H are complete)
+        const uint8_t *l = left + (size_t)b * pitch_bytes * H, *r = right + (size_t)b * pitch_bytes * H;
+        uint8_t *hi = (uint8_t *)h->hostIn[sl];
+        if ((size_t)pitch_bytes == rowIn) {
+            memcpy(hi, l, frameIn);
+            memcpy(hi + frameIn, r, frameIn);
+        } else {
+            for (int y = 0; y < H; y++) {
+                memcpy(hi + (size_t)y * rowIn, l + (size_t)y * pitch_bytes, rowIn);
+                memcpy(hi + frameIn + (size_t)y * rowIn, r + (size_t)y * pitch_bytes, rowIn);
+            }
+        }
+        SGBM_CUDA_CHECK(cudaMemcpyAsync(h->devIn[sl], h->hostIn[sl], 2 * frameIn, cudaMemcpyHostToDevice, h->inStream));
+        SGBM_CUDA_CHECK(cudaEventRecord(h->evIn[sl], h->inStream));
+        SGBM_CUDA_CHECK(cudaStreamWaitEvent(st, h->evIn[sl], 0));
+        rc = compute_frame(h, g, L, (const uint8_t *)h->devIn[sl], (const uint8_t *)h->devIn[sl] + frameIn, (long long)rowIn,
+                           (int16_t *)h->devOut[sl], W, st);
+        if (rc) return rc;
+        SGBM_CUDA_CHECK(cudaEventRecord(h->evComp[sl], st));
+        SGBM_CUDA_CHECK(cudaStreamWaitEvent(h->outStream, h->evComp[sl], 0));
+        SGBM_CUDA_CHECK(cudaMemcpyAsync(h->hostOut[sl], h->devOut[sl], frameOut, cudaMemcpyDeviceToHost, h->outStream));
+        SGBM_CUDA_CHECK(cudaEventRecord(h->evOut[sl], h->outStream));
     }
+    for (int b = batch >= 2 ? batch - 2 : 0; b < batch; b++)
+        if ((rc = drain(b))) return rc;
+    SGBM_CUDA_CHECK(cudaStreamSynchronize(st));
     return 0;
 }
 

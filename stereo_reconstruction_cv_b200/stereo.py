@@ -126,6 +126,27 @@ class StereoSGBM:
             return disparity
         return out
 
+    def compute_batch(self, lefts, rights, disparity=None):
+        """Disparity of B independent pairs: numpy uint8 (B,H,W) or (B,H,W,3) -> numpy int16 (B,H,W).
+
+        One call into the C ABI's host entry point with batch = B: frames are double-buffered through
+        pinned memory, so the host copies and the H2D / D2H transfers of neighbouring frames overlap the
+        kernels (video / batch use; cv2 has no counterpart, the reference loops over compute())."""
+        if _is_tensor(lefts):
+            return self._compute_torch(lefts, rights, disparity)
+        lefts = np.ascontiguousarray(lefts)
+        rights = np.ascontiguousarray(rights)
+        if lefts.dtype != np.uint8 or rights.dtype != np.uint8 or lefts.shape != rights.shape or lefts.ndim not in (3, 4):
+            raise error(-1, "lefts/rights must be uint8 arrays of the same (B,H,W) or (B,H,W,3) shape")
+        B, H, W = lefts.shape[:3]
+        cn = 1 if lefts.ndim == 3 else lefts.shape[3]
+        out = disparity if disparity is not None else np.empty((B, H, W), np.int16)
+        if out.shape != (B, H, W) or out.dtype != np.int16 or not out.flags.c_contiguous:
+            raise error(-1, "bad output array")
+        check(_lib.lib().sgbm_compute_host(self._h, lefts.ctypes.data, rights.ctypes.data, W, H, cn, W * cn, B,
+                                           out.ctypes.data, W * 2))
+        return out
+
     def _compute_torch(self, left, right, disparity=None):
         torch = _torch()
         if not (left.is_cuda and right.is_cuda):
@@ -230,11 +251,26 @@ def disparityToFloat(disp_x16):
     return out
 
 
-def reprojectCompact(disp_x16, Q, colors_bgr=None):
+_PINNED = {}
+
+
+def _pinned(shape, dtype):
+    """Cached pinned host buffer (one per shape/dtype) for device -> host reads of point clouds."""
+    torch = _torch()
+    key = (tuple(shape), dtype)
+    buf = _PINNED.get(key)
+    if buf is None:
+        buf = torch.empty(shape, dtype=dtype).pin_memory()
+        _PINNED[key] = buf
+    return buf
+
+
+def reprojectCompact(disp_x16, Q, colors_bgr=None, to_host=False):
     """Fused tail of the notebook (main.ipynb:668-670, 697, 726-737) on the device.
 
     disp_x16: int16 CUDA tensor HxW (output of compute).  Returns (xyz float32 Nx3, rgb uint8 Nx3 or None):
-    the points with finite X and disparity > 0 in row-major pixel order, colours swapped BGR->RGB."""
+    the points with finite X and disparity > 0 in row-major pixel order, colours swapped BGR->RGB.
+    to_host=True returns numpy views of cached pinned buffers instead (valid until the next call)."""
     torch = _torch()
     L = _lib.lib()
     Q = _q16(Q)
@@ -258,6 +294,15 @@ def reprojectCompact(disp_x16, Q, colors_bgr=None):
                                        rgb.data_ptr() if rgb is not None else None, n.data_ptr(), scratch.data_ptr(),
                                        nbytes.value, _stream_ptr(dev)))
     cnt = int(n.item())
+    if to_host:
+        hx = _pinned((H * W, 3), torch.float32)
+        hx[:cnt].copy_(xyz[:cnt], non_blocking=True)
+        hc = None
+        if rgb is not None:
+            hc = _pinned((H * W, 3), torch.uint8)
+            hc[:cnt].copy_(rgb[:cnt], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return hx[:cnt].numpy(), (hc[:cnt].numpy() if hc is not None else None)
     return xyz[:cnt], (rgb[:cnt] if rgb is not None else None)
 
 

@@ -257,3 +257,18 @@ def test_full_size_properties(sg):
     top = st3.compute(lt[:ss + 64].contiguous(), rt[:ss + 64].contiguous()).cpu().numpy()
     # stripe 0 of the full image only sees rows < ss + r + 1 => identical away from the crop's own stripes
     assert np.array_equal(full[: (ss + 64 + 3) // 4 - 8], top[: (ss + 64 + 3) // 4 - 8])
+
+
+def test_host_batch_pipeline(sg):
+    """compute_batch (double-buffered pinned staging inside sgbm_compute_host) == per-frame oracle results."""
+    W, H, D = 272, 70, 48
+    pairs = [make_pair(W, H, D, seed=40 + i)[:2] for i in range(5)]
+    p = OracleParams(0, D, 5, 200, 800, 1, 63, 10, 50, 2, 0)
+    st = sg.StereoSGBM_create(**_kw(p))
+    lefts = np.stack([a for a, _ in pairs])
+    rights = np.stack([b for _, b in pairs])
+    for B in (1, 2, 5):
+        out = st.compute_batch(lefts[:B], rights[:B])
+        assert out.shape == (B, H, W) and out.dtype == np.int16
+        for i in range(B):
+            assert _mismatch(out[i], oracle.compute(p, pairs[i][0], pairs[i][1])) == 0, "frame %d of batch %d" % (i, B)
