@@ -123,6 +123,22 @@ int sgbm_filter_speckles(int16_t *img, int W, int H, int newVal, int maxSpeckleS
 int sgbm_median3x3(const int16_t *src, int16_t *dst, int W, int H, void *cuda_stream);
 
 /*
+ * Rectification warp in front of the path, device pointers:
+ *   sgbm_init_rectify_map  <- cv2.initUndistortRectifyMap(K, None, R, P, size, CV_32F)   main.ipynb:496-497, gui.py:160-161
+ *   sgbm_remap_linear_u8   <- cv2.remap(img, map1, map2, cv2.INTER_LINEAR)               main.ipynb:499-500, gui.py:163-164
+ * K: 9 doubles (row major, HOST).  dist_or_null: n_dist distortion coefficients, must all be zero
+ * (the reference passes None).  R_or_null: 9 doubles or NULL (identity).  P: 3 x p_cols doubles
+ * (p_cols 3 or 4; only the left 3x3 block is used).  map1/map2: W*H float32 each (x and y
+ * coordinates, the CV_32FC1 pair cv2 returns).  remap: 8-bit, 1 or 3 interleaved channels,
+ * INTER_LINEAR in 1/32-pixel fixed point, BORDER_CONSTANT with value 0; bit-identical to cv2.remap.
+ */
+int sgbm_init_rectify_map(const double *K, const double *dist_or_null, int n_dist, const double *R_or_null,
+                          const double *P, int p_cols, int W, int H, float *map1, float *map2, void *cuda_stream);
+int sgbm_remap_linear_u8(const uint8_t *src, int src_w, int src_h, int channels, ptrdiff_t src_pitch_bytes,
+                         const float *map1, const float *map2, int W, int H, uint8_t *dst, ptrdiff_t dst_pitch_bytes,
+                         void *cuda_stream);
+
+/*
  * Test hooks (used by tests/ only): copy an internal stage of the LAST frame computed by `h` to
  * a host buffer in canonical [y][x1][d] int16 order.  which: 0 = block cost C, 1 = aggregated S
  * (only after sgbm_debug_keep(h,1) was set before compute), 2 = raw disparity before median.

@@ -14,7 +14,7 @@ SYMBOLS = [
     "sgbm_disp_to_float", "sgbm_reproject_f32", "sgbm_reproject_i16", "sgbm_reproject_compact",
     "sgbm_reproject_compact_scratch_bytes", "sgbm_filter_speckles", "sgbm_median3x3",
     "sgbm_debug_keep", "sgbm_debug_fetch", "sgbm_microbench_int16", "sgbm_kernel_launches",
-    "sgbm_profile_enable", "sgbm_profile_read",
+    "sgbm_profile_enable", "sgbm_profile_read", "sgbm_init_rectify_map", "sgbm_remap_linear_u8",
 ]
 
 
@@ -58,6 +58,8 @@ def lib():
     L.sgbm_reproject_compact_scratch_bytes.argtypes = [i, i, C.POINTER(sz)]
     L.sgbm_filter_speckles.argtypes = [vp, i, i, i, i, i, vp, sz, vp]
     L.sgbm_median3x3.argtypes = [vp, vp, i, i, vp]
+    L.sgbm_init_rectify_map.argtypes = [vp, vp, i, vp, vp, i, i, i, vp, vp, vp]
+    L.sgbm_remap_linear_u8.argtypes = [vp, i, i, i, pd, vp, vp, i, i, vp, pd, vp]
     L.sgbm_debug_keep.argtypes = [vp, i]
     L.sgbm_debug_fetch.argtypes = [vp, i, vp, sz]
     L.sgbm_microbench_int16.argtypes = [i, C.POINTER(C.c_double)]

@@ -30,6 +30,9 @@ size_t sgbm_compact_scratch_bytes(int W, int H);
 int sgbm_launch_compact(const int16_t *disp, const double *Qh, int W, int H, const uint8_t *bgr, int bgrCn, long long bgrPitch,
                         float *xyz, uint8_t *rgb, unsigned long long *nOut, void *scratch, cudaStream_t st);
 int sgbm_run_microbench(int which, double *out);
+int sgbm_launch_rectify_map(const double *K, const double *R, const double *P, int pcols, int W, int H, float *map1, float *map2, cudaStream_t st);
+int sgbm_launch_remap_linear(const uint8_t *src, int sw, int sh, int cn, long long spitch, const float *map1, const float *map2, int W,
+                             int H, uint8_t *dst, long long dpitch, cudaStream_t st);
 
 // ---- error reporting ----------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -547,6 +550,28 @@ extern "C" int sgbm_median3x3(const int16_t *src, int16_t *dst, int W, int H, vo
 {
     if (!src || !dst || src == dst || W <= 0 || H <= 0) return sgbm_fail(SGBM_E_INVALID_ARG, "bad argument");
     return sgbm_launch_median(src, dst, W, H, W, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int sgbm_init_rectify_map(const double *K, const double *dist_or_null, int n_dist, const double *R_or_null,
+                                     const double *P, int p_cols, int W, int H, float *map1, float *map2, void *cuda_stream)
+{
+    if (!K || !P || !map1 || !map2 || W <= 0 || H <= 0) return sgbm_fail(SGBM_E_INVALID_ARG, "bad argument");
+    if (p_cols != 3 && p_cols != 4) return sgbm_fail(SGBM_E_INVALID_ARG, "newCameraMatrix must be 3x3 or 3x4");
+    for (int i = 0; dist_or_null && i < n_dist; i++)
+        if (dist_or_null[i] != 0.0)
+            return sgbm_fail(SGBM_E_UNSUPPORTED, "non-zero distortion coefficients are not implemented (the reference passes None)");
+    return sgbm_launch_rectify_map(K, R_or_null, P, p_cols, W, H, map1, map2, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int sgbm_remap_linear_u8(const uint8_t *src, int src_w, int src_h, int channels, ptrdiff_t src_pitch_bytes,
+                                    const float *map1, const float *map2, int W, int H, uint8_t *dst, ptrdiff_t dst_pitch_bytes,
+                                    void *cuda_stream)
+{
+    if (!src || !map1 || !map2 || !dst || src_w <= 0 || src_h <= 0 || W <= 0 || H <= 0) return sgbm_fail(SGBM_E_INVALID_ARG, "bad argument");
+    if (src_pitch_bytes < (ptrdiff_t)src_w * channels || dst_pitch_bytes < (ptrdiff_t)W * channels) return sgbm_fail(SGBM_E_INVALID_ARG, "bad pitch");
+    if (src_w > 32767 || src_h > 32767) return sgbm_fail(SGBM_E_UNSUPPORTED, "source larger than 32767 pixels (cv2 asserts the same for fixed-point remap)");
+    return sgbm_launch_remap_linear(src, src_w, src_h, channels, (long long)src_pitch_bytes, map1, map2, W, H, dst,
+                                    (long long)dst_pitch_bytes, (cudaStream_t)cuda_stream);
 }
 
 extern "C" int sgbm_debug_keep(sgbm_handle *h, int on)

@@ -24,6 +24,9 @@ MODE_SGBM_3WAY = 2
 MODE_HH4 = 3
 DISP_SHIFT = 4
 DISP_SCALE = 16
+INTER_LINEAR = 1          # cv2.INTER_LINEAR
+CV_32F = 5                # cv2.CV_32F / CV_32FC1 (m1type of initUndistortRectifyMap)
+CV_32FC1 = 5
 
 _PARAM_NAMES = ("minDisparity", "numDisparities", "blockSize", "P1", "P2", "disp12MaxDiff",
                 "preFilterCap", "uniquenessRatio", "speckleWindowSize", "speckleRange", "mode")
@@ -338,6 +341,67 @@ def medianBlur3(img):
     with torch.cuda.device(t.device):
         check(_lib.lib().sgbm_median3x3(t.data_ptr(), out.data_ptr(), W, H, _stream_ptr(t.device)))
     return out.cpu().numpy() if host else out
+
+
+def initUndistortRectifyMap(cameraMatrix, distCoeffs, R, newCameraMatrix, size, m1type=CV_32F, device=None):
+    """cv2.initUndistortRectifyMap(K, None, R, P, (W, H), cv2.CV_32F) (main.ipynb:496-497, gui.py:160-161).
+
+    Returns (map1, map2): float32 HxW x- and y-coordinate maps as torch CUDA tensors (they feed remap on
+    the device; call .cpu().numpy() for the arrays cv2 returns).  distCoeffs must be None or all zero,
+    m1type CV_32F / CV_32FC1 -- the forms the reference uses."""
+    torch = _torch()
+    if m1type not in (CV_32F,):
+        raise error(-3, "only m1type=CV_32F (CV_32FC1) is implemented")
+    K = np.ascontiguousarray(np.asarray(cameraMatrix, np.float64))
+    P = np.ascontiguousarray(np.asarray(newCameraMatrix, np.float64))
+    if K.shape != (3, 3) or P.shape not in ((3, 3), (3, 4)):
+        raise error(-1, "cameraMatrix must be 3x3 and newCameraMatrix 3x3 or 3x4")
+    Rm = None if R is None or np.size(R) == 0 else np.ascontiguousarray(np.asarray(R, np.float64))
+    if Rm is not None and Rm.shape != (3, 3):
+        raise error(-1, "R must be 3x3")
+    dist = None if distCoeffs is None else np.ascontiguousarray(np.asarray(distCoeffs, np.float64).ravel())
+    W, H = int(size[0]), int(size[1])
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    m1 = torch.empty((H, W), dtype=torch.float32, device=dev)
+    m2 = torch.empty((H, W), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().sgbm_init_rectify_map(K.ctypes.data, dist.ctypes.data if dist is not None else None,
+                                               0 if dist is None else int(dist.size), Rm.ctypes.data if Rm is not None else None,
+                                               P.ctypes.data, int(P.shape[1]), W, H, m1.data_ptr(), m2.data_ptr(),
+                                               _stream_ptr(dev)))
+    return m1, m2
+
+
+def remap(src, map1, map2, interpolation=INTER_LINEAR, dst=None):
+    """cv2.remap(src, map1, map2, interpolation=cv2.INTER_LINEAR) for uint8 images (main.ipynb:499-500):
+    bilinear in 1/32-pixel fixed point, constant border 0, bit-identical to cv2.  numpy in -> numpy out,
+    CUDA tensors in -> CUDA tensor out; the maps may be numpy float32 arrays or CUDA tensors."""
+    torch = _torch()
+    if interpolation != INTER_LINEAR:
+        raise error(-3, "only INTER_LINEAR is implemented")
+    host = not _is_tensor(src)
+    dev = (map1.device if _is_tensor(map1) and map1.is_cuda else torch.device("cuda", torch.cuda.current_device())) if host else src.device
+    s = torch.from_numpy(np.ascontiguousarray(src)).to(dev) if host else src.contiguous()
+    if s.dtype != torch.uint8 or s.dim() not in (2, 3):
+        raise error(-1, "src must be a uint8 HxW or HxWxC image")
+    cn = 1 if s.dim() == 2 else int(s.shape[2])
+    m1 = (map1 if _is_tensor(map1) else torch.from_numpy(np.ascontiguousarray(map1, np.float32))).to(dev).contiguous()
+    m2 = (map2 if _is_tensor(map2) else torch.from_numpy(np.ascontiguousarray(map2, np.float32))).to(dev).contiguous()
+    if m1.dtype != torch.float32 or m2.dtype != torch.float32 or m1.shape != m2.shape or m1.dim() != 2:
+        raise error(-1, "map1/map2 must be float32 HxW arrays of the same shape")
+    H, W = m1.shape
+    sh, sw = s.shape[:2]
+    out = torch.empty((H, W) if cn == 1 and s.dim() == 2 else (H, W, cn), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().sgbm_remap_linear_u8(s.data_ptr(), sw, sh, cn, sw * cn, m1.data_ptr(), m2.data_ptr(), W, H,
+                                              out.data_ptr(), W * cn, _stream_ptr(dev)))
+    if host:
+        res = out.cpu().numpy()
+        if dst is not None:
+            dst[...] = res
+            return dst
+        return res
+    return out
 
 
 def microbench_int16(which):
