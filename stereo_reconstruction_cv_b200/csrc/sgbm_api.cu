@@ -18,6 +18,7 @@ int sgbm_launch_cost(const Geo &g, const uint8_t *planes, uint16_t *out, int y0,
 int sgbm_launch_prefilter2(const Geo &g, const uint8_t *left, const uint8_t *right, long long pitch, uint8_t *planes, cudaStream_t st);
 int sgbm_launch_cost2(const Geo &g, const uint8_t *planes, uint16_t *out, int y0, int nrows, int ylo, int zeroTail, cudaStream_t st);
 size_t sgbm_cost2_planes_bytes(const Geo &g);
+int sgbm_launch_cost3(const Geo &g, const uint8_t *planes, uint16_t *out, int y0, int nrows, int ylo, cudaStream_t st);
 int sgbm_launch_horizontal(const Geo &g, const uint16_t *C, uint16_t *LhA, uint16_t *LhB, int y0, int nrows, cudaStream_t st);
 int sgbm_launch_vertical(VertArgs &a, int ndir, int numSMs, cudaStream_t st);
 int sgbm_launch_fill_i16(int16_t *p, size_t n, int v, cudaStream_t st);
@@ -307,14 +308,26 @@ static int compute_frame(sgbm_handle *h, const Geo &g, const WsLayout &L, const 
     if ((rc = prof_mark(h, ST_START, st))) return rc;
     // second-generation prefilter + cost kernels (sgbm_cost2.cu); the first generation stays as the
     // fallback for geometries the new kernel does not hold (rc == 1) and for A/B runs (SGBM_COST2=0)
-    bool cost2 = true;
+    bool cost2 = true, cost3 = true;
     if (const char *e = getenv("SGBM_COST2")) cost2 = atoi(e) != 0;
+    if (const char *e = getenv("SGBM_COST3")) cost3 = atoi(e) != 0;
+    if (!cost2) cost3 = false;
     if (cost2) {
         if ((rc = sgbm_launch_prefilter2(g, left, right, pitch, planes, st))) return rc;
         if ((rc = prof_mark(h, ST_PREFILTER, st))) return rc;
-        rc = sgbm_launch_cost2(g, planes, C, 0, g.H, 0, p.mode == SGBM_MODE_HH4, st);
+        // third generation (sgbm_cost3.cu): register-resident pixel costs; 1-channel, blockSize <= 11
+        rc = cost3 ? sgbm_launch_cost3(g, planes, C, 0, g.H, 0, st) : 1;
         if (rc < 0) return rc;
-        if (rc == 1) cost2 = false;
+        cost3 = rc == 0;
+        if (cost3 && p.mode == SGBM_MODE_HH4 && g.r > 0) {            // A.9: the last r rows carry C = 0
+            const int nz = g.r < g.H ? g.r : g.H;
+            SGBM_CUDA_CHECK(cudaMemsetAsync(C + (size_t)(g.H - nz) * g.rowStride, 0, (size_t)nz * g.rowStride * 2, st));
+        }
+        if (!cost3) {
+            rc = sgbm_launch_cost2(g, planes, C, 0, g.H, 0, p.mode == SGBM_MODE_HH4, st);
+            if (rc < 0) return rc;
+            if (rc == 1) cost2 = false;
+        }
     }
     if (!cost2) {
         if ((rc = sgbm_launch_prefilter(g, left, right, pitch, planes, st))) return rc;
@@ -333,7 +346,8 @@ static int compute_frame(sgbm_handle *h, const Geo &g, const WsLayout &L, const 
             if (s0 == 0) continue;
             int nr = g.r < g.H - s0 ? g.r : g.H - s0;
             uint16_t *dst = Calt + (size_t)(n - 1) * g.r * g.rowStride;
-            rc = cost2 ? sgbm_launch_cost2(g, planes, dst, s0, nr, s0, 0, st) : sgbm_launch_cost(g, planes, dst, s0, nr, s0, 0, st);
+            rc = cost3 ? sgbm_launch_cost3(g, planes, dst, s0, nr, s0, st)
+                 : cost2 ? sgbm_launch_cost2(g, planes, dst, s0, nr, s0, 0, st) : sgbm_launch_cost(g, planes, dst, s0, nr, s0, 0, st);
             if (rc) return rc < 0 ? rc : sgbm_fail(SGBM_E_UNSUPPORTED, "cost kernel geometry changed between launches");
         }
     }

@@ -19,17 +19,18 @@
 // ---- geometry of the prefilter outputs (shared with the workspace layout in sgbm_api.cu) ------------
 int sgbm_cost2_left_pitch(const Geo &g) { return ((g.W + 15) & ~15) + 16; }
 int sgbm_cost2_rpw(const Geo &g) { return (g.W / 2 + g.D / 2 + g.r + 160 + 3) & ~3; }   // words per parity row
-size_t sgbm_cost2_planes_bytes(const Geo &g)
+static size_t cost2_right_bytes(const Geo &g) { return (((size_t)g.cn * 6 * g.H * 2 * sgbm_cost2_rpw(g) * 4 + 256) + 255) & ~(size_t)255; }
+// third section (sgbm_cost3.cu, 1-channel only): the left operands of every pixel pre-expanded to packed
+// u16x2 words, 32 bytes per pixel: { u + K, K - u, K - u_hi, u_lo + K } for the gradient and the raw plane
+static size_t cost2_leftx_bytes(const Geo &g) { return g.cn == 1 ? (size_t)g.H * g.W * 32 + 4096 : 0; }
+size_t sgbm_cost2_right_offset(const Geo &g)
 {
     const size_t left = (size_t)g.cn * 6 * g.H * sgbm_cost2_left_pitch(g) + 1024;   // + over-read of the last staged row
-    const size_t right = (size_t)g.cn * 6 * g.H * 2 * sgbm_cost2_rpw(g) * 4 + 256;
-    return ((left + 255) & ~(size_t)255) + right;
-}
-static size_t cost2_right_offset(const Geo &g)
-{
-    const size_t left = (size_t)g.cn * 6 * g.H * sgbm_cost2_left_pitch(g) + 1024;
     return (left + 255) & ~(size_t)255;
 }
+size_t sgbm_cost2_leftx_offset(const Geo &g) { return sgbm_cost2_right_offset(g) + cost2_right_bytes(g); }
+size_t sgbm_cost2_planes_bytes(const Geo &g) { return sgbm_cost2_leftx_offset(g) + cost2_leftx_bytes(g); }
+static size_t cost2_right_offset(const Geo &g) { return sgbm_cost2_right_offset(g); }
 
 __device__ __forceinline__ int pf2_g(const uint8_t *img, long long pitch, int cn, int c, int W, int H, int x, int y, int ftzero)
 {
@@ -67,7 +68,7 @@ __device__ __forceinline__ void pf2_six(const uint8_t *img, long long pitch, int
 }
 
 __global__ void k_prefilter2(const uint8_t *left, const uint8_t *right, long long pitch, int W, int H, int cn, int ftzero,
-                             uint8_t *leftP, int PL, uint32_t *rpairs, int RPW)
+                             uint8_t *leftP, int PL, uint32_t *rpairs, int RPW, uint4 *leftX)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
@@ -79,6 +80,12 @@ __global__ void k_prefilter2(const uint8_t *left, const uint8_t *right, long lon
         pf2_six(left, pitch, cn, c, W, H, x, y, ftzero, a);
 #pragma unroll
         for (int p = 0; p < 6; p++) leftP[((size_t)(c * 6 + p) * H + y) * PL + x] = (uint8_t)a[p];
+        if (leftX) {                           // cn == 1: packed-expanded operands for k_cost3
+            uint4 *o = leftX + ((size_t)y * W + x) * 2;
+            // per plane (g, t): u + K, K - u, K - u_hi, u_lo + K   (K = 256, the bias of k_cost3)
+            o[0] = make_uint4((a[0] + 256u) * 0x10001u, (256u - a[0]) * 0x10001u, (256u - a[2]) * 0x10001u, (a[1] + 256u) * 0x10001u);
+            o[1] = make_uint4((a[3] + 256u) * 0x10001u, (256u - a[3]) * 0x10001u, (256u - a[5]) * 0x10001u, (a[4] + 256u) * 0x10001u);
+        }
     } else {
         int b[6];
         pf2_six(right, pitch, cn, c, W, H, x, y, ftzero, a);
@@ -94,7 +101,8 @@ int sgbm_launch_prefilter2(const Geo &g, const uint8_t *left, const uint8_t *rig
 {
     dim3 grid((g.W + 255) / 256, g.H, 2 * g.cn);
     k_prefilter2<<<grid, 256, 0, st>>>(left, right, pitch, g.W, g.H, g.cn, g.ftzero, planes, sgbm_cost2_left_pitch(g),
-                                       reinterpret_cast<uint32_t *>(planes + cost2_right_offset(g)), sgbm_cost2_rpw(g));
+                                       reinterpret_cast<uint32_t *>(planes + cost2_right_offset(g)), sgbm_cost2_rpw(g),
+                                       g.cn == 1 ? reinterpret_cast<uint4 *>(planes + sgbm_cost2_leftx_offset(g)) : nullptr);
     sgbm_count_launch(1);
     SGBM_CUDA_CHECK(cudaGetLastError());
     return 0;
