@@ -1,5 +1,6 @@
 cd /root/repo
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+export SGBM_COST3_VERBOSE=1
 for wl in cfg3 cfg4 cfg2; do
   python bench.py --workload $wl --steps 6 --warmup 3 2>gpurun_out/err_$wl.log | python -c "
 import sys,json
@@ -8,4 +9,5 @@ for l in sys.stdin:
     except Exception: continue
     print('$wl', round(j['ms_per_step'],3),'ms', round(j['value']),'MDE/s e2e',round(j['e2e']['value']), j['stages_ms'], j['e2e'].get('matches_device_path'))
 "
+grep -m1 cost3: gpurun_out/err_$wl.log
 done

@@ -15,7 +15,9 @@
 // ---- launchers implemented in the other translation units -------------------------------------
 int sgbm_launch_prefilter(const Geo &g, const uint8_t *left, const uint8_t *right, long long pitch, uint8_t *planes, cudaStream_t st);
 int sgbm_launch_cost(const Geo &g, const uint8_t *planes, uint16_t *out, int y0, int nrows, int ylo, int zeroTail, cudaStream_t st);
-int sgbm_launch_prefilter2(const Geo &g, const uint8_t *left, const uint8_t *right, long long pitch, uint8_t *planes, cudaStream_t st);
+int sgbm_launch_prefilter2(const Geo &g, const uint8_t *left, const uint8_t *right, long long pitch, uint8_t *planes, int eshift, cudaStream_t st);
+int sgbm_cost3_supported(const Geo &g);
+int sgbm_cost3_eshift(const Geo &g);
 int sgbm_launch_cost2(const Geo &g, const uint8_t *planes, uint16_t *out, int y0, int nrows, int ylo, int zeroTail, cudaStream_t st);
 size_t sgbm_cost2_planes_bytes(const Geo &g);
 int sgbm_launch_cost3(const Geo &g, const uint8_t *planes, uint16_t *out, int y0, int nrows, int ylo, cudaStream_t st);
@@ -312,13 +314,17 @@ static int compute_frame(sgbm_handle *h, const Geo &g, const WsLayout &L, const 
     if (const char *e = getenv("SGBM_COST2")) cost2 = atoi(e) != 0;
     if (const char *e = getenv("SGBM_COST3")) cost3 = atoi(e) != 0;
     if (!cost2) cost3 = false;
+    if (cost3) {
+        rc = sgbm_cost3_supported(g);
+        if (rc < 0) return rc;
+        cost3 = rc == 1;
+    }
     if (cost2) {
-        if ((rc = sgbm_launch_prefilter2(g, left, right, pitch, planes, st))) return rc;
+        if ((rc = sgbm_launch_prefilter2(g, left, right, pitch, planes, cost3 ? sgbm_cost3_eshift(g) : 0, st))) return rc;
         if ((rc = prof_mark(h, ST_PREFILTER, st))) return rc;
         // third generation (sgbm_cost3.cu): register-resident pixel costs; 1-channel, blockSize <= 11
-        rc = cost3 ? sgbm_launch_cost3(g, planes, C, 0, g.H, 0, st) : 1;
-        if (rc < 0) return rc;
-        cost3 = rc == 0;
+        if (cost3 && (rc = sgbm_launch_cost3(g, planes, C, 0, g.H, 0, st)))
+            return rc < 0 ? rc : sgbm_fail(SGBM_E_UNSUPPORTED, "cost kernel geometry changed between plan and launch");
         if (cost3 && p.mode == SGBM_MODE_HH4 && g.r > 0) {            // A.9: the last r rows carry C = 0
             const int nz = g.r < g.H ? g.r : g.H;
             SGBM_CUDA_CHECK(cudaMemsetAsync(C + (size_t)(g.H - nz) * g.rowStride, 0, (size_t)nz * g.rowStride * 2, st));

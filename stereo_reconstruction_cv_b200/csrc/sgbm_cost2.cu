@@ -68,7 +68,7 @@ __device__ __forceinline__ void pf2_six(const uint8_t *img, long long pitch, int
 }
 
 __global__ void k_prefilter2(const uint8_t *left, const uint8_t *right, long long pitch, int W, int H, int cn, int ftzero,
-                             uint8_t *leftP, int PL, uint32_t *rpairs, int RPW, uint4 *leftX)
+                             uint8_t *leftP, int PL, uint32_t *rpairs, int RPW, uint4 *leftX, int eshift)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
@@ -92,17 +92,18 @@ __global__ void k_prefilter2(const uint8_t *left, const uint8_t *right, long lon
         pf2_six(right, pitch, cn, c, W, H, min(x + 1, W - 1), y, ftzero, b);
 #pragma unroll
         for (int p = 0; p < 6; p++)            // pair word of q = x: lo = v(q+1), hi = v(q)
-            rpairs[(((size_t)(c * 6 + p) * H + y) * 2 + (x & 1)) * RPW + (x >> 1)] = (uint32_t)b[p] | ((uint32_t)a[p] << 16);
+            rpairs[(((size_t)(c * 6 + p) * H + y) * 2 + (x & 1)) * RPW + (x >> 1) + ((x & 1) ? 0 : eshift)] =
+                (uint32_t)b[p] | ((uint32_t)a[p] << 16);  // eshift: k_cost3 wants the even array one word to the right
     }
 }
 
 int sgbm_launch_prefilter2(const Geo &g, const uint8_t *left, const uint8_t *right, long long pitch, uint8_t *planes,
-                           cudaStream_t st)
+                           int eshift, cudaStream_t st)
 {
     dim3 grid((g.W + 255) / 256, g.H, 2 * g.cn);
     k_prefilter2<<<grid, 256, 0, st>>>(left, right, pitch, g.W, g.H, g.cn, g.ftzero, planes, sgbm_cost2_left_pitch(g),
                                        reinterpret_cast<uint32_t *>(planes + cost2_right_offset(g)), sgbm_cost2_rpw(g),
-                                       g.cn == 1 ? reinterpret_cast<uint4 *>(planes + sgbm_cost2_leftx_offset(g)) : nullptr);
+                                       g.cn == 1 ? reinterpret_cast<uint4 *>(planes + sgbm_cost2_leftx_offset(g)) : nullptr, eshift);
     sgbm_count_launch(1);
     SGBM_CUDA_CHECK(cudaGetLastError());
     return 0;
