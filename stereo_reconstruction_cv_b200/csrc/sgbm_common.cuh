@@ -180,6 +180,17 @@ __device__ __forceinline__ uint32_t path_step(uint32_t (&Ln)[NREG], const uint32
     return group_min<LPC>(t);
 }
 
+// A multiply-add by an opaque +-1 (a kernel argument the compiler cannot fold) is an IMAD and issues on the
+// FMA pipe; the packed min / max / permute instructions issue on the ALU pipe only, at half rate.  Used
+// by sgbm_cost3.cu, where the ALU pipe is the nearest bound.  (Tried in the path step as well, b + (C - m)
+// as two IMADs: one more instruction per word, sweeps 2 % SLOWER -- they are latency-, not pipe-bound.)
+__device__ __forceinline__ uint32_t fma_mad(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 // Path start (predecessor outside the image): L = C, m = min C.
 template <int NREG, int LPC>
 __device__ __forceinline__ uint32_t path_start(uint32_t (&Ln)[NREG], const uint32_t (&C)[NREG], int lg,

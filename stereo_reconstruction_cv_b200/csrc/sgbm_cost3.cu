@@ -69,12 +69,6 @@ __device__ __forceinline__ void ring_st(uint32_t addr, uint32_t x, uint32_t y)
 // The left operands arrive pre-biased (uK = u + K, KmU = K - u, KmUhi = K - u_hi, UloK = u_lo + K), so each
 // of the four differences is ONE multiply-add a * (+-1) + c.  The multipliers are kernel arguments the
 // compiler cannot fold: that forces IMAD, which issues on the FMA pipe.
-__device__ __forceinline__ uint32_t fma_mad(uint32_t a, uint32_t b, uint32_t c)
-{
-    uint32_t d;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
 // Birchfield-Tomasi cost of one plane for two adjacent disparities, biased by K (A.2):
 //   min( max(u - vhi, vlo - u, 0), max(v - uhi, ulo - v, 0) ) + K
 __device__ __forceinline__ uint32_t bt3(uint32_t uK, uint32_t KmU, uint32_t KmUhi, uint32_t UloK, uint32_t v, uint32_t vlo,
