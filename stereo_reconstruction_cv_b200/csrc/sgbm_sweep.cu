@@ -37,6 +37,7 @@ struct SweepArgs {
     unsigned int *d2key;
     int SW, nstrips, R, NB;          // max columns per strip, strips, rows per super-step, batches
     int nwA, nwV;                    // warps of each diagonal role / of the vertical role
+    int aA, aV, nwW, wPass;          // WROLE: warps allocated per role (multiples of 4), WTA warps, their passes per row
     int NSC, NSI, K, nAB;            // ring depths (cost rows, input rows, S slots), input volumes
     unsigned int stgCOff, stgIOff, pOff, ssmOff, barOff;
     int backward;
@@ -82,7 +83,7 @@ __device__ __forceinline__ void load_vec_l2(uint32_t (&v)[NREG], const uint16_t 
 
 struct SweepSmem {
     uint16_t *stgC, *stgI, *P, *ssm;
-    uint64_t *fullC, *emptyC, *fullI, *emptyI, *fullV, *fullM, *freeP;
+    uint64_t *fullC, *emptyC, *fullI, *emptyI, *fullV, *fullM, *freeP, *fullW;
 };
 __device__ __forceinline__ SweepSmem sweep_carve(const SweepArgs &a, uint8_t *smem)
 {
@@ -98,7 +99,8 @@ __device__ __forceinline__ SweepSmem sweep_carve(const SweepArgs &a, uint8_t *sm
     s.emptyI = b; b += a.NSI;
     s.fullV = b; b += a.K;
     s.fullM = b; b += a.K;
-    s.freeP = b;
+    s.freeP = b; b += a.K;
+    s.fullW = b;
     return s;
 }
 
@@ -287,7 +289,7 @@ __device__ __forceinline__ void sweep_wta(const SweepArgs &a, const uint32_t (&S
 }
 
 // ---- roles A (DIR = +1) and C (DIR = -1, finishes the pixel) -----------------------------------------
-template <int NREG, int LPC, int DIR, bool SAT>
+template <int NREG, int LPC, int DIR, bool SAT, bool WROLE>
 __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepSmem &s, int rwarp, int strip, int xs,
                                                 int xe, int yBegin, int yStep, int nRows)
 {
@@ -359,7 +361,8 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
             for (int j = 0; j < NREG; j++) L[j] = 0;
             m = 0;
         }
-        uint64_t *waitBar = FINAL ? s.fullM : s.fullV, *doneBar = FINAL ? s.freeP : s.fullM;
+        // WROLE: the finished S goes back into the slot and the winner-take-all warps release it
+        uint64_t *waitBar = FINAL ? s.fullM : s.fullV, *doneBar = FINAL ? (WROLE ? s.fullW : s.freeP) : s.fullM;
         SWEEP_TR(DIR > 0 ? 1 : 2, 0, rwarp == a.nwA / 2);
         if (!okC) mbar_wait(&s.fullC[sc], pc);
         SWEEP_TR(DIR > 0 ? 1 : 2, 1, rwarp == a.nwA / 2);
@@ -400,7 +403,7 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
             load_vec<NREG, LPC>(S, ps, lg);
 #pragma unroll
             for (int j = 0; j < NREG; j++) S[j] = sacc<SAT>(S[j], Ln[j]);
-            if (!FINAL) store_vec<NREG, LPC>(S, ps, lg);
+            if (!FINAL || WROLE) store_vec<NREG, LPC>(S, ps, lg);
         } else if (FINAL) {
 #pragma unroll
             for (int j = 0; j < NREG; j++) S[j] = SGBM_MAX_S;
@@ -411,7 +414,7 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
             mbar_arrive(&s.emptyC[sc]);
         }
         SWEEP_TR(DIR > 0 ? 1 : 2, 4, rwarp == a.nwA / 2);
-        if (FINAL && __any_sync(0xFFFFFFFFu, own)) {
+        if (FINAL && !WROLE && __any_sync(0xFFFFFFFFu, own)) {
             const int y = yBegin + t * yStep;
             const int x1 = own ? col : xs;
             if (a.sout) {
@@ -437,10 +440,116 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
     }
 }
 
-template <int NREG> struct SweepMaxThreads { static const int value = NREG >= 12 ? 768 : 1024; };
+// ---- role W (WROLE kernels): winner-take-all of the finished rows --------------------------------------
+// Reads the final S of a pixel from the ring slot role C left it in, uses the slot itself as the scratch
+// of the masked uniqueness re-scan, and releases the slot.  S in the slot is the plain (unclamped) sum
+// when !SAT; the clamp to 32767 (A.4) is applied to what is read.
+template <int NREG, int LPC, bool SAT>
+__device__ __forceinline__ void sweep_wta_slot(const SweepArgs &a, uint16_t *col, int lg, bool own, int x1, int y)
+{
+    const Geo &g = a.g;
+    const int lastLane = g.lanesUsed - 1;
+    uint32_t key = 0xFFFFFFFFu;
+    {
+        uint32_t S[NREG];
+        load_vec<NREG, LPC>(S, col, lg);
+        if (!SAT) {
+#pragma unroll
+            for (int j = 0; j < NREG; j++) S[j] = pmin(S[j], SGBM_MAX_S);
+        }
+        if (a.sdbg && own) store_vec<NREG, LPC>(S, a.sdbg + (size_t)y * g.rowStride + (size_t)x1 * g.Dp, lg);
+#pragma unroll
+        for (int j = 0; j < NREG; j += 2) {
+            const uint32_t i0 = (uint32_t)(2 * j) | ((uint32_t)(2 * j + 1) << 16), i1 = i0 + 0x00020002u;
+            const uint32_t k0 = min(__byte_perm(S[j], i0, 0x1054), __byte_perm(S[j], i0, 0x3276));
+            const uint32_t k1 = min(__byte_perm(S[j + 1], i1, 0x1054), __byte_perm(S[j + 1], i1, 0x3276));
+            key = __vimin3_u32(key, k0, k1);
+        }
+    }
+    key += (uint32_t)(lg * 2 * NREG);                                   // lane-local index -> disparity
+    if (lg > lastLane) key = 0xFFFFFFFFu;
+#pragma unroll
+    for (int off = LPC / 2; off >= 1; off >>= 1) key = min(key, __shfl_xor_sync(0xFFFFFFFFu, key, off, LPC));
+    const int minS = (int)(key >> 16);
+    const int best = (minS == 32767) ? -1 : (int)(key & 0xFFFFu);       // first minimum (A.5)
+    int Sm = 0, Sp = 0;
+    const bool interior = best > 0 && best < g.D - 1;
+    if (lg == 0 && interior) {
+        Sm = min((int)col[sgbm_pos(best - 1, NREG, LPC)], 32767);
+        Sp = min((int)col[sgbm_pos(best + 1, NREG, LPC)], 32767);
+    }
+    bool reject = false;
+    if (g.UR > 0) {
+        const int av = 100 - g.UR;                                       // S(d)*(100-UR) < minS*100  <=>  S(d) < T
+        const unsigned num = (unsigned)(100 * minS + av - 1);
+        const int T = av > 0 ? min((int)(av == 1 ? num : __umulhi(num, a.urMagic)), 32768) : (minS > 0 ? 32768 : 0);
+        __syncwarp();
+        if (lg == 0 && own) {
+#pragma unroll
+            for (int dd = -1; dd <= 1; dd++) {
+                const int d = best + dd;
+                if (d >= 0 && d < g.D) col[sgbm_pos(d, NREG, LPC)] = 0xFFFFu;
+            }
+        }
+        __syncwarp();
+        uint32_t S2[NREG];
+        load_vec<NREG, LPC>(S2, col, lg);
+        const uint32_t t2 = local_min<NREG>(S2);
+        const bool viol = lg <= lastLane && min((int)(t2 & 0xFFFFu), 32767) < T;
+        const unsigned ball = __ballot_sync(0xFFFFFFFFu, viol);
+        const int lane = threadIdx.x & 31;
+        const unsigned gmask = (LPC == 32 ? 0xFFFFFFFFu : ((1u << LPC) - 1u)) << (lane & ~(LPC - 1));
+        reject = (ball & gmask) != 0u;
+    }
+    if (lg == 0 && own) {
+        const int x = x1 + g.minX1;
+        int out = g.INV;
+        if (!reject) {
+            const int x2 = x - best - g.minD;
+            if (minS < 32767 && x2 >= 0 && x2 < g.W)
+                atomicMin(a.d2key + (size_t)y * g.W + x2, ((unsigned)minS << 16) | (0xFFFFu - (unsigned)x1));
+            int dq = best * 16;
+            if (interior) {
+                const int den = max(Sm + Sp - 2 * minS, 1);
+                dq += (int)((float)((Sm - Sp) * 16 + den) / (float)(2 * den));   // exactness: see sweep_wta
+            }
+            out = dq + g.minD * 16;
+        }
+        a.raw[(size_t)y * g.W + x] = (int16_t)out;
+    }
+}
 
 template <int NREG, int LPC, bool SAT>
-__global__ void __launch_bounds__(SweepMaxThreads<NREG>::value, 1) k_sweep(SweepArgs a)
+__device__ __forceinline__ void sweep_role_w(const SweepArgs &a, const SweepSmem &s, int wwarp, int xs, int SW, int yBegin,
+                                             int yStep, int nRows)
+{
+    constexpr int GPW = 32 / LPC;
+    const int lane = threadIdx.x & 31, lg = lane % LPC;
+    const int Dp = a.g.Dp, K = a.K, pStride = a.SW * Dp;
+    int k = 0, pOff = 0;
+    uint32_t pk = 0;
+    for (int t = 0; t < nRows; t++) {
+        const int y = yBegin + t * yStep;
+        mbar_wait(&s.fullW[k], pk);
+        for (int it = 0; it < a.wPass; it++) {
+            const int gi = (it * a.nwW + wwarp) * GPW + lane / LPC;
+            const bool own = gi < SW;
+            if (!__any_sync(0xFFFFFFFFu, own)) continue;
+            const int ci = own ? gi : SW - 1;
+            // (groups without a column read column SW-1 along with the warp; all their writes are guarded by own)
+            sweep_wta_slot<NREG, LPC, SAT>(a, s.P + pOff + ci * Dp, lg, own, xs + ci, y);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.freeP[k]);
+        pOff += pStride;
+        if (++k == K) { k = 0; pk ^= 1u; pOff = 0; }
+    }
+}
+
+template <int NREG, bool WROLE> struct SweepMaxThreads { static const int value = (NREG >= 12 && !WROLE) ? 768 : 1024; };
+
+template <int NREG, int LPC, bool SAT, bool WROLE>
+__global__ void __launch_bounds__((SweepMaxThreads<NREG, WROLE>::value), 1) k_sweep(SweepArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const Geo &g = a.g;
@@ -454,16 +563,41 @@ __global__ void __launch_bounds__(SweepMaxThreads<NREG>::value, 1) k_sweep(Sweep
         const int nCons = a.nwV + 2 * a.nwA;
         for (int q = 0; q < a.NSC; q++) { mbar_init(&s.fullC[q], 1); mbar_init(&s.emptyC[q], nCons); }
         for (int q = 0; q < a.NSI; q++) { mbar_init(&s.fullI[q], 1); mbar_init(&s.emptyI[q], a.nwV); }
-        for (int q = 0; q < a.K; q++) { mbar_init(&s.fullV[q], a.nwV); mbar_init(&s.fullM[q], a.nwA); mbar_init(&s.freeP[q], a.nwA); }
+        for (int q = 0; q < a.K; q++) {
+            mbar_init(&s.fullV[q], a.nwV); mbar_init(&s.fullM[q], a.nwA);
+            mbar_init(&s.freeP[q], WROLE ? a.nwW : a.nwA); mbar_init(&s.fullW[q], a.nwA);
+        }
         mbar_fence_init();
     }
     __syncthreads();
+    if (WROLE) {
+        // Warp layout [V: aV][A: aA][C: aA][W: nwW, producer, idle: 8 in all], every role a whole number of
+        // warpgroups so that registers can move between them: the three path roles need ~80 registers at
+        // NREG >= 12, the winner-take-all and producer warps give theirs up (1024 threads x 64 at launch).
+        constexpr bool SPLIT = NREG >= 12;
+        if (warp < a.aV + 2 * a.aA) {
+            if (SPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 72;");
+            if (warp < a.aV) {
+                if (warp < a.nwV) sweep_role_v<NREG, LPC, SAT>(a, s, warp, xe - xs, nRows);
+            } else if (warp < a.aV + a.aA) {
+                if (warp - a.aV < a.nwA) sweep_role_diag<NREG, LPC, +1, SAT, true>(a, s, warp - a.aV, strip, xs, xe, yBegin, yStep, nRows);
+            } else {
+                if (warp - a.aV - a.aA < a.nwA) sweep_role_diag<NREG, LPC, -1, SAT, true>(a, s, warp - a.aV - a.aA, strip, xs, xe, yBegin, yStep, nRows);
+            }
+        } else {
+            if (SPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+            const int ww = warp - a.aV - 2 * a.aA;
+            if (ww < a.nwW) sweep_role_w<NREG, LPC, SAT>(a, s, ww, xs, xe - xs, yBegin, yStep, nRows);
+            else if (ww == a.nwW && (threadIdx.x & 31) == 0) sweep_producer(a, s, xs, xe, yBegin, yStep, nRows);
+        }
+        return;
+    }
     if (warp < a.nwV) {
         sweep_role_v<NREG, LPC, SAT>(a, s, warp, xe - xs, nRows);
     } else if (warp < a.nwV + a.nwA) {
-        sweep_role_diag<NREG, LPC, +1, SAT>(a, s, warp - a.nwV, strip, xs, xe, yBegin, yStep, nRows);
+        sweep_role_diag<NREG, LPC, +1, SAT, false>(a, s, warp - a.nwV, strip, xs, xe, yBegin, yStep, nRows);
     } else if (warp < a.nwV + 2 * a.nwA) {
-        sweep_role_diag<NREG, LPC, -1, SAT>(a, s, warp - a.nwV - a.nwA, strip, xs, xe, yBegin, yStep, nRows);
+        sweep_role_diag<NREG, LPC, -1, SAT, false>(a, s, warp - a.nwV - a.nwA, strip, xs, xe, yBegin, yStep, nRows);
     } else if ((threadIdx.x & 31) == 0) {
         sweep_producer(a, s, xs, xe, yBegin, yStep, nRows);
     }
@@ -472,7 +606,7 @@ __global__ void __launch_bounds__(SweepMaxThreads<NREG>::value, 1) k_sweep(Sweep
 // =================================================================================================
 // Host side
 // =================================================================================================
-static size_t sweep_layout(SweepArgs &a, int groupsC, bool wta)
+static size_t sweep_layout(SweepArgs &a, int groupsC, bool scratch)
 {
     const Geo &g = a.g;
     const size_t col = (size_t)g.Dp * 2;
@@ -480,20 +614,20 @@ static size_t sweep_layout(SweepArgs &a, int groupsC, bool wta)
     a.stgCOff = (unsigned)off; off += (size_t)a.NSC * (a.SW + 2 * (a.R - 1)) * col;
     a.stgIOff = (unsigned)off; off += (size_t)a.NSI * a.nAB * a.SW * col;
     a.pOff = (unsigned)off; off += (size_t)a.K * a.SW * col;
-    a.ssmOff = (unsigned)off; if (wta) off += (size_t)groupsC * col;
+    a.ssmOff = (unsigned)off; if (scratch) off += (size_t)groupsC * col;
     off = (off + 15) & ~(size_t)15;
-    a.barOff = (unsigned)off; off += (size_t)(2 * a.NSC + 2 * a.NSI + 3 * a.K) * 8;
+    a.barOff = (unsigned)off; off += (size_t)(2 * a.NSC + 2 * a.NSI + 4 * a.K) * 8;
     return off;
 }
 
 // Returns 0 on success, 1 if this geometry does not fit the role-specialised sweep (the caller falls
-// back to k_vertical), negative on error.
-template <int NREG, int LPC, bool SAT>
+// back to k_vertical), negative on error.  WROLE: winner-take-all sweep with the dedicated WTA role.
+template <int NREG, int LPC, bool SAT, bool WROLE>
 static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
 {
     constexpr int GPW = 32 / LPC;
     const Geo &g = va.g;
-    auto kern = k_sweep<NREG, LPC, SAT>;
+    auto kern = k_sweep<NREG, LPC, SAT, WROLE>;
     static bool attrDone = false;
     static int maxSmem = 0;
     if (!attrDone) {
@@ -511,11 +645,12 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
     a.nAB = va.inB ? 2 : 1;
     a.urMagic = g.UR < 99 ? 0xFFFFFFFFu / (unsigned)(100 - g.UR) + 1u : 0u;
     const bool wta = va.sout == nullptr;
-    const int maxThreads = SweepMaxThreads<NREG>::value;
+    if (WROLE && !wta) return 1;
+    const int maxThreads = SweepMaxThreads<NREG, WROLE>::value;
     int R = 8;
     if (const char *e = getenv("SGBM_VR")) R = atoi(e) > 0 ? atoi(e) : 1;
     if (R > 16) R = 16;
-    int Kwant = 3, NSCwant = 5, NSIwant = 3;
+    int Kwant = WROLE ? 4 : 3, NSCwant = 5, NSIwant = 3;
     if (const char *e = getenv("SGBM_SWEEP_K")) Kwant = atoi(e) >= 1 && atoi(e) <= 8 ? atoi(e) : Kwant;
     if (const char *e = getenv("SGBM_SWEEP_NSC")) NSCwant = atoi(e) >= 2 && atoi(e) <= 8 ? atoi(e) : NSCwant;
     if (const char *e = getenv("SGBM_SWEEP_NSI")) NSIwant = atoi(e) >= 2 && atoi(e) <= 8 ? atoi(e) : NSIwant;
@@ -533,7 +668,15 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
         const int groupsA = NB * R;
         a.nwA = (groupsA + GPW - 1) / GPW;
         a.nwV = (SWmax + GPW - 1) / GPW;
-        threads = (a.nwV + 2 * a.nwA + 1) * 32;
+        if (WROLE) {
+            a.aA = (a.nwA + 3) & ~3; a.aV = (a.nwV + 3) & ~3;
+            a.nwW = a.nwV < 7 ? a.nwV : 7;                // 8 warps: WTA warps, the producer, idle
+            if (const char *e = getenv("SGBM_SWEEP_NWW")) { const int v = atoi(e); if (v >= 1 && v <= 7) a.nwW = v; }
+            a.wPass = (SWmax + a.nwW * GPW - 1) / (a.nwW * GPW);
+            threads = (a.aV + 2 * a.aA + 8) * 32;
+        } else {
+            threads = (a.nwV + 2 * a.nwA + 1) * 32;
+        }
         if (threads > maxThreads) continue;
         a.SW = SWmax; a.nstrips = nstrips; a.R = R; a.NB = NB;
         // ring depths: shrink until the layout fits
@@ -543,7 +686,7 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
             if (a.K < 1) a.K = 1;
             if (a.NSC < 2) a.NSC = 2;
             if (a.NSI < 2) a.NSI = 2;
-            smem = sweep_layout(a, a.nwA * GPW, wta);
+            smem = sweep_layout(a, a.nwA * GPW, wta && !WROLE);
             if (smem <= (size_t)maxSmem) { found = true; break; }
         }
     }
@@ -560,6 +703,9 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
         SGBM_CUDA_CHECK(cudaMemsetAsync(a.trace, 0, traceBytes, st));
         a.traceStrip = a.nstrips / 2;
     }
+    if (getenv("SGBM_SWEEP_VERBOSE"))
+        fprintf(stderr, "sweep: wrole=%d wta=%d strips=%d SW=%d R=%d NB=%d nwV=%d nwA=%d nwW=%d wPass=%d K=%d NSC=%d NSI=%d threads=%d smem=%zu\n",
+                (int)WROLE, (int)wta, a.nstrips, a.SW, a.R, a.NB, a.nwV, a.nwA, a.nwW, a.wPass, a.K, a.NSC, a.NSI, threads, smem);
     void *args[] = {&a};
     SGBM_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)kern, dim3(a.nstrips), dim3(threads), args, smem, st));
     sgbm_count_launch(1);
@@ -576,9 +722,24 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
     return 0;
 }
 
+// the winner-take-all sweep first tries the kernel with the dedicated WTA role (SGBM_SWEEP_W=0 disables it)
+template <int NREG, int LPC, bool SAT>
+static int launch_sweep_any(const VertArgs &va, int numSMs, cudaStream_t st)
+{
+    if (va.sout == nullptr) {
+        bool w = true;
+        if (const char *e = getenv("SGBM_SWEEP_W")) w = atoi(e) != 0;
+        if (w) {
+            const int rc = launch_sweep_t<NREG, LPC, SAT, true>(va, numSMs, st);
+            if (rc <= 0) return rc;
+        }
+    }
+    return launch_sweep_t<NREG, LPC, SAT, false>(va, numSMs, st);
+}
+
 #define SWEEP_DISPATCH(NREG_, LPC_)                                                               \
     if (g.nreg == NREG_ && g.lpc == LPC_)                                                         \
-        return sat ? launch_sweep_t<NREG_, LPC_, true>(a, numSMs, st) : launch_sweep_t<NREG_, LPC_, false>(a, numSMs, st);
+        return sat ? launch_sweep_any<NREG_, LPC_, true>(a, numSMs, st) : launch_sweep_any<NREG_, LPC_, false>(a, numSMs, st);
 
 int sgbm_launch_sweep(const VertArgs &a, int numSMs, cudaStream_t st)
 {
