@@ -15,7 +15,7 @@
 // ---- launchers implemented in the other translation units -------------------------------------
 int sgbm_launch_prefilter(const Geo &g, const uint8_t *left, const uint8_t *right, long long pitch, uint8_t *planes, cudaStream_t st);
 int sgbm_launch_cost(const Geo &g, const uint8_t *planes, uint16_t *out, int y0, int nrows, int ylo, int zeroTail, cudaStream_t st);
-int sgbm_launch_prefilter2(const Geo &g, const uint8_t *left, const uint8_t *right, long long pitch, uint8_t *planes, int eshift, cudaStream_t st);
+int sgbm_launch_prefilter2(const Geo &g, const uint8_t *left, const uint8_t *right, long long pitch, uint8_t *planes, int eshift, int only3, cudaStream_t st);
 int sgbm_cost3_supported(const Geo &g);
 int sgbm_cost3_eshift(const Geo &g);
 int sgbm_launch_cost2(const Geo &g, const uint8_t *planes, uint16_t *out, int y0, int nrows, int ylo, int zeroTail, cudaStream_t st);
@@ -320,7 +320,7 @@ static int compute_frame(sgbm_handle *h, const Geo &g, const WsLayout &L, const 
         cost3 = rc == 1;
     }
     if (cost2) {
-        if ((rc = sgbm_launch_prefilter2(g, left, right, pitch, planes, cost3 ? sgbm_cost3_eshift(g) : 0, st))) return rc;
+        if ((rc = sgbm_launch_prefilter2(g, left, right, pitch, planes, cost3 ? sgbm_cost3_eshift(g) : 0, cost3 ? 1 : 0, st))) return rc;
         if ((rc = prof_mark(h, ST_PREFILTER, st))) return rc;
         // third generation (sgbm_cost3.cu): register-resident pixel costs; 1-channel, blockSize <= 11
         if (cost3 && (rc = sgbm_launch_cost3(g, planes, C, 0, g.H, 0, st)))

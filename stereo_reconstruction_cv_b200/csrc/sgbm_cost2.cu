@@ -68,7 +68,7 @@ __device__ __forceinline__ void pf2_six(const uint8_t *img, long long pitch, int
 }
 
 __global__ void k_prefilter2(const uint8_t *left, const uint8_t *right, long long pitch, int W, int H, int cn, int ftzero,
-                             uint8_t *leftP, int PL, uint32_t *rpairs, int RPW, uint4 *leftX, int eshift)
+                             uint8_t *leftP, int PL, uint32_t *rpairs, int RPW, uint4 *leftX, int eshift, int only3)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
@@ -78,8 +78,10 @@ __global__ void k_prefilter2(const uint8_t *left, const uint8_t *right, long lon
     int a[6];
     if (im == 0) {
         pf2_six(left, pitch, cn, c, W, H, x, y, ftzero, a);
+        if (!only3) {
 #pragma unroll
-        for (int p = 0; p < 6; p++) leftP[((size_t)(c * 6 + p) * H + y) * PL + x] = (uint8_t)a[p];
+            for (int p = 0; p < 6; p++) leftP[((size_t)(c * 6 + p) * H + y) * PL + x] = (uint8_t)a[p];
+        }
         if (leftX) {                           // cn == 1: packed-expanded operands for k_cost3
             uint4 *o = leftX + ((size_t)y * W + x) * 2;
             // per plane (g, t): u + K, K - u, K - u_hi, u_lo + K   (K = 256, the bias of k_cost3)
@@ -87,6 +89,7 @@ __global__ void k_prefilter2(const uint8_t *left, const uint8_t *right, long lon
             o[1] = make_uint4((a[3] + 256u) * 0x10001u, (256u - a[3]) * 0x10001u, (256u - a[5]) * 0x10001u, (a[4] + 256u) * 0x10001u);
         }
     } else {
+        if (only3 && (x & 1)) return;          // k_cost3 reads the even-parity pair words only
         int b[6];
         pf2_six(right, pitch, cn, c, W, H, x, y, ftzero, a);
         pf2_six(right, pitch, cn, c, W, H, min(x + 1, W - 1), y, ftzero, b);
@@ -98,12 +101,12 @@ __global__ void k_prefilter2(const uint8_t *left, const uint8_t *right, long lon
 }
 
 int sgbm_launch_prefilter2(const Geo &g, const uint8_t *left, const uint8_t *right, long long pitch, uint8_t *planes,
-                           int eshift, cudaStream_t st)
+                           int eshift, int only3, cudaStream_t st)
 {
     dim3 grid((g.W + 255) / 256, g.H, 2 * g.cn);
     k_prefilter2<<<grid, 256, 0, st>>>(left, right, pitch, g.W, g.H, g.cn, g.ftzero, planes, sgbm_cost2_left_pitch(g),
                                        reinterpret_cast<uint32_t *>(planes + cost2_right_offset(g)), sgbm_cost2_rpw(g),
-                                       g.cn == 1 ? reinterpret_cast<uint4 *>(planes + sgbm_cost2_leftx_offset(g)) : nullptr, eshift);
+                                       g.cn == 1 ? reinterpret_cast<uint4 *>(planes + sgbm_cost2_leftx_offset(g)) : nullptr, eshift, only3);
     sgbm_count_launch(1);
     SGBM_CUDA_CHECK(cudaGetLastError());
     return 0;

@@ -650,7 +650,7 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
     int R = 8;
     if (const char *e = getenv("SGBM_VR")) R = atoi(e) > 0 ? atoi(e) : 1;
     if (R > 16) R = 16;
-    int Kwant = WROLE ? 4 : 3, NSCwant = 5, NSIwant = 3;
+    int Kwant = 5, NSCwant = 5, NSIwant = 3;
     if (const char *e = getenv("SGBM_SWEEP_K")) Kwant = atoi(e) >= 1 && atoi(e) <= 8 ? atoi(e) : Kwant;
     if (const char *e = getenv("SGBM_SWEEP_NSC")) NSCwant = atoi(e) >= 2 && atoi(e) <= 8 ? atoi(e) : NSCwant;
     if (const char *e = getenv("SGBM_SWEEP_NSI")) NSIwant = atoi(e) >= 2 && atoi(e) <= 8 ? atoi(e) : NSIwant;
