@@ -41,7 +41,7 @@ struct SweepArgs {
     int NSC, NSI, K, nAB;            // ring depths (cost rows, input rows, S slots), input volumes
     unsigned int stgCOff, stgIOff, pOff, ssmOff, barOff;
     int backward;
-    uint16_t *haloA, *haloC;         // [nstrips][4][R][Dp + 8]
+    uint16_t *haloA, *haloC;         // [nstrips][64 / R][R][Dp + 8]
     unsigned int *flagA, *flagC;     // [nstrips][R] super-steps published per column
     int dbgNoSync;
     unsigned int urMagic;            // floor(2^32 / (100 - uniquenessRatio)) + 1
@@ -49,11 +49,17 @@ struct SweepArgs {
     int traceStrip;
 };
 
+// clock64 time stamps of one strip: compiled in only with -DSGBM_SWEEP_TRACING (make TRACE=1); the
+// predicated-off stamps cost ~12 instructions per warp and row otherwise
+#ifndef SGBM_SWEEP_TRACING
+#define SWEEP_TR(ROLE, IDX, COND) do { } while (0)
+#else
 #define SWEEP_TR(ROLE, IDX, COND)                                                                          \
     do {                                                                                                   \
         if (a.trace && (COND) && (threadIdx.x & 31) == 0 && (int)blockIdx.x == a.traceStrip)                \
             a.trace[((size_t)t * 4 + (ROLE)) * 8 + (IDX)] = (unsigned long long)clock64();                 \
     } while (0)
+#endif
 
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
@@ -311,11 +317,15 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
     const bool hasNbr = DIR > 0 ? strip > 0 : strip < a.nstrips - 1;
     const bool canPub = DIR > 0 ? strip < a.nstrips - 1 : strip > 0;
     const size_t haloStride = (size_t)Dp + 8;
-    uint16_t *haloOut = (DIR > 0 ? a.haloA : a.haloC) + (size_t)strip * 4 * R * haloStride;
+    // Halo ring: 64 column entries per strip = HS = 64 / R super-step slots.  A strip's publishing role can
+    // run ahead of the neighbour's consuming role by the S-ring depth plus one super-step, i.e. by up to
+    // (K + R) / R + 1 slots, and nothing but the depth of this ring holds it back.
+    const int HS = 64 / R;
+    uint16_t *haloOut = (DIR > 0 ? a.haloA : a.haloC) + (size_t)strip * 64 * haloStride;
     unsigned int *flagOut = (DIR > 0 ? a.flagA : a.flagC) + (size_t)strip * R;
     const int nbr = DIR > 0 ? strip - 1 : strip + 1;
     const int hidx = DIR > 0 ? i : R - 1 - i;             // which published column chain i continues
-    const uint16_t *haloIn = (DIR > 0 ? a.haloA : a.haloC) + ((size_t)nbr * 4 * R + hidx) * haloStride;
+    const uint16_t *haloIn = (DIR > 0 ? a.haloA : a.haloC) + ((size_t)nbr * 64 + hidx) * haloStride;
     const unsigned int *flagIn = (DIR > 0 ? a.flagA : a.flagC) + (size_t)nbr * R + hidx;
     uint16_t *ssm = s.ssm + (size_t)gg * Dp;
 
@@ -342,7 +352,7 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
                 }
                 __syncwarp();
                 if (restart) {
-                    const uint16_t *h = haloIn + (size_t)((n - 1) & 3) * R * haloStride;
+                    const uint16_t *h = haloIn + (size_t)((n - 1) % HS) * R * haloStride;
                     load_vec_l2<NREG, LPC>(L, h, lg);
                     m = __ldcg(reinterpret_cast<const unsigned int *>(h + Dp));
                 }
@@ -383,7 +393,7 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
             const int pi = DIR > 0 ? col - (xe - R) : col - xs;
             const bool pub = own && pi >= 0 && pi < R;
             if (pub) {
-                uint16_t *h = haloOut + ((size_t)(n & 3) * R + pi) * haloStride;
+                uint16_t *h = haloOut + ((size_t)(n % HS) * R + pi) * haloStride;
                 store_vec<NREG, LPC>(Ln, h, lg);
                 if (lg == 0) *reinterpret_cast<unsigned int *>(h + Dp) = mN;
             }
@@ -647,8 +657,12 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
     const bool wta = va.sout == nullptr;
     if (WROLE && !wta) return 1;
     const int maxThreads = SweepMaxThreads<NREG, WROLE>::value;
+    // Rows per super-step.  R = 4 .. 8 are validated (bit-exact and deterministic over hundreds of frames);
+    // with R <= 3 a stress run at 1280x720 D=128 ended in a launch failure / rare mismatches that are not
+    // understood yet, so those are not offered: geometries that would need them use k_vertical instead.
+    const int Rmin = 4;
     int R = 8;
-    if (const char *e = getenv("SGBM_VR")) R = atoi(e) > 0 ? atoi(e) : 1;
+    if (const char *e = getenv("SGBM_VR")) R = atoi(e) >= Rmin ? atoi(e) : Rmin;
     if (R > 16) R = 16;
     int Kwant = 5, NSCwant = 5, NSIwant = 3;
     if (const char *e = getenv("SGBM_SWEEP_K")) Kwant = atoi(e) >= 1 && atoi(e) <= 8 ? atoi(e) : Kwant;
@@ -657,7 +671,7 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
     int threads = 0;
     size_t smem = 0;
     bool found = false;
-    for (; R >= 1 && !found; R--) {
+    for (; R >= Rmin && !found; R--) {
         int nstrips = numSMs;
         const int minCols = R > 2 ? R : 2;                // every strip owns >= R (and >= 2) columns
         if (nstrips > g.W1 / minCols) nstrips = g.W1 / minCols;
@@ -697,6 +711,9 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
     SGBM_CUDA_CHECK(cudaMemsetAsync(a.flagA, 0, sizeof(unsigned int) * 2 * (size_t)a.nstrips * 16, st));
     a.flagC = a.flagA + (size_t)a.nstrips * 16;
     const char *tracePath = getenv("SGBM_SWEEP_TRACE");       // debug: dump one strip's time stamps to a file
+#ifndef SGBM_SWEEP_TRACING
+    if (tracePath) { fprintf(stderr, "SGBM_SWEEP_TRACE needs a build with make TRACE=1\n"); tracePath = nullptr; }
+#endif
     const size_t traceBytes = (size_t)g.H * 4 * 8 * sizeof(unsigned long long);
     if (tracePath) {
         SGBM_CUDA_CHECK(cudaMalloc(&a.trace, traceBytes));

@@ -272,3 +272,49 @@ def test_host_batch_pipeline(sg):
         assert out.shape == (B, H, W) and out.dtype == np.int16
         for i in range(B):
             assert _mismatch(out[i], oracle.compute(p, pairs[i][0], pairs[i][1])) == 0, "frame %d of batch %d" % (i, B)
+
+
+# ------------------------------------------------------------------------------------------------
+# the sweep's strip hand-off: every legal number of rows per super-step, wide enough for many strips
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("R", [4, 5, 6, 7, 8])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_sweep_rows_per_superstep(sg, monkeypatch, R, mode):
+    W, H, D = 1500, 96, 32
+    l, r, _ = make_pair(W, H, D, seed=90 + R)
+    p = OracleParams(0, D, 5, 200, 800, 1, 63, 10, 0, 0, mode)
+    ref = oracle.compute(p, l, r)
+    monkeypatch.setenv("SGBM_VR", str(R))
+    st = sg.StereoSGBM_create(**_kw(p))
+    for rep in range(3):                       # hand-off races are timing dependent: repeat
+        assert _mismatch(st.compute(l, r), ref) == 0, (R, mode, rep)
+
+
+@pytest.mark.parametrize("env", [{}, {"SGBM_SWEEP_W": "0"}, {"SGBM_SWEEP": "0"}, {"SGBM_COST3": "0"}, {"SGBM_COST2": "0"}])
+def test_kernel_generations_agree(sg, monkeypatch, env):
+    """The fallback kernels (sweep without the WTA role, lock-step vertical kernel, cost generations 1/2)
+    stay bit-exact: they serve the geometries the newest kernels do not hold."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    W, H, D = 700, 80, 64
+    l, r, _ = make_pair(W, H, D, seed=11)
+    for mode in (0, 1, 2):
+        p = OracleParams(0, D, 5, 200, 800, 1, 63, 10, 100, 32, mode)
+        assert _mismatch(sg.StereoSGBM_create(**_kw(p)).compute(l, r), oracle.compute(p, l, r)) == 0, (env, mode)
+
+
+def test_repeatability_under_load(sg):
+    """Strip hand-offs and role hand-offs are timing dependent: 150 back-to-back frames of a
+    many-strip geometry must give the same disparity every time (and the oracle's)."""
+    import torch
+    W, H, D = 1280, 360, 128
+    frames = [make_pair(W, H, D, seed=s)[:2] for s in range(2)]
+    for mode in (0, 1):
+        p = OracleParams(0, D, 5, 200, 800, 1, 63, 10, 100, 32, mode)
+        st = sg.StereoSGBM_create(**_kw(p))
+        lt = [torch.from_numpy(f[0]).cuda() for f in frames]
+        rt = [torch.from_numpy(f[1]).cuda() for f in frames]
+        ref = [torch.from_numpy(oracle.compute(p, f[0], f[1])).cuda() for f in frames]
+        for it in range(150):
+            d = st.compute(lt[it % 2], rt[it % 2])
+            assert bool((d == ref[it % 2]).all()), (mode, it)
