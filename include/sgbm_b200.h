@@ -148,6 +148,15 @@ int sgbm_debug_fetch(sgbm_handle *h, int which, void *host_dst, size_t bytes);
 
 
 /*
+ * Deferred error of the asynchronous entry points.  The sweep kernels bound every hand-off wait; a wait
+ * that makes no progress for ~2 s (a protocol error) makes the kernel drain instead of hanging the GPU.
+ * sgbm_compute reports that for an earlier frame at its next call, sgbm_compute_host before it returns,
+ * and sgbm_status on demand (after the caller synchronised its stream).  0 = ok.  No counterpart in cv2:
+ * StereoSGBM.compute (main.ipynb:668) is synchronous.
+ */
+int sgbm_status(sgbm_handle *h);
+
+/*
  * Measurement hooks for bench.py.  sgbm_kernel_launches: number of CUDA kernels this library has
  * launched in the calling process so far.  sgbm_profile_enable(h,1): record CUDA events around
  * every stage of compute() on the compute stream; sgbm_profile_read synchronises that stream and

@@ -15,6 +15,7 @@ SYMBOLS = [
     "sgbm_reproject_compact_scratch_bytes", "sgbm_filter_speckles", "sgbm_median3x3",
     "sgbm_debug_keep", "sgbm_debug_fetch", "sgbm_microbench_int16", "sgbm_kernel_launches",
     "sgbm_profile_enable", "sgbm_profile_read", "sgbm_init_rectify_map", "sgbm_remap_linear_u8",
+    "sgbm_status",
 ]
 
 
@@ -60,6 +61,7 @@ def lib():
     L.sgbm_median3x3.argtypes = [vp, vp, i, i, vp]
     L.sgbm_init_rectify_map.argtypes = [vp, vp, i, vp, vp, i, i, i, vp, vp, vp]
     L.sgbm_remap_linear_u8.argtypes = [vp, i, i, i, pd, vp, vp, i, i, vp, pd, vp]
+    L.sgbm_status.argtypes = [vp]
     L.sgbm_debug_keep.argtypes = [vp, i]
     L.sgbm_debug_fetch.argtypes = [vp, i, vp, sz]
     L.sgbm_microbench_int16.argtypes = [i, C.POINTER(C.c_double)]

@@ -76,6 +76,8 @@ struct sgbm_handle {
     size_t hostInBytes[2] = {0, 0}, hostOutBytes[2] = {0, 0}, devInBytes[2] = {0, 0}, devOutBytes[2] = {0, 0};
     cudaStream_t ownStream = nullptr, inStream = nullptr, outStream = nullptr;
     cudaEvent_t evIn[2] = {nullptr, nullptr}, evComp[2] = {nullptr, nullptr}, evOut[2] = {nullptr, nullptr};
+    unsigned int *watch = nullptr;   // pinned copy of the sweep watchdog words
+    unsigned int *watchDev = nullptr;
     // debug
     int keep = 0;
     Geo lastGeo{};
@@ -167,7 +169,7 @@ static int make_geo(const sgbm_params &p, int W, int H, int cn, Geo &g)
 }
 
 struct WsLayout {
-    size_t planes, C, LhA, LhB, Calt, raw, d2key, med, speck, haloA, haloC, flags, sdbg, total;
+    size_t planes, C, LhA, LhB, Calt, raw, d2key, med, speck, haloA, haloC, flags, watch, sdbg, total;
 };
 
 static void ws_layout(const Geo &g, const sgbm_params &p, int numSMs, int keep, WsLayout &L)
@@ -175,6 +177,7 @@ static void ws_layout(const Geo &g, const sgbm_params &p, int numSMs, int keep, 
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     size_t vol = (size_t)g.rowStride * g.H * 2;
+    L.watch = take(64);       // hand-off watchdog of the sweep (sgbm_sweep.cu); first, so its place never moves
     {   // prefilter output: the larger of the two generations' formats (sgbm_cost.cu / sgbm_cost2.cu)
         const size_t v1 = (size_t)2 * g.cn * 6 * g.W * g.H, v2 = sgbm_cost2_planes_bytes(g);
         L.planes = take(v1 > v2 ? v1 : v2);
@@ -191,7 +194,7 @@ static void ws_layout(const Geo &g, const sgbm_params &p, int numSMs, int keep, 
     const int maxR = 16;
     L.haloA = take((size_t)maxStrips * 4 * maxR * (g.Dp + 8) * 2);    // 4 super-step slots (sgbm_sweep.cu)
     L.haloC = take((size_t)maxStrips * 4 * maxR * (g.Dp + 8) * 2);
-    L.flags = take((size_t)2 * maxStrips * maxR * 4);                 // one flag per published column
+    L.flags = take((size_t)2 * maxStrips * 64 * 4);                   // one flag per halo ring entry
     L.sdbg = take(keep ? vol : 16);
     L.total = off;
 }
@@ -234,6 +237,7 @@ extern "C" int sgbm_destroy(sgbm_handle *h)
 {
     if (!h) return 0;
     if (h->ws) cudaFree(h->ws);
+    if (h->watch) cudaFreeHost(h->watch);
     for (int i = 0; i < 2; i++) {
         if (h->devIn[i]) cudaFree(h->devIn[i]);
         if (h->devOut[i]) cudaFree(h->devOut[i]);
@@ -292,7 +296,20 @@ static int ensure_ws(sgbm_handle *h, size_t bytes, cudaStream_t st)
         return sgbm_fail(SGBM_E_NOMEM, "cudaMalloc of %zu workspace bytes failed: %s", bytes, cudaGetErrorString(e));
     }
     h->wsBytes = bytes;
+    // zero it once: the padding words of the volumes are never written, and the sweep watchdog is sticky
+    SGBM_CUDA_CHECK(cudaMemsetAsync(h->ws, 0, bytes, st));
     return 0;
+}
+
+// Reports (once) a sweep hand-off that timed out in a frame that has completed; see sgbm_sweep.cu.
+static int check_watch(sgbm_handle *h, cudaStream_t st)
+{
+    if (!h->watch || h->watch[0] == 0u) return 0;
+    const unsigned strip = h->watch[1], warp = h->watch[2], id = h->watch[3], row = h->watch[4];
+    h->watch[0] = 0u;
+    if (h->watchDev) cudaMemsetAsync(h->watchDev, 0, 32, st);
+    return sgbm_fail(SGBM_E_CUDA, "sweep hand-off timed out (strip %u, warp %u, wait %u, row %u): the frame's disparity is invalid",
+                     strip, warp, id, row);
 }
 
 // One frame: the kernel schedule for each mode.
@@ -307,6 +324,12 @@ static int compute_frame(sgbm_handle *h, const Geo &g, const WsLayout &L, const 
     int16_t *raw = (int16_t *)(base + L.raw), *med = (int16_t *)(base + L.med);
     unsigned int *d2key = (unsigned int *)(base + L.d2key);
     int rc;
+    if (!h->watch) {
+        SGBM_CUDA_CHECK(cudaMallocHost((void **)&h->watch, 32));
+        memset(h->watch, 0, 32);
+    }
+    h->watchDev = (unsigned int *)(base + L.watch);
+    if ((rc = check_watch(h, st))) return rc;               // a previous frame's sweep gave up
     if ((rc = prof_mark(h, ST_START, st))) return rc;
     // second-generation prefilter + cost kernels (sgbm_cost2.cu); the first generation stays as the
     // fallback for geometries the new kernel does not hold (rc == 1) and for A/B runs (SGBM_COST2=0)
@@ -370,6 +393,7 @@ static int compute_frame(sgbm_handle *h, const Geo &g, const WsLayout &L, const 
     a.haloA = (uint16_t *)(base + L.haloA); a.haloC = (uint16_t *)(base + L.haloC);
     a.flagA = (unsigned int *)(base + L.flags); a.flagC = a.flagA + (g.W1 < h->numSMs ? g.W1 : h->numSMs);
     a.ss = ss; a.ov = ov;
+    a.watchDev = h->watchDev; a.watchHost = h->watch;
     a.dbgNoSync = getenv("SGBM_DBG_NOSYNC") ? 1 : 0;
     a.sdbg = h->keep ? (uint16_t *)(base + L.sdbg) : nullptr;
     switch (p.mode) {
@@ -520,7 +544,13 @@ extern "C" int sgbm_compute_host(sgbm_handle *h, const uint8_t *left, const uint
     for (int b = batch >= 2 ? batch - 2 : 0; b < batch; b++)
         if ((rc = drain(b))) return rc;
     SGBM_CUDA_CHECK(cudaStreamSynchronize(st));
-    return 0;
+    return check_watch(h, st);
+}
+
+extern "C" int sgbm_status(sgbm_handle *h)
+{
+    if (!h) return sgbm_fail(SGBM_E_INVALID_ARG, "null handle");
+    return check_watch(h, h->ownStream);
 }
 
 extern "C" int sgbm_disp_to_float(const int16_t *disp_x16, int W, int H, float *out, void *cuda_stream)

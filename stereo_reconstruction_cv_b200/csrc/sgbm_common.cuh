@@ -226,6 +226,8 @@ struct VertArgs {
     unsigned int *flagA;      // [nstrips] super-steps published
     unsigned int *flagC;      // unused
     int dbgNoSync;            // experiment only: skip neighbour-strip waits (results invalid)
+    unsigned int *watchDev;   // [8] device words of the sweep's hand-off watchdog (sticky until reported)
+    unsigned int *watchHost;  // pinned host copy, refreshed after every sweep (or null)
 };
 
 #define SGBM_CUDA_CHECK(call)                                                              \

@@ -42,9 +42,10 @@ struct SweepArgs {
     unsigned int stgCOff, stgIOff, pOff, ssmOff, barOff;
     int backward;
     uint16_t *haloA, *haloC;         // [nstrips][64 / R][R][Dp + 8]
-    unsigned int *flagA, *flagC;     // [nstrips][R] super-steps published per column
+    unsigned int *flagA, *flagC;     // [nstrips][64 / R][R] super-step (+1) each halo ring entry was last published for
     int dbgNoSync;
     unsigned int urMagic;            // floor(2^32 / (100 - uniquenessRatio)) + 1
+    unsigned int *dbg;               // [8] hand-off watchdog: {tripped, strip, warp, wait id, row, ...}, zeroed per launch
     unsigned long long *trace;       // debug: clock64 time stamps of one strip [row][role 4][8] (or null)
     int traceStrip;
 };
@@ -65,6 +66,57 @@ struct SweepArgs {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded waits of the sweep.  A hand-off that makes no progress for ~2 s (a protocol error: it never
+// happens in the validated configurations) does not trap -- that would poison the CUDA context -- but
+// records where it happened, raises the abort word and returns; every other wait then returns at once,
+// the kernel drains with garbage, and the host reports SGBM_E_CUDA for the frame.
+#define SWEEP_WAIT_LIMIT 4000000000ll
+#ifdef SGBM_SWEEP_TRACING
+__device__ unsigned int g_sweep_prog[1024 * 8];          // tracing builds: current row of every role of every strip
+#define SWEEP_PROG(ROLE, COND) do { if ((COND) && (threadIdx.x & 31) == 0) g_sweep_prog[blockIdx.x * 8 + (ROLE)] = (unsigned)t; } while (0)
+#else
+#define SWEEP_PROG(ROLE, COND) do { } while (0)
+#endif
+__device__ __noinline__ void sweep_timeout(unsigned int *dbg, int id, int t)
+{
+    if (atomicExch(&dbg[0], 1u) == 0u) {
+        dbg[1] = blockIdx.x; dbg[2] = threadIdx.x >> 5; dbg[3] = (unsigned)id; dbg[4] = (unsigned)t;
+        __threadfence();
+#ifdef SGBM_SWEEP_TRACING
+        for (int s = (int)blockIdx.x - 3; s <= (int)blockIdx.x + 3; s++)
+            if (s >= 0 && s < (int)gridDim.x)
+                printf("strip %d: V %u  A0 %u  Alast %u  C0 %u  Clast %u  W %u  P %u\n", s, g_sweep_prog[s * 8 + 0], g_sweep_prog[s * 8 + 1],
+                       g_sweep_prog[s * 8 + 2], g_sweep_prog[s * 8 + 3], g_sweep_prog[s * 8 + 4], g_sweep_prog[s * 8 + 5], g_sweep_prog[s * 8 + 6]);
+#endif
+    }
+}
+__device__ __forceinline__ void sweep_wait(const SweepArgs &a, uint64_t *bar, uint32_t parity, int id, int t)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    // the retry loop stays inline PTX (no call, two scratch registers): waiting here is the normal case
+    uint32_t to;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .u32 f;\n\t"
+        ".reg .u64 c0, c1;\n\t"
+        "mov.u32 %0, 0;\n\t"
+        "mov.u64 c0, %%clock64;\n"
+        "SGBM_SW_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x186A0;\n\t"
+        "@p bra SGBM_SW_DONE;\n\t"
+        "ld.volatile.global.u32 f, [%3];\n\t"
+        "setp.ne.u32 q, f, 0;\n\t"
+        "@q bra SGBM_SW_DONE;\n\t"
+        "mov.u64 c1, %%clock64;\n\t"
+        "sub.u64 c1, c1, c0;\n\t"
+        "setp.lt.u64 q, c1, 4000000000;\n\t"
+        "@q bra SGBM_SW_WAIT;\n\t"
+        "mov.u32 %0, 1;\n"
+        "SGBM_SW_DONE:\n\t"
+        "}" : "=r"(to) : "r"(smem_u32(bar)), "r"(parity), "l"(a.dbg) : "memory");
+    if (to) sweep_timeout(a.dbg, id, t);
 }
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p)
 {
@@ -124,12 +176,12 @@ __device__ __forceinline__ void sweep_producer(const SweepArgs &a, const SweepSm
     for (int t = 0; t < nRows; t++) {
         const int y = yBegin + t * yStep;
         SWEEP_TR(3, 0, true);
-        if (t >= a.NSC) mbar_wait(&s.emptyC[sc], pc ^ 1u);
+        if (t >= a.NSC) sweep_wait(a, &s.emptyC[sc], pc ^ 1u, 1, t);
         SWEEP_TR(3, 1, true);
         mbar_expect_tx(&s.fullC[sc], bytesC);
         bulk_g2s(s.stgC + ((size_t)sc * ngC + (clo - scol0)) * Dp, a.C + (size_t)y * g.rowStride + (size_t)clo * Dp, bytesC,
                  &s.fullC[sc]);
-        if (t >= a.NSI) mbar_wait(&s.emptyI[si], pi ^ 1u);
+        if (t >= a.NSI) sweep_wait(a, &s.emptyI[si], pi ^ 1u, 2, t);
         const size_t off = (size_t)y * g.rowStride + (size_t)xs * Dp;
         mbar_expect_tx(&s.fullI[si], bytesI * (uint32_t)a.nAB);
         bulk_g2s(s.stgI + (size_t)(si * a.nAB + 0) * a.SW * Dp, a.inA + off, bytesI, &s.fullI[si]);
@@ -171,8 +223,9 @@ __device__ __forceinline__ void sweep_role_v(const SweepArgs &a, const SweepSmem
     bool okC = false;                                     // early probe of the next row's cost stage
     for (int t = 0; t < nRows; t++) {
         uint32_t S[NREG];
+        SWEEP_PROG(0, rwarp == 0);
         SWEEP_TR(0, 0, rwarp == 0);
-        if (!okC) mbar_wait(&s.fullC[sc], pc);
+        if (!okC) sweep_wait(a, &s.fullC[sc], pc, 3, t);
         SWEEP_TR(0, 1, rwarp == 0);
         // probes whose latency hides behind the path step
         const bool okI = mbar_test_wait(&s.fullI[si], pi);
@@ -185,7 +238,7 @@ __device__ __forceinline__ void sweep_role_v(const SweepArgs &a, const SweepSmem
             mB = path_step<NREG, LPC>(LB, LB, mB, Cc, P1p, P2mP1p, lg, lastLane);   // in place (reads run ahead of writes)
         }
         SWEEP_TR(0, 2, rwarp == 0);
-        if (!okI) mbar_wait(&s.fullI[si], pi);
+        if (!okI) sweep_wait(a, &s.fullI[si], pi, 4, t);
         load_vec<NREG, LPC>(S, s.stgI + iOff, lg);
 #pragma unroll
         for (int j = 0; j < NREG; j++) S[j] = sacc<SAT>(S[j], LB[j]);
@@ -196,7 +249,7 @@ __device__ __forceinline__ void sweep_role_v(const SweepArgs &a, const SweepSmem
             for (int j = 0; j < NREG; j++) S[j] = sacc<SAT>(S[j], Bv[j]);
         }
         SWEEP_TR(0, 3, rwarp == 0);
-        if (!okP) mbar_wait(&s.freeP[k], pk ^ 1u);
+        if (!okP) sweep_wait(a, &s.freeP[k], pk ^ 1u, 5, t);
         SWEEP_TR(0, 4, rwarp == 0);
         if (own) store_vec<NREG, LPC>(S, s.P + pOff, lg);
         __syncwarp();
@@ -322,11 +375,16 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
     // (K + R) / R + 1 slots, and nothing but the depth of this ring holds it back.
     const int HS = 64 / R;
     uint16_t *haloOut = (DIR > 0 ? a.haloA : a.haloC) + (size_t)strip * 64 * haloStride;
-    unsigned int *flagOut = (DIR > 0 ? a.flagA : a.flagC) + (size_t)strip * R;
+    // One flag per halo ring ENTRY (slot, column), not per column: the warps of a role drift apart by up to
+    // the S-ring depth, so the same column can be published for super-step n+1 by one warp before another
+    // warp has published it for super-step n.  A per-column "latest super-step" flag then lets the
+    // neighbour read a slot that is not written yet, and a late smaller value can even make it wait
+    // forever (seen as rare mismatches / watchdog trips with R <= 3 rows per super-step).
+    unsigned int *flagOut = (DIR > 0 ? a.flagA : a.flagC) + (size_t)strip * 64;
     const int nbr = DIR > 0 ? strip - 1 : strip + 1;
     const int hidx = DIR > 0 ? i : R - 1 - i;             // which published column chain i continues
     const uint16_t *haloIn = (DIR > 0 ? a.haloA : a.haloC) + ((size_t)nbr * 64 + hidx) * haloStride;
-    const unsigned int *flagIn = (DIR > 0 ? a.flagA : a.flagC) + (size_t)nbr * R + hidx;
+    const unsigned int *flagIn = (DIR > 0 ? a.flagA : a.flagC) + (size_t)nbr * 64 + hidx;
     uint16_t *ssm = s.ssm + (size_t)gg * Dp;
 
     uint32_t L[NREG], m = 0;
@@ -338,16 +396,20 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
     uint32_t pc = 0, pk = 0;
     bool okC = false;                                     // early probe of the next row's cost stage
     for (int t = 0; t < nRows; t++) {
+        SWEEP_PROG(DIR > 0 ? 1 : 3, rwarp == 0);
+        SWEEP_PROG(DIR > 0 ? 2 : 4, rwarp == a.nwA - 1);
         // ---- super-step start: batch nm restarts from the neighbour's published columns -------------
         if (kk == 0 && t > 0) {
             const bool restart = exists && nm == b;
             if (restart) p = i;
             if (hasNbr) {
                 if (restart && lg == 0 && !a.dbgNoSync) {
-                    unsigned int spins = 0;
-                    while (ld_acquire_u32(flagIn) < (unsigned)n) {
+                    const long long t0 = clock64();
+                    const unsigned int *fl = flagIn + ((n - 1) % HS) * R;
+                    while (ld_acquire_u32(fl) < (unsigned)n) {
                         __nanosleep(32);
-                        if (++spins > (1u << 28)) __trap();
+                        if (*reinterpret_cast<volatile unsigned int *>(a.dbg) != 0u) break;
+                        if (clock64() - t0 > SWEEP_WAIT_LIMIT) { sweep_timeout(a.dbg, DIR > 0 ? 6 : 7, t); break; }
                     }
                 }
                 __syncwarp();
@@ -374,7 +436,7 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
         // WROLE: the finished S goes back into the slot and the winner-take-all warps release it
         uint64_t *waitBar = FINAL ? s.fullM : s.fullV, *doneBar = FINAL ? (WROLE ? s.fullW : s.freeP) : s.fullM;
         SWEEP_TR(DIR > 0 ? 1 : 2, 0, rwarp == a.nwA / 2);
-        if (!okC) mbar_wait(&s.fullC[sc], pc);
+        if (!okC) sweep_wait(a, &s.fullC[sc], pc, DIR > 0 ? 8 : 9, t);
         SWEEP_TR(DIR > 0 ? 1 : 2, 1, rwarp == a.nwA / 2);
         const bool okS = mbar_test_wait(&waitBar[k], pk);  // latency hides behind the path step
         {
@@ -400,12 +462,12 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
             __syncwarp();
             if (pub && lg == 0) {
                 __threadfence();
-                st_release_u32(flagOut + pi, (unsigned)(n + 1));
+                st_release_u32(flagOut + (n % HS) * R + pi, (unsigned)(n + 1));
             }
         }
         // ---- S slot of this row ---------------------------------------------------------------------
         SWEEP_TR(DIR > 0 ? 1 : 2, 2, rwarp == a.nwA / 2);
-        if (!okS) mbar_wait(&waitBar[k], pk);
+        if (!okS) sweep_wait(a, &waitBar[k], pk, DIR > 0 ? 10 : 11, t);
         SWEEP_TR(DIR > 0 ? 1 : 2, 3, rwarp == a.nwA / 2);
         uint32_t S[NREG];
         if (own) {
@@ -540,7 +602,8 @@ __device__ __forceinline__ void sweep_role_w(const SweepArgs &a, const SweepSmem
     uint32_t pk = 0;
     for (int t = 0; t < nRows; t++) {
         const int y = yBegin + t * yStep;
-        mbar_wait(&s.fullW[k], pk);
+        SWEEP_PROG(5, wwarp == 0);
+        sweep_wait(a, &s.fullW[k], pk, 12, t);
         for (int it = 0; it < a.wPass; it++) {
             const int gi = (it * a.nwW + wwarp) * GPW + lane / LPC;
             const bool own = gi < SW;
@@ -657,10 +720,9 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
     const bool wta = va.sout == nullptr;
     if (WROLE && !wta) return 1;
     const int maxThreads = SweepMaxThreads<NREG, WROLE>::value;
-    // Rows per super-step.  R = 4 .. 8 are validated (bit-exact and deterministic over hundreds of frames);
-    // with R <= 3 a stress run at 1280x720 D=128 ended in a launch failure / rare mismatches that are not
-    // understood yet, so those are not offered: geometries that would need them use k_vertical instead.
-    const int Rmin = 4;
+    // Rows per super-step (every value is covered by tests/test_gpu_parity.py::test_sweep_rows_per_superstep
+    // and a repeatability run; 8 is the fastest at every size measured).
+    const int Rmin = 1;
     int R = 8;
     if (const char *e = getenv("SGBM_VR")) R = atoi(e) >= Rmin ? atoi(e) : Rmin;
     if (R > 16) R = 16;
@@ -708,8 +770,9 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
     int occ = 0;
     SGBM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
     if (occ * numSMs < a.nstrips) return 1;
-    SGBM_CUDA_CHECK(cudaMemsetAsync(a.flagA, 0, sizeof(unsigned int) * 2 * (size_t)a.nstrips * 16, st));
-    a.flagC = a.flagA + (size_t)a.nstrips * 16;
+    SGBM_CUDA_CHECK(cudaMemsetAsync(a.flagA, 0, sizeof(unsigned int) * 2 * (size_t)a.nstrips * 64, st));
+    a.flagC = a.flagA + (size_t)a.nstrips * 64;
+    a.dbg = va.watchDev;                                  // sticky: zeroed with the workspace and after a report
     const char *tracePath = getenv("SGBM_SWEEP_TRACE");       // debug: dump one strip's time stamps to a file
 #ifndef SGBM_SWEEP_TRACING
     if (tracePath) { fprintf(stderr, "SGBM_SWEEP_TRACE needs a build with make TRACE=1\n"); tracePath = nullptr; }
@@ -726,6 +789,8 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
     void *args[] = {&a};
     SGBM_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)kern, dim3(a.nstrips), dim3(threads), args, smem, st));
     sgbm_count_launch(1);
+    if (va.watchHost)                                         // the caller checks it at its next synchronisation point
+        SGBM_CUDA_CHECK(cudaMemcpyAsync(va.watchHost, va.watchDev, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     if (tracePath) {
         SGBM_CUDA_CHECK(cudaStreamSynchronize(st));
         void *hbuf = malloc(traceBytes);
