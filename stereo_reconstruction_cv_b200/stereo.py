@@ -179,6 +179,10 @@ class StereoSGBM:
         return disparity
 
     # -- test hooks ----------------------------------------------------------------------------------
+    def status(self):
+        """Raise if a sweep of an already completed asynchronous compute() gave up (sgbm_status)."""
+        check(_lib.lib().sgbm_status(self._h))
+
     def _debug_keep(self, on=True):
         check(_lib.lib().sgbm_debug_keep(self._h, 1 if on else 0))
 
