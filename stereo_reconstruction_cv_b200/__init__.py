@@ -5,7 +5,7 @@ from .stereo import (DISP_SCALE, DISP_SHIFT, MODE_HH, MODE_HH4, MODE_SGBM, MODE_
                      microbench_int16, reprojectCompact, reprojectImageTo3D, initUndistortRectifyMap, remap,
                      INTER_LINEAR, CV_32F, CV_32FC1)
 
-from . import pointcloud, sharding  # noqa: E402,F401
+from . import disparity_tab, pointcloud, sharding  # noqa: E402,F401
 from .pointcloud import open3d_arrays, write_ply  # noqa: E402,F401
 from .sharding import compute_shard, gather_point_cloud, shard_range  # noqa: E402,F401
 
