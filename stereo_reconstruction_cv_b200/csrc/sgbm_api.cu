@@ -496,20 +496,30 @@ extern "C" int sgbm_compute_host(sgbm_handle *h, const uint8_t *left, const uint
     cudaStream_t st = h->ownStream;
     const size_t rowIn = (size_t)W * channels, frameIn = rowIn * H, frameOut = (size_t)W * H * 2;
     const int nslots = batch > 1 ? 2 : 1;
+    // Page-locked caller buffers (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) with dense rows
+    // are DMA'd directly; pageable ones are staged through the handle's pinned slots by the host thread.
+    auto pinned = [](const void *p) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return at.type == cudaMemoryTypeHost;
+    };
+    const bool directIn = (size_t)pitch_bytes == rowIn && pinned(left) && pinned(right);
+    const bool directOut = (size_t)out_pitch_bytes == (size_t)W * 2 && pinned(disp_out);
     for (int i = 0; i < nslots; i++) {
-        if ((rc = ensure_buf(&h->hostIn[i], &h->hostInBytes[i], 2 * frameIn, true))) return rc;
-        if ((rc = ensure_buf(&h->hostOut[i], &h->hostOutBytes[i], frameOut, true))) return rc;
+        if (!directIn && (rc = ensure_buf(&h->hostIn[i], &h->hostInBytes[i], 2 * frameIn, true))) return rc;
+        if (!directOut && (rc = ensure_buf(&h->hostOut[i], &h->hostOutBytes[i], frameOut, true))) return rc;
         if ((rc = ensure_buf(&h->devIn[i], &h->devInBytes[i], 2 * frameIn, false))) return rc;
         if ((rc = ensure_buf(&h->devOut[i], &h->devOutBytes[i], frameOut, false))) return rc;
     }
     WsLayout L;
     ws_layout(g, h->p, h->numSMs, h->keep, L);
     if ((rc = ensure_ws(h, L.total, st))) return rc;
-    // Frames are staged through pinned memory (dense rows).  Three streams: H2D, kernels, D2H; while the
-    // kernels of frame b run, the host copies frame b+1 into the other slot and frame b-1 out of it.
+    // Three streams: H2D, kernels, D2H; while the kernels of frame b run, frame b+1 goes in and frame b-1
+    // comes out (and, for pageable buffers, the host copies them into / out of the other staging slot).
     auto drain = [&](int b) -> int {                      // wait for frame b's D2H and hand the rows to the caller
         const int sl = b & 1;
         SGBM_CUDA_CHECK(cudaEventSynchronize(h->evOut[sl]));
+        if (directOut) return 0;
         uint8_t *o = (uint8_t *)disp_out + (size_t)b * out_pitch_bytes * H;
         if ((size_t)out_pitch_bytes == (size_t)W * 2) memcpy(o, h->hostOut[sl], frameOut);
         else
@@ -520,17 +530,22 @@ extern "C" int sgbm_compute_host(sgbm_handle *h, const uint8_t *left, const uint
         const int sl = nslots == 2 ? (b & 1) : 0;
         if (b >= 2 && (rc = drain(b - 2))) return rc;     // frees slot sl (its kernels and D2H are complete)
         const uint8_t *l = left + (size_t)b * pitch_bytes * H, *r = right + (size_t)b * pitch_bytes * H;
-        uint8_t *hi = (uint8_t *)h->hostIn[sl];
-        if ((size_t)pitch_bytes == rowIn) {
-            memcpy(hi, l, frameIn);
-            memcpy(hi + frameIn, r, frameIn);
+        if (directIn) {
+            SGBM_CUDA_CHECK(cudaMemcpyAsync(h->devIn[sl], l, frameIn, cudaMemcpyHostToDevice, h->inStream));
+            SGBM_CUDA_CHECK(cudaMemcpyAsync((uint8_t *)h->devIn[sl] + frameIn, r, frameIn, cudaMemcpyHostToDevice, h->inStream));
         } else {
-            for (int y = 0; y < H; y++) {
-                memcpy(hi + (size_t)y * rowIn, l + (size_t)y * pitch_bytes, rowIn);
-                memcpy(hi + frameIn + (size_t)y * rowIn, r + (size_t)y * pitch_bytes, rowIn);
+            uint8_t *hi = (uint8_t *)h->hostIn[sl];
+            if ((size_t)pitch_bytes == rowIn) {
+                memcpy(hi, l, frameIn);
+                memcpy(hi + frameIn, r, frameIn);
+            } else {
+                for (int y = 0; y < H; y++) {
+                    memcpy(hi + (size_t)y * rowIn, l + (size_t)y * pitch_bytes, rowIn);
+                    memcpy(hi + frameIn + (size_t)y * rowIn, r + (size_t)y * pitch_bytes, rowIn);
+                }
             }
+            SGBM_CUDA_CHECK(cudaMemcpyAsync(h->devIn[sl], h->hostIn[sl], 2 * frameIn, cudaMemcpyHostToDevice, h->inStream));
         }
-        SGBM_CUDA_CHECK(cudaMemcpyAsync(h->devIn[sl], h->hostIn[sl], 2 * frameIn, cudaMemcpyHostToDevice, h->inStream));
         SGBM_CUDA_CHECK(cudaEventRecord(h->evIn[sl], h->inStream));
         SGBM_CUDA_CHECK(cudaStreamWaitEvent(st, h->evIn[sl], 0));
         rc = compute_frame(h, g, L, (const uint8_t *)h->devIn[sl], (const uint8_t *)h->devIn[sl] + frameIn, (long long)rowIn,
@@ -538,8 +553,11 @@ extern "C" int sgbm_compute_host(sgbm_handle *h, const uint8_t *left, const uint
         if (rc) return rc;
         SGBM_CUDA_CHECK(cudaEventRecord(h->evComp[sl], st));
         SGBM_CUDA_CHECK(cudaStreamWaitEvent(h->outStream, h->evComp[sl], 0));
-        SGBM_CUDA_CHECK(cudaMemcpyAsync(h->hostOut[sl], h->devOut[sl], frameOut, cudaMemcpyDeviceToHost, h->outStream));
+        void *dst = directOut ? (void *)((uint8_t *)disp_out + (size_t)b * frameOut) : h->hostOut[sl];
+        SGBM_CUDA_CHECK(cudaMemcpyAsync(dst, h->devOut[sl], frameOut, cudaMemcpyDeviceToHost, h->outStream));
         SGBM_CUDA_CHECK(cudaEventRecord(h->evOut[sl], h->outStream));
+        // the next H2D into this slot's device input must not overtake these kernels
+        SGBM_CUDA_CHECK(cudaStreamWaitEvent(h->inStream, h->evComp[sl], 0));
     }
     for (int b = batch >= 2 ? batch - 2 : 0; b < batch; b++)
         if ((rc = drain(b))) return rc;
