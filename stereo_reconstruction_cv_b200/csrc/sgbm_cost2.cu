@@ -100,9 +100,77 @@ __global__ void k_prefilter2(const uint8_t *left, const uint8_t *right, long lon
     }
 }
 
+// Prefilter for the k_cost3 path (1-channel input): one block per 256-pixel row segment and image.  The
+// gradient / raw values are computed once per pixel into shared memory, the half-sample intervals from
+// those, and only what k_cost3 reads is written: 32 bytes of packed operands per left pixel, one pair
+// word per EVEN right position and plane (threads map to pair indices, so the stores are dense).
+#define PF3_TX 256
+__global__ void __launch_bounds__(PF3_TX) k_prefilter3(const uint8_t *__restrict__ left, const uint8_t *__restrict__ right,
+                                                       long long pitch, int W, int H, int ftzero, uint4 *__restrict__ leftX,
+                                                       uint32_t *__restrict__ rpairs, int RPW, int eshift)
+{
+    __shared__ uint8_t sgt[2][PF3_TX + 4];                // g, t at x0-1 .. x0+TX+1
+    __shared__ uint8_t s6[6][PF3_TX + 2];                 // the six plane values at x0 .. x0+TX
+    const int tid = threadIdx.x, x0 = blockIdx.x * PF3_TX, y = blockIdx.y, im = blockIdx.z;
+    const uint8_t *img = im ? right : left;
+    const uint8_t *r0 = img + (long long)y * pitch, *rm = img + (long long)max(y - 1, 0) * pitch,
+                  *rp = img + (long long)min(y + 1, H - 1) * pitch;
+    for (int i = tid; i < PF3_TX + 3; i += PF3_TX) {
+        const int x = x0 - 1 + i;
+        int gv = ftzero & 0xFF, tv = ftzero & 0xFF;       // columns 0 and W-1 (and outside) carry ftzero (A.1)
+        if (x > 0 && x < W - 1) {
+            const int v = 2 * ((int)r0[x + 1] - (int)r0[x - 1]) + ((int)rm[x + 1] - (int)rm[x - 1]) + ((int)rp[x + 1] - (int)rp[x - 1]);
+            gv = (min(max(v, -ftzero), ftzero) + ftzero) & 0xFF;
+            tv = r0[x];
+        }
+        sgt[0][i] = (uint8_t)gv; sgt[1][i] = (uint8_t)tv;
+    }
+    __syncthreads();
+    for (int i = tid; i < PF3_TX + 1; i += PF3_TX) {
+        const int x = x0 + i;
+        if (x < W) {
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int v0 = sgt[q][i + 1];
+                int lo = v0, hi = v0;
+                if (x > 0) { const int v1 = (v0 + sgt[q][i]) >> 1; lo = min(lo, v1); hi = max(hi, v1); }
+                if (x < W - 1) { const int v1 = (v0 + sgt[q][i + 2]) >> 1; lo = min(lo, v1); hi = max(hi, v1); }
+                s6[3 * q + 0][i] = (uint8_t)v0; s6[3 * q + 1][i] = (uint8_t)lo; s6[3 * q + 2][i] = (uint8_t)hi;
+            }
+        }
+    }
+    __syncthreads();
+    if (im == 0) {
+        const int x = x0 + tid;
+        if (x < W) {
+            const uint32_t a0 = s6[0][tid], a1 = s6[1][tid], a2 = s6[2][tid], a3 = s6[3][tid], a4 = s6[4][tid], a5 = s6[5][tid];
+            uint4 *o = leftX + ((size_t)y * W + x) * 2;
+            o[0] = make_uint4((a0 + 256u) * 0x10001u, (256u - a0) * 0x10001u, (256u - a2) * 0x10001u, (a1 + 256u) * 0x10001u);
+            o[1] = make_uint4((a3 + 256u) * 0x10001u, (256u - a3) * 0x10001u, (256u - a5) * 0x10001u, (a4 + 256u) * 0x10001u);
+        }
+    } else if (tid < PF3_TX / 2) {
+        const int i = 2 * tid, x = x0 + i;                // even right position: lo = v(x+1), hi = v(x)
+        if (x < W) {
+            const int i1 = x + 1 < W ? i + 1 : i;
+#pragma unroll
+            for (int p = 0; p < 6; p++)
+                rpairs[((size_t)p * H + y) * 2 * RPW + (x >> 1) + eshift] = (uint32_t)s6[p][i1] | ((uint32_t)s6[p][i] << 16);
+        }
+    }
+}
+
 int sgbm_launch_prefilter2(const Geo &g, const uint8_t *left, const uint8_t *right, long long pitch, uint8_t *planes,
                            int eshift, int only3, cudaStream_t st)
 {
+    if (only3 && g.cn == 1) {
+        dim3 grid3((g.W + PF3_TX - 1) / PF3_TX, g.H, 2);
+        k_prefilter3<<<grid3, PF3_TX, 0, st>>>(left, right, pitch, g.W, g.H, g.ftzero,
+                                               reinterpret_cast<uint4 *>(planes + sgbm_cost2_leftx_offset(g)),
+                                               reinterpret_cast<uint32_t *>(planes + cost2_right_offset(g)), sgbm_cost2_rpw(g), eshift);
+        sgbm_count_launch(1);
+        SGBM_CUDA_CHECK(cudaGetLastError());
+        return 0;
+    }
     dim3 grid((g.W + 255) / 256, g.H, 2 * g.cn);
     k_prefilter2<<<grid, 256, 0, st>>>(left, right, pitch, g.W, g.H, g.cn, g.ftzero, planes, sgbm_cost2_left_pitch(g),
                                        reinterpret_cast<uint32_t *>(planes + cost2_right_offset(g)), sgbm_cost2_rpw(g),
