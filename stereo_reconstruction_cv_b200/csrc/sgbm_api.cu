@@ -169,7 +169,7 @@ static int make_geo(const sgbm_params &p, int W, int H, int cn, Geo &g)
 }
 
 struct WsLayout {
-    size_t planes, C, LhA, LhB, Calt, raw, d2key, med, speck, haloA, haloC, flags, watch, sdbg, total;
+    size_t planes, C, LhA, LhB, Calt, raw, d2key, med, speck, haloA, haloC, flags, watch, rowState, sdbg, total;
 };
 
 static void ws_layout(const Geo &g, const sgbm_params &p, int numSMs, int keep, WsLayout &L)
@@ -195,6 +195,7 @@ static void ws_layout(const Geo &g, const sgbm_params &p, int numSMs, int keep, 
     L.haloA = take((size_t)maxStrips * 4 * maxR * (g.Dp + 8) * 2);    // 4 super-step slots (sgbm_sweep.cu)
     L.haloC = take((size_t)maxStrips * 4 * maxR * (g.Dp + 8) * 2);
     L.flags = take((size_t)2 * maxStrips * 64 * 4);                   // one flag per halo ring entry
+    L.rowState = take((size_t)2 * 3 * g.W1 * (g.Dp + 8) * 2);         // row-at-a-time fallback (sgbm_sweep.cu)
     L.sdbg = take(keep ? vol : 16);
     L.total = off;
 }
@@ -394,6 +395,7 @@ static int compute_frame(sgbm_handle *h, const Geo &g, const WsLayout &L, const 
     a.flagA = (unsigned int *)(base + L.flags); a.flagC = a.flagA + (g.W1 < h->numSMs ? g.W1 : h->numSMs);
     a.ss = ss; a.ov = ov;
     a.watchDev = h->watchDev; a.watchHost = h->watch;
+    a.rowState = (uint16_t *)(base + L.rowState);
     a.dbgNoSync = getenv("SGBM_DBG_NOSYNC") ? 1 : 0;
     a.sdbg = h->keep ? (uint16_t *)(base + L.sdbg) : nullptr;
     switch (p.mode) {

@@ -226,6 +226,7 @@ struct VertArgs {
     unsigned int *flagA;      // [nstrips] super-steps published
     unsigned int *flagC;      // unused
     int dbgNoSync;            // experiment only: skip neighbour-strip waits (results invalid)
+    uint16_t *rowState;       // [2][3][W1][Dp + 8] path state of the row-at-a-time fallback (sgbm_sweep.cu)
     unsigned int *watchDev;   // [8] device words of the sweep's hand-off watchdog (sticky until reported)
     unsigned int *watchHost;  // pinned host copy, refreshed after every sweep (or null)
 };

@@ -565,7 +565,7 @@ static int launch_vertical_t(VertArgs &a, int numSMs, cudaStream_t st)
     int nstrips = numSMs, SWmax = 1, threads = 32, nstg = 2;
     size_t smem = 0;
     for (;; R--) {
-        if (R < 1) return sgbm_fail(-3, "image too wide for the vertical sweep (W1=%d, lanes/column=%d, SMs=%d)", g.W1, LPC, numSMs);
+        if (R < 1) return 1;                              // too wide for this kernel: the caller goes row by row
         nstrips = numSMs;
         const int minCols = R > 2 ? R : 2;                // every strip owns >= R (and >= 2) columns
         if (nstrips > g.W1 / minCols) nstrips = g.W1 / minCols;
@@ -614,6 +614,7 @@ int sgbm_launch_horizontal(const Geo &g, const uint16_t *C, uint16_t *LhA, uint1
 }
 
 int sgbm_launch_sweep(const VertArgs &a, int numSMs, cudaStream_t st);   // sgbm_sweep.cu
+int sgbm_launch_rowstep(const VertArgs &a, cudaStream_t st);             // sgbm_sweep.cu
 
 int sgbm_launch_vertical(VertArgs &a, int ndir, int numSMs, cudaStream_t st)
 {
@@ -622,11 +623,17 @@ int sgbm_launch_vertical(VertArgs &a, int ndir, int numSMs, cudaStream_t st)
         // role-specialised sweep (sgbm_sweep.cu); the lock-step kernel below remains as the fallback for
         // geometries it cannot hold (and for A/B runs with SGBM_SWEEP=0)
         const char *e = getenv("SGBM_SWEEP");
+        if (const char *rs = getenv("SGBM_ROWSTEP")) { if (atoi(rs) != 0) return sgbm_launch_rowstep(a, st); }
         if (!e || atoi(e) != 0) {
             const int rc = sgbm_launch_sweep(a, numSMs, st);
             if (rc <= 0) return rc;
         }
-        SGBM_DISPATCH_ALL((launch_vertical_t<NREG, LPC, 3>(a, numSMs, st)))
+#define SGBM_TRY3(NREG_, LPC_) if (g.nreg == NREG_ && g.lpc == LPC_) { const int rc = launch_vertical_t<NREG_, LPC_, 3>(a, numSMs, st); if (rc <= 0) return rc; return sgbm_launch_rowstep(a, st); }
+        SGBM_TRY3(4, 2) SGBM_TRY3(4, 4) SGBM_TRY3(4, 8) SGBM_TRY3(4, 16) SGBM_TRY3(4, 32)
+        SGBM_TRY3(8, 2) SGBM_TRY3(8, 4) SGBM_TRY3(8, 8) SGBM_TRY3(8, 16) SGBM_TRY3(8, 32)
+        SGBM_TRY3(12, 2) SGBM_TRY3(12, 4) SGBM_TRY3(12, 8) SGBM_TRY3(12, 16) SGBM_TRY3(12, 32)
+        SGBM_TRY3(16, 2) SGBM_TRY3(16, 4) SGBM_TRY3(16, 8) SGBM_TRY3(16, 16) SGBM_TRY3(16, 32)
+#undef SGBM_TRY3
     } else {
         SGBM_DISPATCH_ALL((launch_vertical_t<NREG, LPC, 1>(a, numSMs, st)))
     }

@@ -819,6 +819,110 @@ static int launch_sweep_any(const VertArgs &va, int numSMs, cudaStream_t st)
     return launch_sweep_t<NREG, LPC, SAT, false>(va, numSMs, st);
 }
 
+// =================================================================================================
+// Row-at-a-time fallback: any width.  One launch per image row, one lane group per column; the state of
+// the three paths of the previous row lives in global memory ([2][3][W1][Dp + 8], ping-pong, L2 resident).
+// No device-side synchronisation at all (the launches order the rows), ~4 us per row: the last resort for
+// images whose strips do not fit the persistent kernels (e.g. 7680 wide with numDisparities = 256), and
+// an independent implementation for the tests (SGBM_ROWSTEP=1).
+// =================================================================================================
+struct RowArgs {
+    SweepArgs sw;            // g, C, inA, inB, sout, sdbg, raw, d2key, urMagic are used
+    uint16_t *state;
+    int y, first, cur;
+};
+
+template <int NREG, int LPC>
+__global__ void __launch_bounds__(128) k_rowstep(RowArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int GPW = 32 / LPC;
+    const SweepArgs &sa = a.sw;
+    const Geo &g = sa.g;
+    const int lane = threadIdx.x & 31, lg = lane % LPC;
+    const int gIn = (threadIdx.x >> 5) * GPW + lane / LPC;            // group within the CTA
+    const int xRaw = blockIdx.x * (blockDim.x / LPC) + gIn;
+    const bool own = xRaw < g.W1;
+    const int x = own ? xRaw : g.W1 - 1;
+    const int Dp = g.Dp, lastLane = g.lanesUsed - 1;
+    const size_t sst = (size_t)Dp + 8, plane = (size_t)g.W1 * sst;
+    const uint16_t *prev = a.state + (size_t)(a.cur ^ 1) * 3 * plane;
+    uint16_t *cur = a.state + (size_t)a.cur * 3 * plane;
+    const uint32_t P1p = (uint32_t)g.P1 * 0x10001u, P2mP1p = (uint32_t)(g.P2 - g.P1) * 0x10001u;
+    const size_t off = (size_t)a.y * g.rowStride + (size_t)x * Dp;
+    uint32_t Cc[NREG], S[NREG];
+    load_vec_nc<NREG, LPC>(Cc, sa.C + off, lg);
+    load_vec_nc<NREG, LPC>(S, sa.inA + off, lg);
+    if (sa.inB) {
+        uint32_t Bv[NREG];
+        load_vec_nc<NREG, LPC>(Bv, sa.inB + off, lg);
+#pragma unroll
+        for (int j = 0; j < NREG; j++) S[j] = paddmin(S[j], Bv[j], SGBM_MAX_S);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {                         // k = 0: (0,-1), 1: (-1,-1), 2: (+1,-1)
+        const int xp = x + (k == 1 ? -1 : (k == 2 ? 1 : 0));
+        uint32_t L[NREG], m = 0;
+#pragma unroll
+        for (int j = 0; j < NREG; j++) L[j] = 0;          // "predecessor outside" == L = 0, m = 0 (A.4)
+        if (!a.first && xp >= 0 && xp < g.W1) {
+            const uint16_t *p = prev + (size_t)k * plane + (size_t)xp * sst;
+            load_vec_l2<NREG, LPC>(L, p, lg);
+            m = __ldcg(reinterpret_cast<const unsigned int *>(p + Dp));
+        }
+        m = path_step<NREG, LPC>(L, L, m, Cc, P1p, P2mP1p, lg, lastLane);
+        if (own) {
+            uint16_t *q = cur + (size_t)k * plane + (size_t)x * sst;
+            store_vec<NREG, LPC>(L, q, lg);
+            if (lg == 0) *reinterpret_cast<unsigned int *>(q + Dp) = m;
+        }
+#pragma unroll
+        for (int j = 0; j < NREG; j++) S[j] = paddmin(S[j], L[j], SGBM_MAX_S);
+    }
+    if (sa.sout) {
+        if (own) store_vec<NREG, LPC>(S, sa.sout + off, lg);
+    } else {
+        if (sa.sdbg && own) store_vec<NREG, LPC>(S, sa.sdbg + off, lg);
+        sweep_wta<NREG, LPC>(sa, S, reinterpret_cast<uint16_t *>(smem) + (size_t)gIn * Dp, lg, own, x, a.y);
+    }
+}
+
+template <int NREG, int LPC>
+static int launch_rowstep_t(const VertArgs &va, cudaStream_t st)
+{
+    const Geo &g = va.g;
+    RowArgs a;
+    memset(&a, 0, sizeof(a));
+    a.sw.g = g; a.sw.C = va.C; a.sw.inA = va.inA; a.sw.inB = va.inB; a.sw.sout = va.sout; a.sw.sdbg = va.sdbg;
+    a.sw.raw = va.raw; a.sw.d2key = va.d2key;
+    a.sw.urMagic = g.UR < 99 ? 0xFFFFFFFFu / (unsigned)(100 - g.UR) + 1u : 0u;
+    a.state = va.rowState;
+    if (!a.state) return sgbm_fail(-3, "row-step fallback has no state buffer");
+    const int threads = 128, groups = threads / LPC;
+    const size_t smem = (size_t)groups * g.Dp * 2;
+    const int grid = (g.W1 + groups - 1) / groups;
+    for (int t = 0; t < g.H; t++) {
+        a.y = va.backward ? g.H - 1 - t : t;
+        a.first = t == 0;
+        a.cur = t & 1;
+        k_rowstep<NREG, LPC><<<grid, threads, smem, st>>>(a);
+    }
+    sgbm_count_launch(g.H);
+    SGBM_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+#define ROWSTEP_DISPATCH(NREG_, LPC_) if (g.nreg == NREG_ && g.lpc == LPC_) return launch_rowstep_t<NREG_, LPC_>(a, st);
+int sgbm_launch_rowstep(const VertArgs &a, cudaStream_t st)
+{
+    const Geo &g = a.g;
+    ROWSTEP_DISPATCH(4, 2) ROWSTEP_DISPATCH(4, 4) ROWSTEP_DISPATCH(4, 8) ROWSTEP_DISPATCH(4, 16) ROWSTEP_DISPATCH(4, 32)
+    ROWSTEP_DISPATCH(8, 2) ROWSTEP_DISPATCH(8, 4) ROWSTEP_DISPATCH(8, 8) ROWSTEP_DISPATCH(8, 16) ROWSTEP_DISPATCH(8, 32)
+    ROWSTEP_DISPATCH(12, 2) ROWSTEP_DISPATCH(12, 4) ROWSTEP_DISPATCH(12, 8) ROWSTEP_DISPATCH(12, 16) ROWSTEP_DISPATCH(12, 32)
+    ROWSTEP_DISPATCH(16, 2) ROWSTEP_DISPATCH(16, 4) ROWSTEP_DISPATCH(16, 8) ROWSTEP_DISPATCH(16, 16) ROWSTEP_DISPATCH(16, 32)
+    return sgbm_fail(-3, "no kernel for lane mapping nreg=%d lpc=%d", g.nreg, g.lpc);
+}
+
 #define SWEEP_DISPATCH(NREG_, LPC_)                                                               \
     if (g.nreg == NREG_ && g.lpc == LPC_)                                                         \
         return sat ? launch_sweep_any<NREG_, LPC_, true>(a, numSMs, st) : launch_sweep_any<NREG_, LPC_, false>(a, numSMs, st);

@@ -290,10 +290,11 @@ def test_sweep_rows_per_superstep(sg, monkeypatch, R, mode):
         assert _mismatch(st.compute(l, r), ref) == 0, (R, mode, rep)
 
 
-@pytest.mark.parametrize("env", [{}, {"SGBM_SWEEP_W": "0"}, {"SGBM_SWEEP": "0"}, {"SGBM_COST3": "0"}, {"SGBM_COST2": "0"}])
+@pytest.mark.parametrize("env", [{}, {"SGBM_SWEEP_W": "0"}, {"SGBM_SWEEP": "0"}, {"SGBM_ROWSTEP": "1"}, {"SGBM_COST3": "0"},
+                                 {"SGBM_COST2": "0"}])
 def test_kernel_generations_agree(sg, monkeypatch, env):
-    """The fallback kernels (sweep without the WTA role, lock-step vertical kernel, cost generations 1/2)
-    stay bit-exact: they serve the geometries the newest kernels do not hold."""
+    """The fallback kernels (sweep without the WTA role, lock-step vertical kernel, row-at-a-time kernel,
+    cost generations 1/2) stay bit-exact: they serve the geometries the newest kernels do not hold."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     W, H, D = 700, 80, 64
@@ -321,3 +322,13 @@ def test_repeatability_under_load(sg, monkeypatch, R):
         for it in range(150):
             d = st.compute(lt[it % 2], rt[it % 2])
             assert bool((d == ref[it % 2]).all()), (mode, it)
+
+
+def test_very_wide_image(sg):
+    """7680 columns at numDisparities = 256: the strips do not fit the persistent sweeps, the row-at-a-time
+    fallback takes over (cv2 has no width limit, neither has the drop-in)."""
+    W, H, D = 7680, 40, 256
+    l, r, _ = make_pair(W, H, D, seed=3)
+    for mode in (0, 1):
+        p = OracleParams(0, D, 5, 200, 800, 1, 63, 10, 100, 32, mode)
+        assert _mismatch(sg.StereoSGBM_create(**_kw(p)).compute(l, r), oracle.compute(p, l, r)) == 0, mode
