@@ -525,7 +525,9 @@ __device__ __forceinline__ void sweep_wta_slot(const SweepArgs &a, uint16_t *col
     {
         uint32_t S[NREG];
         load_vec<NREG, LPC>(S, col, lg);
-        if (!SAT) {
+        // The clamp to 32767 is monotone, so it commutes with the min reduction; a saturated minimum makes
+        // the pixel invalid whichever disparity carries it, so only the debug dump needs clamped vectors.
+        if (!SAT && a.sdbg) {
 #pragma unroll
             for (int j = 0; j < NREG; j++) S[j] = pmin(S[j], SGBM_MAX_S);
         }
@@ -542,7 +544,7 @@ __device__ __forceinline__ void sweep_wta_slot(const SweepArgs &a, uint16_t *col
     if (lg > lastLane) key = 0xFFFFFFFFu;
 #pragma unroll
     for (int off = LPC / 2; off >= 1; off >>= 1) key = min(key, __shfl_xor_sync(0xFFFFFFFFu, key, off, LPC));
-    const int minS = (int)(key >> 16);
+    const int minS = min((int)(key >> 16), 32767);
     const int best = (minS == 32767) ? -1 : (int)(key & 0xFFFFu);       // first minimum (A.5)
     int Sm = 0, Sp = 0;
     const bool interior = best > 0 && best < g.D - 1;
