@@ -176,7 +176,7 @@ def run_reference(args, W, H, D, mode, modename):
            "cpu_baseline": {"value": value, "unit": "MDE/s", "cores": threads, "kind": kind, "sample": sample},
            "e2e": {"value": value, "unit": "MDE/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    emit(out)
 
 
 def cpu_baseline_single(W, H, D, mode, modename):
@@ -377,7 +377,7 @@ def run_product(args, W, H, D, mode, modename):
                         "d2h_bytes_per_step": int(d2h_cloud[0] if with_reproject else 2 * W * H), "steps": e2e_steps, "matches_device_path": same},
                 "gpu_launches": launches, "clocks": clocks, "stages_ms": {k: round(v["ms"], 4) for k, v in stages.items()},
                 "roofline": roof, "alu_roofline": alu, "cpu_baseline": cpu}
-        print(json.dumps(outj))
+        emit(outj)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -388,7 +388,23 @@ def check(L, rc):
         raise RuntimeError(L.sgbm_last_error().decode())
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The one JSON line of the contract, on the process's real stdout."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    # Libraries chat on stdout (NCCL prints its version banner there): keep the real stdout for the JSON
+    # line and send everything else written to fd 1 to stderr.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
