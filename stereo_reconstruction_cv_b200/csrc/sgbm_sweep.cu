@@ -44,6 +44,7 @@ struct SweepArgs {
     uint16_t *haloA, *haloC;         // [nstrips][64 / R][R][Dp + 8]
     unsigned int *flagA, *flagC;     // [nstrips][64 / R][R] super-step (+1) each halo ring entry was last published for
     int dbgNoSync;
+    int dbgStall;                    // test hook (SGBM_DBG_STALL=1): role V withholds one hand-off so that the watchdog trips
     unsigned int urMagic;            // floor(2^32 / (100 - uniquenessRatio)) + 1
     unsigned int *dbg;               // [8] hand-off watchdog: {tripped, strip, warp, wait id, row, ...}, zeroed per launch
     unsigned long long *trace;       // debug: clock64 time stamps of one strip [row][role 4][8] (or null)
@@ -254,7 +255,7 @@ __device__ __forceinline__ void sweep_role_v(const SweepArgs &a, const SweepSmem
         if (own) store_vec<NREG, LPC>(S, s.P + pOff, lg);
         __syncwarp();
         if (lane == 0) {
-            mbar_arrive(&s.fullV[k]);
+            if (!(a.dbgStall && t == 5 && blockIdx.x == 0)) mbar_arrive(&s.fullV[k]);
             mbar_arrive(&s.emptyC[sc]);
             mbar_arrive(&s.emptyI[si]);
         }
@@ -717,6 +718,7 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
     a.g = g; a.C = va.C; a.inA = va.inA; a.inB = va.inB; a.sout = va.sout; a.sdbg = va.sdbg; a.raw = va.raw;
     a.d2key = va.d2key; a.backward = va.backward; a.haloA = va.haloA; a.haloC = va.haloC; a.flagA = va.flagA;
     a.flagC = va.flagC; a.dbgNoSync = va.dbgNoSync;
+    a.dbgStall = getenv("SGBM_DBG_STALL") ? 1 : 0;
     a.nAB = va.inB ? 2 : 1;
     a.urMagic = g.UR < 99 ? 0xFFFFFFFFu / (unsigned)(100 - g.UR) + 1u : 0u;
     const bool wta = va.sout == nullptr;

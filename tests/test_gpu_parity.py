@@ -332,3 +332,22 @@ def test_very_wide_image(sg):
     for mode in (0, 1):
         p = OracleParams(0, D, 5, 200, 800, 1, 63, 10, 100, 32, mode)
         assert _mismatch(sg.StereoSGBM_create(**_kw(p)).compute(l, r), oracle.compute(p, l, r)) == 0, mode
+
+
+def test_handoff_watchdog_reports_and_recovers(sg, monkeypatch):
+    """A sweep hand-off that never happens (test hook: role V of strip 0 withholds one arrival) must not
+    hang the GPU: the kernel drains after ~2 s, the call reports an error, the next call is fine."""
+    import time
+    W, H, D = 900, 64, 64
+    l, r, _ = make_pair(W, H, D, seed=21)
+    p = OracleParams(0, D, 5, 200, 800, 1, 63, 10, 0, 0, 0)
+    ref = oracle.compute(p, l, r)
+    st = sg.StereoSGBM_create(**_kw(p))
+    assert _mismatch(st.compute(l, r), ref) == 0
+    monkeypatch.setenv("SGBM_DBG_STALL", "1")
+    t0 = time.time()
+    with pytest.raises(sg.error, match="hand-off timed out"):
+        st.compute(l, r)
+    assert time.time() - t0 < 30
+    monkeypatch.delenv("SGBM_DBG_STALL")
+    assert _mismatch(st.compute(l, r), ref) == 0
