@@ -6,7 +6,7 @@
 // row into a shared-memory buffer (one warp per column) and summed them in a second phase (16.6
 // shared-memory wavefronts and 65 instructions per output word, two block barriers per row).  Here
 // one thread owns TWO adjacent disparity pairs (packed u16x2 words 2j and 2j+1 = disparities 4j..4j+3)
-// of XPT = 16 consecutive columns and walks along the row:
+// of XPT = 12 consecutive columns and walks along the row:
 //   * the pixel cost never leaves registers: the horizontal (2r+1) window sum slides in a register
 //     window (the walk is fully unrolled, so the rotating window has compile-time indices);
 //   * right-image operands are a stream: the pair word of an odd right position is assembled with one
@@ -30,7 +30,7 @@
 
 #define COST3_K 256u          // bias; multiple of 4 so that (bt_t + K) >> 2 == (bt_t >> 2) + K/4
 #ifndef COST3_XPT
-#define COST3_XPT 16
+#define COST3_XPT 12
 #endif
 //         // output columns per thread
 
@@ -186,7 +186,7 @@ __device__ __forceinline__ void cost3_walk(const uint4 *__restrict__ lrow, const
 }
 
 template <int R, int PAR, int DWT, int NTT>
-__global__ void __launch_bounds__(NTT ? NTT : 320) k_cost3(Cost3Args a)
+__global__ void __launch_bounds__(NTT ? NTT : 448) k_cost3(Cost3Args a)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int XPT = COST3_XPT, NS = 2 * R + 1, NCOL = XPT + 2 * R;
@@ -309,14 +309,14 @@ static bool cost3_plan(const Geo &g, int maxSmem, Cost3Args &a, int *threadsOut,
 {
     if (g.cn != 1 || g.r > 5 || (g.D & 3)) return false;
     const int Dw = g.Dp / 2, Dh = Dw / 2, R = g.r;
-    if (Dh > 320) return false;
+    if (Dh > 448) return false;
     memset(&a, 0, sizeof(a));
     a.g = g;
     a.RPW = sgbm_cost2_rpw(g);
     a.one = 1u; a.neg1 = 0xFFFFFFFFu;
     a.eshift = sgbm_cost3_eshift(g);
-    // thread groups along x: as many as fit (<= 320 threads, <= 16 groups, not more than the image needs)
-    int cap = 320 / Dh;
+    // thread groups along x: as many as fit (<= 448 threads, <= 16 groups, not more than the image needs)
+    int cap = 448 / Dh;
     if (cap > 16) cap = 16;
     if (cap < 1) cap = 1;
     const int need = (g.W1 + COST3_XPT - 1) / COST3_XPT;
@@ -423,8 +423,8 @@ int sgbm_launch_cost3(const Geo &g, const uint8_t *planes, uint16_t *out, int y0
         return par ? launch_cost3_t<RR, 1, DW_, NT_>(a, threads, smem, grid, maxSmem, st)                          \
                    : launch_cost3_t<RR, 0, DW_, NT_>(a, threads, smem, grid, maxSmem, st);
 #ifndef COST3_NO_HOT
-    COST3_HOT(1, 64, 320) COST3_HOT(1, 96, 288) COST3_HOT(1, 128, 320)
-    COST3_HOT(2, 64, 320) COST3_HOT(2, 96, 288) COST3_HOT(2, 128, 320)
+    COST3_HOT(1, 64, 448) COST3_HOT(1, 96, 448) COST3_HOT(1, 128, 448)
+    COST3_HOT(2, 64, 416) COST3_HOT(2, 96, 384) COST3_HOT(2, 128, 384)
 #endif
 #undef COST3_HOT
 #define COST3_CASE(RR)                                                                                  \
