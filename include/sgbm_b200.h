@@ -83,7 +83,12 @@ int sgbm_compute(sgbm_handle *h, const uint8_t *left, const uint8_t *right, int 
                  int channels, ptrdiff_t pitch_bytes, int batch, int16_t *disp_out,
                  ptrdiff_t out_pitch_bytes, void *cuda_stream);
 
-/* Same with HOST pointers: pinned staging, H2D, compute, D2H, stream synchronise. */
+/*
+ * Same with HOST pointers: H2D, compute, D2H, stream synchronise (what the numpy call site
+ * main.ipynb:668 needs).  Page-locked buffers with dense rows are DMA'd directly, pageable ones are
+ * staged through the handle's pinned slots; with batch > 1 three streams overlap the copies of
+ * neighbouring frames with the kernels.
+ */
 int sgbm_compute_host(sgbm_handle *h, const uint8_t *left, const uint8_t *right, int W, int H,
                       int channels, ptrdiff_t pitch_bytes, int batch, int16_t *disp_out,
                       ptrdiff_t out_pitch_bytes);
