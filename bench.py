@@ -225,13 +225,23 @@ def run_product(args, W, H, D, mode, modename):
     lts = [torch.from_numpy(f[0]).to(dev) for f in frames]
     rts = [torch.from_numpy(f[1]).to(dev) for f in frames]
     st = sg.StereoSGBM_create(numDisparities=D, mode=mode, **PARAMS)
-    out = torch.empty((H, W), dtype=torch.int16, device=dev)
     with_reproject = args.workload == "cfg5"
+    # Frames per step: the video-sized workloads (BASELINE cfg2 / cfg4, "batch of ... pairs") hand the engine
+    # two pairs per call, which lets it run them side by side on half of the SMs each (sgbm_compute batch
+    # schedule); the 4K workloads are one pair per step.
+    fps = args.frames_per_step if args.frames_per_step > 0 else (2 if (H <= 1080 and not with_reproject) else 1)
+    out = torch.empty((H, W) if fps == 1 else (fps, H, W), dtype=torch.int16, device=dev)
+    if fps > 1:
+        lb = [torch.stack([lts[(i + k) % pool] for k in range(fps)]) for i in range(pool)]
+        rb = [torch.stack([rts[(i + k) % pool] for k in range(fps)]) for i in range(pool)]
     counter = [0]
 
     def step_device():
         i = counter[0] % pool
         counter[0] += 1
+        if fps > 1:
+            st.compute(lb[i], rb[i], out)
+            return None
         st.compute(lts[i], rts[i], out)
         if with_reproject:
             return sg.reprojectCompact(out, NOTEBOOK_Q)
@@ -242,11 +252,28 @@ def run_product(args, W, H, D, mode, modename):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def read_stages():
+        names = C.create_string_buffer(32 * 16)
+        tot = (C.c_double * 16)()
+        runs = (C.c_int * 16)()
+        kers = (C.c_int * 16)()
+        n = C.c_int()
+        check(L, L.sgbm_profile_read(st._h, names, tot, runs, kers, 16, C.byref(n)))
+        check(L, L.sgbm_profile_enable(st._h, 0))
+        res = {}
+        for i in range(n.value):
+            nm = names.raw[32 * i:32 * i + 32].split(b"\0")[0].decode()
+            res[nm] = {"ms": tot[i] / max(runs[i], 1), "kernels": kers[i] // max(runs[i], 1)}
+        return res
+
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
     # ---- timed region: inputs resident in HBM, CUDA events on the launching stream ----------------
-    check(L, L.sgbm_profile_enable(st._h, 1))
+    # (per-stage events are recorded inside the timed region for one-frame steps; with two frames side by
+    # side the stages of the two lanes overlap, so they are timed frame by frame in a pass of their own)
+    if fps == 1:
+        check(L, L.sgbm_profile_enable(st._h, 1))
     launches0 = L.sgbm_kernel_launches()
     sampler = ClockSampler(local)
     sampler.start()
@@ -260,23 +287,20 @@ def run_product(args, W, H, D, mode, modename):
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     launches = int(L.sgbm_kernel_launches() - launches0)
-    # per-stage device times of the same timed region
-    names = C.create_string_buffer(32 * 16)
-    tot = (C.c_double * 16)()
-    runs = (C.c_int * 16)()
-    kers = (C.c_int * 16)()
-    n = C.c_int()
-    check(L, L.sgbm_profile_read(st._h, names, tot, runs, kers, 16, C.byref(n)))
-    check(L, L.sgbm_profile_enable(st._h, 0))
-    stages = {}
-    for i in range(n.value):
-        nm = names.raw[32 * i:32 * i + 32].split(b"\0")[0].decode()
-        stages[nm] = {"ms": tot[i] / max(runs[i], 1), "kernels": kers[i] // max(runs[i], 1)}
+    if fps == 1:
+        stages = read_stages()
+    else:
+        check(L, L.sgbm_profile_enable(st._h, 1))
+        single = torch.empty((H, W), dtype=torch.int16, device=dev)
+        for i in range(min(args.steps, pool)):
+            st.compute(lts[i], rts[i], single)
+        stages = read_stages()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    evals_step = float(W) * H * D
+    evals_frame = float(W) * H * D
+    evals_step = evals_frame * fps
     value = evals_step * args.steps * world / (ms_max * 1e-3) / 1e6
 
     # ---- end to end through the reference-facing call with HOST buffers ------------------------------
@@ -317,9 +341,10 @@ def run_product(args, W, H, D, mode, modename):
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = evals_step * e2e_steps * world / float(t.item()) / 1e6
-    st.compute(lts[0], rts[0], out)
-    same = bool((torch.from_numpy(res).to(dev) == out).all().item())
+    e2e_value = evals_frame * e2e_steps * world / float(t.item()) / 1e6
+    chk = torch.empty((H, W), dtype=torch.int16, device=dev)
+    st.compute(lts[0], rts[0], chk)
+    same = bool((torch.from_numpy(res).to(dev) == chk).all().item())
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
@@ -342,13 +367,13 @@ def run_product(args, W, H, D, mode, modename):
             ach = bpe * elems / (dom_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
-                    "kernel_ms": dom_ms, "share_of_step": dom_ms / (ms / args.steps),
+                    "kernel_ms": dom_ms, "share_of_step": dom_ms * fps / (ms / args.steps),
                     "algorithmic_bytes_per_launch": bpe * elems}
             # whole pipeline: sum of the stages' algorithmic bytes over the step time
             pipe_bpe = {0: 16, 1: 22, 2: 16, 3: 22}[mode]
             roof["pipeline"] = {"algorithmic_bytes_per_step": pipe_bpe * elems,
-                                "achieved": pipe_bpe * elems / (ms / args.steps * 1e-3) / 1e9,
-                                "frac": pipe_bpe * elems / (ms / args.steps * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+                                "achieved": pipe_bpe * elems * fps / (ms / args.steps * 1e-3) / 1e9,
+                                "frac": pipe_bpe * elems * fps / (ms / args.steps * 1e-3) / 1e9 / peaks["hbm_gbs"]}
             try:
                 mix = sg.microbench_int16(6)               # G lane-ops/s of the path-step instruction mix
                 ops_per_elem = {"horizontal": 2 * 3.3, "vertical_fwd": 3 * 3.3, "vertical_wta": 3 * 3.3 + 1.5,
@@ -364,11 +389,13 @@ def run_product(args, W, H, D, mode, modename):
         outj = {"metric": "MDE/s", "value": value, "unit": "MDE/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-                "config": {"workload": "%s (BASELINE.json configs[%d]): synthetic %dx%d rectified pair per GPU per step, "
+                "config": {"workload": "%s (BASELINE.json configs[%d]): %s synthetic %dx%d rectified pair%s per GPU per step, "
                                        "D=%d, blockSize=5, %s, speckle filter + LR check on%s"
-                                       % (args.workload, WORKLOADS[args.workload][5], W, H, D, modename,
+                                       % (args.workload, WORKLOADS[args.workload][5], "one" if fps == 1 else str(fps), W, H,
+                                          "" if fps == 1 else "s (one batched call)", D, modename,
                                           ", + fused reprojectImageTo3D/compaction" if with_reproject else ""),
-                           "frames_per_s": args.steps * world / (ms_max * 1e-3),
+                           "frames_per_step": fps,
+                           "frames_per_s": args.steps * fps * world / (ms_max * 1e-3),
                            "l2": "no flush: each step streams the %.1f GB cost/path volumes (>> 126 MB L2)"
                                  % (3 * elems * 2 / 1e9),
                            "frame_pool": "%d distinct synthetic pairs per GPU (seeds rank*%d..), resident in HBM, round-robin" % (pool, pool),
@@ -412,6 +439,7 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--pool", type=int, default=4, help="distinct synthetic pairs per GPU visited round-robin")
+    ap.add_argument("--frames-per-step", type=int, default=0, help="pairs per compute() call (0: 2 for <= 1080p, else 1)")
     args = ap.parse_args()
     W, H, D, mode, modename, _ = WORKLOADS[args.workload]
     if args.impl == "reference":

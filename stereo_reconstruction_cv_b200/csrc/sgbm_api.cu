@@ -23,6 +23,7 @@ size_t sgbm_cost2_planes_bytes(const Geo &g);
 int sgbm_launch_cost3(const Geo &g, const uint8_t *planes, uint16_t *out, int y0, int nrows, int ylo, cudaStream_t st);
 int sgbm_launch_horizontal(const Geo &g, const uint16_t *C, uint16_t *LhA, uint16_t *LhB, int y0, int nrows, cudaStream_t st);
 int sgbm_launch_vertical(VertArgs &a, int ndir, int numSMs, cudaStream_t st);
+bool sgbm_sweep_fits(const Geo &g, int numSMs, int mode);
 int sgbm_launch_fill_i16(int16_t *p, size_t n, int v, cudaStream_t st);
 int sgbm_launch_lrcheck(const Geo &g, int16_t *raw, const unsigned int *d2key, cudaStream_t st);
 int sgbm_launch_median(const int16_t *src, int16_t *dst, int W, int H, long long dstPitchElems, cudaStream_t st);
@@ -67,17 +68,20 @@ struct ProfMark { int stage; cudaEvent_t ev; unsigned long long launches; };
 struct sgbm_handle {
     sgbm_params p{};
     int numSMs = 0;
-    // device workspace (grown on demand)
-    void *ws = nullptr;
-    size_t wsBytes = 0;
+    // device workspace (grown on demand); lane 1 exists only while batches run two frames side by side
+    void *ws[2] = {nullptr, nullptr};
+    size_t wsBytes[2] = {0, 0};
+    int lanesWanted = 2;             // SGBM_LANES=1 switches the two-lane batch schedule off
+    cudaStream_t laneStream = nullptr;
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
     // pinned + device staging for the _host entry point: two slots so that the host copies and the
     // PCIe transfers of frame b+1 / b-1 overlap the kernels of frame b
-    void *hostIn[2] = {nullptr, nullptr}, *hostOut[2] = {nullptr, nullptr}, *devIn[2] = {nullptr, nullptr}, *devOut[2] = {nullptr, nullptr};
-    size_t hostInBytes[2] = {0, 0}, hostOutBytes[2] = {0, 0}, devInBytes[2] = {0, 0}, devOutBytes[2] = {0, 0};
+    void *hostIn[4] = {}, *hostOut[4] = {}, *devIn[4] = {}, *devOut[4] = {};
+    size_t hostInBytes[4] = {}, hostOutBytes[4] = {}, devInBytes[4] = {}, devOutBytes[4] = {};
     cudaStream_t ownStream = nullptr, inStream = nullptr, outStream = nullptr;
-    cudaEvent_t evIn[2] = {nullptr, nullptr}, evComp[2] = {nullptr, nullptr}, evOut[2] = {nullptr, nullptr};
-    unsigned int *watch = nullptr;   // pinned copy of the sweep watchdog words
-    unsigned int *watchDev = nullptr;
+    cudaEvent_t evIn[4] = {}, evComp[4] = {}, evOut[4] = {};
+    unsigned int *watch = nullptr;   // pinned copy of the sweep watchdog words, [2 lanes][8]
+    unsigned int *watchDev[2] = {nullptr, nullptr};
     // debug
     int keep = 0;
     Geo lastGeo{};
@@ -230,6 +234,8 @@ extern "C" int sgbm_create(const sgbm_params *p, sgbm_handle **out)
     int dev = 0;
     SGBM_CUDA_CHECK(cudaGetDevice(&dev));
     SGBM_CUDA_CHECK(cudaDeviceGetAttribute(&h->numSMs, cudaDevAttrMultiProcessorCount, dev));
+    if (const char *e = getenv("SGBM_SM_LIMIT")) { const int v = atoi(e); if (v >= 1 && v < h->numSMs) h->numSMs = v; }
+    if (const char *e = getenv("SGBM_LANES")) h->lanesWanted = atoi(e) >= 2 ? 2 : 1;
     *out = h;
     return 0;
 }
@@ -237,9 +243,13 @@ extern "C" int sgbm_create(const sgbm_params *p, sgbm_handle **out)
 extern "C" int sgbm_destroy(sgbm_handle *h)
 {
     if (!h) return 0;
-    if (h->ws) cudaFree(h->ws);
+    for (int i = 0; i < 2; i++)
+        if (h->ws[i]) cudaFree(h->ws[i]);
     if (h->watch) cudaFreeHost(h->watch);
-    for (int i = 0; i < 2; i++) {
+    if (h->laneStream) cudaStreamDestroy(h->laneStream);
+    if (h->evFork) cudaEventDestroy(h->evFork);
+    if (h->evJoin) cudaEventDestroy(h->evJoin);
+    for (int i = 0; i < 4; i++) {
         if (h->devIn[i]) cudaFree(h->devIn[i]);
         if (h->devOut[i]) cudaFree(h->devOut[i]);
         if (h->hostIn[i]) cudaFreeHost(h->hostIn[i]);
@@ -283,42 +293,66 @@ extern "C" int sgbm_workspace_bytes(const sgbm_handle *h, int W, int H, int chan
     return 0;
 }
 
-static int ensure_ws(sgbm_handle *h, size_t bytes, cudaStream_t st)
+static int ensure_ws(sgbm_handle *h, int lane, size_t bytes, cudaStream_t st)
 {
-    if (h->wsBytes >= bytes) return 0;
-    if (h->ws) {
+    if (h->wsBytes[lane] >= bytes) return 0;
+    if (h->ws[lane]) {
         SGBM_CUDA_CHECK(cudaStreamSynchronize(st));
-        SGBM_CUDA_CHECK(cudaFree(h->ws));
-        h->ws = nullptr; h->wsBytes = 0;
+        SGBM_CUDA_CHECK(cudaFree(h->ws[lane]));
+        h->ws[lane] = nullptr; h->wsBytes[lane] = 0;
     }
-    cudaError_t e = cudaMalloc(&h->ws, bytes);
+    cudaError_t e = cudaMalloc(&h->ws[lane], bytes);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return sgbm_fail(SGBM_E_NOMEM, "cudaMalloc of %zu workspace bytes failed: %s", bytes, cudaGetErrorString(e));
     }
-    h->wsBytes = bytes;
+    h->wsBytes[lane] = bytes;
     // zero it once: the padding words of the volumes are never written, and the sweep watchdog is sticky
-    SGBM_CUDA_CHECK(cudaMemsetAsync(h->ws, 0, bytes, st));
+    SGBM_CUDA_CHECK(cudaMemsetAsync(h->ws[lane], 0, bytes, st));
     return 0;
 }
 
 // Reports (once) a sweep hand-off that timed out in a frame that has completed; see sgbm_sweep.cu.
 static int check_watch(sgbm_handle *h, cudaStream_t st)
 {
-    if (!h->watch || h->watch[0] == 0u) return 0;
-    const unsigned strip = h->watch[1], warp = h->watch[2], id = h->watch[3], row = h->watch[4];
-    h->watch[0] = 0u;
-    if (h->watchDev) cudaMemsetAsync(h->watchDev, 0, 32, st);
-    return sgbm_fail(SGBM_E_CUDA, "sweep hand-off timed out (strip %u, warp %u, wait %u, row %u): the frame's disparity is invalid",
-                     strip, warp, id, row);
+    if (!h->watch) return 0;
+    for (int lane = 0; lane < 2; lane++) {
+        unsigned int *w = h->watch + 8 * lane;
+        if (w[0] == 0u) continue;
+        const unsigned strip = w[1], warp = w[2], id = w[3], row = w[4];
+        w[0] = 0u;
+        if (h->watchDev[lane]) cudaMemsetAsync(h->watchDev[lane], 0, 32, st);
+        return sgbm_fail(SGBM_E_CUDA, "sweep hand-off timed out (strip %u, warp %u, wait %u, row %u): the frame's disparity is invalid",
+                         strip, warp, id, row);
+    }
+    return 0;
+}
+
+// Two frames side by side, each on half of the SMs: the sweeps are bound by per-row hand-off latency, not
+// by throughput, when their strips are narrow (1080p and below), so two half-width launches finish two
+// frames in little more than the time of one.  Only where the half-GPU sweep holds the geometry.
+static int lanes_for(const sgbm_handle *h, const Geo &g, int batch)
+{
+    if (batch < 2 || h->lanesWanted < 2 || h->prof || h->keep || h->numSMs < 2) return 1;
+    if (h->p.mode != SGBM_MODE_SGBM && h->p.mode != SGBM_MODE_HH) return 1;
+    return sgbm_sweep_fits(g, h->numSMs / 2, h->p.mode) ? 2 : 1;
+}
+
+static int ensure_lane_stream(sgbm_handle *h)
+{
+    if (h->laneStream) return 0;
+    SGBM_CUDA_CHECK(cudaStreamCreateWithFlags(&h->laneStream, cudaStreamNonBlocking));
+    SGBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
+    SGBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming));
+    return 0;
 }
 
 // One frame: the kernel schedule for each mode.
-static int compute_frame(sgbm_handle *h, const Geo &g, const WsLayout &L, const uint8_t *left, const uint8_t *right,
-                         long long pitch, int16_t *out, long long outPitchElems, cudaStream_t st)
+static int compute_frame(sgbm_handle *h, int lane, int sweepSMs, const Geo &g, const WsLayout &L, const uint8_t *left,
+                         const uint8_t *right, long long pitch, int16_t *out, long long outPitchElems, cudaStream_t st)
 {
     const sgbm_params &p = h->p;
-    uint8_t *base = (uint8_t *)h->ws;
+    uint8_t *base = (uint8_t *)h->ws[lane];
     uint8_t *planes = base + L.planes;
     uint16_t *C = (uint16_t *)(base + L.C), *LhA = (uint16_t *)(base + L.LhA), *LhB = (uint16_t *)(base + L.LhB);
     uint16_t *Calt = (uint16_t *)(base + L.Calt);
@@ -326,10 +360,10 @@ static int compute_frame(sgbm_handle *h, const Geo &g, const WsLayout &L, const 
     unsigned int *d2key = (unsigned int *)(base + L.d2key);
     int rc;
     if (!h->watch) {
-        SGBM_CUDA_CHECK(cudaMallocHost((void **)&h->watch, 32));
-        memset(h->watch, 0, 32);
+        SGBM_CUDA_CHECK(cudaMallocHost((void **)&h->watch, 64));
+        memset(h->watch, 0, 64);
     }
-    h->watchDev = (unsigned int *)(base + L.watch);
+    h->watchDev[lane] = (unsigned int *)(base + L.watch);
     if ((rc = check_watch(h, st))) return rc;               // a previous frame's sweep gave up
     if ((rc = prof_mark(h, ST_START, st))) return rc;
     // second-generation prefilter + cost kernels (sgbm_cost2.cu); the first generation stays as the
@@ -394,21 +428,21 @@ static int compute_frame(sgbm_handle *h, const Geo &g, const WsLayout &L, const 
     a.haloA = (uint16_t *)(base + L.haloA); a.haloC = (uint16_t *)(base + L.haloC);
     a.flagA = (unsigned int *)(base + L.flags); a.flagC = a.flagA + (g.W1 < h->numSMs ? g.W1 : h->numSMs);
     a.ss = ss; a.ov = ov;
-    a.watchDev = h->watchDev; a.watchHost = h->watch;
+    a.watchDev = h->watchDev[lane]; a.watchHost = h->watch + 8 * lane;
     a.rowState = (uint16_t *)(base + L.rowState);
     a.dbgNoSync = getenv("SGBM_DBG_NOSYNC") ? 1 : 0;
     a.sdbg = h->keep ? (uint16_t *)(base + L.sdbg) : nullptr;
     switch (p.mode) {
     case SGBM_MODE_SGBM:
         a.inA = LhA; a.inB = LhB; a.sout = nullptr; a.backward = 0;
-        if ((rc = sgbm_launch_vertical(a, 3, h->numSMs, st))) return rc;
+        if ((rc = sgbm_launch_vertical(a, 3, sweepSMs, st))) return rc;
         break;
     case SGBM_MODE_HH:
         a.inA = LhA; a.inB = LhB; a.sout = LhA; a.backward = 0;      // S_fwd overwrites LhA in place
-        if ((rc = sgbm_launch_vertical(a, 3, h->numSMs, st))) return rc;
+        if ((rc = sgbm_launch_vertical(a, 3, sweepSMs, st))) return rc;
         if ((rc = prof_mark(h, ST_VERT_FWD, st))) return rc;
         a.inA = LhA; a.inB = nullptr; a.sout = nullptr; a.backward = 1;
-        if ((rc = sgbm_launch_vertical(a, 3, h->numSMs, st))) return rc;
+        if ((rc = sgbm_launch_vertical(a, 3, sweepSMs, st))) return rc;
         break;
     case SGBM_MODE_SGBM_3WAY:
         a.inA = LhA; a.inB = LhB; a.sout = nullptr; a.threeway = 1;
@@ -456,13 +490,29 @@ extern "C" int sgbm_compute(sgbm_handle *h, const uint8_t *left, const uint8_t *
     cudaStream_t st = (cudaStream_t)cuda_stream;
     WsLayout L;
     ws_layout(g, h->p, h->numSMs, h->keep, L);
-    if ((rc = ensure_ws(h, L.total, st))) return rc;
-    for (int b = 0; b < batch; b++) {
-        rc = compute_frame(h, g, L, left + (size_t)b * pitch_bytes * H, right + (size_t)b * pitch_bytes * H, pitch_bytes,
-                           (int16_t *)((uint8_t *)disp_out + (size_t)b * out_pitch_bytes * H), out_pitch_bytes / 2, st);
-        if (rc) return rc;
+    const int lanes = lanes_for(h, g, batch);
+    if ((rc = ensure_ws(h, 0, L.total, st))) return rc;
+    if (lanes == 2) {
+        // odd frames run on an internal stream forked from the caller's stream and joined before returning:
+        // to the caller everything is still ordered on `cuda_stream`
+        if ((rc = ensure_lane_stream(h))) return rc;
+        if ((rc = ensure_ws(h, 1, L.total, st))) return rc;
+        SGBM_CUDA_CHECK(cudaEventRecord(h->evFork, st));
+        SGBM_CUDA_CHECK(cudaStreamWaitEvent(h->laneStream, h->evFork, 0));
     }
-    return 0;
+    const int sweepSMs = lanes == 2 ? h->numSMs / 2 : h->numSMs;
+    for (int b = 0; b < batch; b++) {
+        const int lane = lanes == 2 ? (b & 1) : 0;
+        rc = compute_frame(h, lane, sweepSMs, g, L, left + (size_t)b * pitch_bytes * H, right + (size_t)b * pitch_bytes * H,
+                           pitch_bytes, (int16_t *)((uint8_t *)disp_out + (size_t)b * out_pitch_bytes * H), out_pitch_bytes / 2,
+                           lane ? h->laneStream : st);
+        if (rc) break;
+    }
+    if (lanes == 2) {
+        SGBM_CUDA_CHECK(cudaEventRecord(h->evJoin, h->laneStream));
+        SGBM_CUDA_CHECK(cudaStreamWaitEvent(st, h->evJoin, 0));
+    }
+    return rc;
 }
 
 static int ensure_buf(void **p, size_t *have, size_t need, bool pinned)
@@ -489,7 +539,7 @@ extern "C" int sgbm_compute_host(sgbm_handle *h, const uint8_t *left, const uint
         SGBM_CUDA_CHECK(cudaStreamCreateWithFlags(&h->ownStream, cudaStreamNonBlocking));
         SGBM_CUDA_CHECK(cudaStreamCreateWithFlags(&h->inStream, cudaStreamNonBlocking));
         SGBM_CUDA_CHECK(cudaStreamCreateWithFlags(&h->outStream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < 4; i++) {
             SGBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->evIn[i], cudaEventDisableTiming));
             SGBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->evComp[i], cudaEventDisableTiming));
             SGBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->evOut[i], cudaEventDisableTiming));
@@ -497,7 +547,11 @@ extern "C" int sgbm_compute_host(sgbm_handle *h, const uint8_t *left, const uint
     }
     cudaStream_t st = h->ownStream;
     const size_t rowIn = (size_t)W * channels, frameIn = rowIn * H, frameOut = (size_t)W * H * 2;
-    const int nslots = batch > 1 ? 2 : 1;
+    WsLayout L;
+    ws_layout(g, h->p, h->numSMs, h->keep, L);
+    const int lanes = lanes_for(h, g, batch);
+    // staging slots: two per lane, so that every lane always has its next frame queued behind the running one
+    const int nslots = batch > 1 ? (2 * lanes < batch ? 2 * lanes : batch) : 1;
     // Page-locked caller buffers (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) with dense rows
     // are DMA'd directly; pageable ones are staged through the handle's pinned slots by the host thread.
     auto pinned = [](const void *p) {
@@ -513,13 +567,18 @@ extern "C" int sgbm_compute_host(sgbm_handle *h, const uint8_t *left, const uint
         if ((rc = ensure_buf(&h->devIn[i], &h->devInBytes[i], 2 * frameIn, false))) return rc;
         if ((rc = ensure_buf(&h->devOut[i], &h->devOutBytes[i], frameOut, false))) return rc;
     }
-    WsLayout L;
-    ws_layout(g, h->p, h->numSMs, h->keep, L);
-    if ((rc = ensure_ws(h, L.total, st))) return rc;
-    // Three streams: H2D, kernels, D2H; while the kernels of frame b run, frame b+1 goes in and frame b-1
-    // comes out (and, for pageable buffers, the host copies them into / out of the other staging slot).
+    if ((rc = ensure_ws(h, 0, L.total, st))) return rc;
+    if (lanes == 2) {                                     // odd frames compute on their own stream and workspace
+        if ((rc = ensure_lane_stream(h))) return rc;
+        if ((rc = ensure_ws(h, 1, L.total, st))) return rc;
+        SGBM_CUDA_CHECK(cudaStreamSynchronize(st));       // (its first-use memset was enqueued on st)
+    }
+    const int sweepSMs = lanes == 2 ? h->numSMs / 2 : h->numSMs;
+    // Three kinds of streams: H2D, kernels (one per lane), D2H; while the kernels of frame b run, later
+    // frames go in and earlier ones come out (and, for pageable buffers, the host copies them into / out
+    // of the other staging slots).
     auto drain = [&](int b) -> int {                      // wait for frame b's D2H and hand the rows to the caller
-        const int sl = b & 1;
+        const int sl = b % nslots;
         SGBM_CUDA_CHECK(cudaEventSynchronize(h->evOut[sl]));
         if (directOut) return 0;
         uint8_t *o = (uint8_t *)disp_out + (size_t)b * out_pitch_bytes * H;
@@ -529,8 +588,8 @@ extern "C" int sgbm_compute_host(sgbm_handle *h, const uint8_t *left, const uint
         return 0;
     };
     for (int b = 0; b < batch; b++) {
-        const int sl = nslots == 2 ? (b & 1) : 0;
-        if (b >= 2 && (rc = drain(b - 2))) return rc;     // frees slot sl (its kernels and D2H are complete)
+        const int sl = b % nslots;
+        if (b >= nslots && (rc = drain(b - nslots))) return rc;     // frees slot sl (its kernels and D2H are complete)
         const uint8_t *l = left + (size_t)b * pitch_bytes * H, *r = right + (size_t)b * pitch_bytes * H;
         if (directIn) {
             SGBM_CUDA_CHECK(cudaMemcpyAsync(h->devIn[sl], l, frameIn, cudaMemcpyHostToDevice, h->inStream));
@@ -548,22 +607,25 @@ extern "C" int sgbm_compute_host(sgbm_handle *h, const uint8_t *left, const uint
             }
             SGBM_CUDA_CHECK(cudaMemcpyAsync(h->devIn[sl], h->hostIn[sl], 2 * frameIn, cudaMemcpyHostToDevice, h->inStream));
         }
+        const int lane = lanes == 2 ? (b & 1) : 0;
+        cudaStream_t cs = lane ? h->laneStream : st;
         SGBM_CUDA_CHECK(cudaEventRecord(h->evIn[sl], h->inStream));
-        SGBM_CUDA_CHECK(cudaStreamWaitEvent(st, h->evIn[sl], 0));
-        rc = compute_frame(h, g, L, (const uint8_t *)h->devIn[sl], (const uint8_t *)h->devIn[sl] + frameIn, (long long)rowIn,
-                           (int16_t *)h->devOut[sl], W, st);
+        SGBM_CUDA_CHECK(cudaStreamWaitEvent(cs, h->evIn[sl], 0));
+        rc = compute_frame(h, lane, sweepSMs, g, L, (const uint8_t *)h->devIn[sl],
+                           (const uint8_t *)h->devIn[sl] + frameIn, (long long)rowIn, (int16_t *)h->devOut[sl], W, cs);
         if (rc) return rc;
-        SGBM_CUDA_CHECK(cudaEventRecord(h->evComp[sl], st));
+        SGBM_CUDA_CHECK(cudaEventRecord(h->evComp[sl], cs));
         SGBM_CUDA_CHECK(cudaStreamWaitEvent(h->outStream, h->evComp[sl], 0));
         void *dst = directOut ? (void *)((uint8_t *)disp_out + (size_t)b * frameOut) : h->hostOut[sl];
         SGBM_CUDA_CHECK(cudaMemcpyAsync(dst, h->devOut[sl], frameOut, cudaMemcpyDeviceToHost, h->outStream));
         SGBM_CUDA_CHECK(cudaEventRecord(h->evOut[sl], h->outStream));
-        // the next H2D into this slot's device input must not overtake these kernels
-        SGBM_CUDA_CHECK(cudaStreamWaitEvent(h->inStream, h->evComp[sl], 0));
+        // (the next H2D into this slot is enqueued only after drain() has seen this frame's D2H complete, so
+        // it cannot overtake these kernels; the H2D stream itself never waits for kernels)
     }
-    for (int b = batch >= 2 ? batch - 2 : 0; b < batch; b++)
+    for (int b = batch > nslots ? batch - nslots : 0; b < batch; b++)
         if ((rc = drain(b))) return rc;
     SGBM_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (lanes == 2) SGBM_CUDA_CHECK(cudaStreamSynchronize(h->laneStream));
     return check_watch(h, st);
 }
 

@@ -696,6 +696,80 @@ static size_t sweep_layout(SweepArgs &a, int groupsC, bool scratch)
     return off;
 }
 
+// Strip / warp / ring geometry of one launch (a.nAB must be set).  False when the geometry does not fit.
+static bool sweep_plan(const Geo &g, int numSMs, bool wrole, bool wta, int maxThreads, int maxSmem, SweepArgs &a, int *threadsOut,
+                       size_t *smemOut)
+{
+    const int GPW = 32 / g.lpc;
+    // Rows per super-step (every value is covered by tests/test_gpu_parity.py::test_sweep_rows_per_superstep
+    // and a repeatability run; 8 is the fastest at every size measured).
+    const int Rmin = 1;
+    int R = 8;
+    if (const char *e = getenv("SGBM_VR")) R = atoi(e) >= Rmin ? atoi(e) : Rmin;
+    if (R > 16) R = 16;
+    int Kwant = 5, NSCwant = 5, NSIwant = 3;
+    if (const char *e = getenv("SGBM_SWEEP_K")) Kwant = atoi(e) >= 1 && atoi(e) <= 8 ? atoi(e) : Kwant;
+    if (const char *e = getenv("SGBM_SWEEP_NSC")) NSCwant = atoi(e) >= 2 && atoi(e) <= 8 ? atoi(e) : NSCwant;
+    if (const char *e = getenv("SGBM_SWEEP_NSI")) NSIwant = atoi(e) >= 2 && atoi(e) <= 8 ? atoi(e) : NSIwant;
+    for (; R >= Rmin; R--) {
+        int nstrips = numSMs;
+        const int minCols = R > 2 ? R : 2;                // every strip owns >= R (and >= 2) columns
+        if (nstrips > g.W1 / minCols) nstrips = g.W1 / minCols;
+        if (nstrips < 1) nstrips = 1;
+        if (nstrips == 1 && R > 1) continue;              // a single strip has no halos
+        const int SWmax = (g.W1 + nstrips - 1) / nstrips;
+        const int NB = (SWmax + R - 1 + R - 1) / R;       // ceil((SW + HG) / R)
+        const int groupsA = NB * R;
+        a.nwA = (groupsA + GPW - 1) / GPW;
+        a.nwV = (SWmax + GPW - 1) / GPW;
+        int threads;
+        if (wrole) {
+            a.aA = (a.nwA + 3) & ~3; a.aV = (a.nwV + 3) & ~3;
+            a.nwW = a.nwV < 7 ? a.nwV : 7;                // 8 warps: WTA warps, the producer, idle
+            if (const char *e = getenv("SGBM_SWEEP_NWW")) { const int v = atoi(e); if (v >= 1 && v <= 7) a.nwW = v; }
+            a.wPass = (SWmax + a.nwW * GPW - 1) / (a.nwW * GPW);
+            threads = (a.aV + 2 * a.aA + 8) * 32;
+        } else {
+            threads = (a.nwV + 2 * a.nwA + 1) * 32;
+        }
+        if (threads > maxThreads) continue;
+        a.SW = SWmax; a.nstrips = nstrips; a.R = R; a.NB = NB;
+        // ring depths: shrink until the layout fits
+        static const int tries[][3] = {{0, 0, 0}, {0, 0, -1}, {0, -1, -1}, {-1, -1, -1}, {-1, -2, -1}, {-2, -2, -1}, {-2, -3, -1}};
+        for (const auto &tr : tries) {
+            a.K = Kwant + tr[0]; a.NSC = NSCwant + tr[1]; a.NSI = NSIwant + tr[2];
+            if (a.K < 1) a.K = 1;
+            if (a.NSC < 2) a.NSC = 2;
+            if (a.NSI < 2) a.NSI = 2;
+            const size_t smem = sweep_layout(a, a.nwA * GPW, wta && !wrole);
+            if (smem <= (size_t)maxSmem) { *threadsOut = threads; *smemOut = smem; return true; }
+        }
+    }
+    return false;
+}
+
+// Whether the persistent sweeps of mode SGBM (0) / HH (1) hold this geometry on `numSMs` SMs: what the
+// batch entry points ask before they run two frames side by side, each on half of the GPU.
+bool sgbm_sweep_fits(const Geo &g, int numSMs, int mode)
+{
+    int dev = 0, maxSmem = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    if (cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return false;
+    SweepArgs a;
+    int threads = 0;
+    size_t smem = 0;
+    memset(&a, 0, sizeof(a));
+    a.g = g;
+    a.nAB = mode == 1 ? 1 : 2;                            // last sweep: S_fwd (HH) or L_hA + L_hB (SGBM)
+    if (!sweep_plan(g, numSMs, true, true, 1024, maxSmem, a, &threads, &smem) || a.nstrips > numSMs) return false;
+    if (mode == 1) {                                      // forward sweep of MODE_HH
+        memset(&a, 0, sizeof(a));
+        a.g = g; a.nAB = 2;
+        if (!sweep_plan(g, numSMs, false, false, g.nreg >= 12 ? 768 : 1024, maxSmem, a, &threads, &smem)) return false;
+    }
+    return true;
+}
+
 // Returns 0 on success, 1 if this geometry does not fit the role-specialised sweep (the caller falls
 // back to k_vertical), negative on error.  WROLE: winner-take-all sweep with the dedicated WTA role.
 template <int NREG, int LPC, bool SAT, bool WROLE>
@@ -724,52 +798,9 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
     const bool wta = va.sout == nullptr;
     if (WROLE && !wta) return 1;
     const int maxThreads = SweepMaxThreads<NREG, WROLE>::value;
-    // Rows per super-step (every value is covered by tests/test_gpu_parity.py::test_sweep_rows_per_superstep
-    // and a repeatability run; 8 is the fastest at every size measured).
-    const int Rmin = 1;
-    int R = 8;
-    if (const char *e = getenv("SGBM_VR")) R = atoi(e) >= Rmin ? atoi(e) : Rmin;
-    if (R > 16) R = 16;
-    int Kwant = 5, NSCwant = 5, NSIwant = 3;
-    if (const char *e = getenv("SGBM_SWEEP_K")) Kwant = atoi(e) >= 1 && atoi(e) <= 8 ? atoi(e) : Kwant;
-    if (const char *e = getenv("SGBM_SWEEP_NSC")) NSCwant = atoi(e) >= 2 && atoi(e) <= 8 ? atoi(e) : NSCwant;
-    if (const char *e = getenv("SGBM_SWEEP_NSI")) NSIwant = atoi(e) >= 2 && atoi(e) <= 8 ? atoi(e) : NSIwant;
     int threads = 0;
     size_t smem = 0;
-    bool found = false;
-    for (; R >= Rmin && !found; R--) {
-        int nstrips = numSMs;
-        const int minCols = R > 2 ? R : 2;                // every strip owns >= R (and >= 2) columns
-        if (nstrips > g.W1 / minCols) nstrips = g.W1 / minCols;
-        if (nstrips < 1) nstrips = 1;
-        if (nstrips == 1 && R > 1) continue;              // a single strip has no halos
-        const int SWmax = (g.W1 + nstrips - 1) / nstrips;
-        const int NB = (SWmax + R - 1 + R - 1) / R;       // ceil((SW + HG) / R)
-        const int groupsA = NB * R;
-        a.nwA = (groupsA + GPW - 1) / GPW;
-        a.nwV = (SWmax + GPW - 1) / GPW;
-        if (WROLE) {
-            a.aA = (a.nwA + 3) & ~3; a.aV = (a.nwV + 3) & ~3;
-            a.nwW = a.nwV < 7 ? a.nwV : 7;                // 8 warps: WTA warps, the producer, idle
-            if (const char *e = getenv("SGBM_SWEEP_NWW")) { const int v = atoi(e); if (v >= 1 && v <= 7) a.nwW = v; }
-            a.wPass = (SWmax + a.nwW * GPW - 1) / (a.nwW * GPW);
-            threads = (a.aV + 2 * a.aA + 8) * 32;
-        } else {
-            threads = (a.nwV + 2 * a.nwA + 1) * 32;
-        }
-        if (threads > maxThreads) continue;
-        a.SW = SWmax; a.nstrips = nstrips; a.R = R; a.NB = NB;
-        // ring depths: shrink until the layout fits
-        static const int tries[][3] = {{0, 0, 0}, {0, 0, -1}, {0, -1, -1}, {-1, -1, -1}, {-1, -2, -1}, {-2, -2, -1}, {-2, -3, -1}};
-        for (const auto &tr : tries) {
-            a.K = Kwant + tr[0]; a.NSC = NSCwant + tr[1]; a.NSI = NSIwant + tr[2];
-            if (a.K < 1) a.K = 1;
-            if (a.NSC < 2) a.NSC = 2;
-            if (a.NSI < 2) a.NSI = 2;
-            smem = sweep_layout(a, a.nwA * GPW, wta && !WROLE);
-            if (smem <= (size_t)maxSmem) { found = true; break; }
-        }
-    }
+    const bool found = sweep_plan(g, numSMs, WROLE, wta, maxThreads, maxSmem, a, &threads, &smem);
     if (!found) return 1;
     int occ = 0;
     SGBM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
