@@ -227,9 +227,9 @@ def run_product(args, W, H, D, mode, modename):
     st = sg.StereoSGBM_create(numDisparities=D, mode=mode, **PARAMS)
     with_reproject = args.workload == "cfg5"
     # Frames per step: the video-sized workloads (BASELINE cfg2 / cfg4, "batch of ... pairs") hand the engine
-    # two pairs per call, which lets it run them side by side on half of the SMs each (sgbm_compute batch
-    # schedule); the 4K workloads are one pair per step.
-    fps = args.frames_per_step if args.frames_per_step > 0 else (2 if (H <= 1080 and not with_reproject) else 1)
+    # six pairs per call, which lets it run two or three of them side by side, each on its share of the
+    # SMs (sgbm_compute batch schedule); the 4K workloads are one pair per step.
+    fps = args.frames_per_step if args.frames_per_step > 0 else (6 if (H <= 1080 and not with_reproject) else 1)
     out = torch.empty((H, W) if fps == 1 else (fps, H, W), dtype=torch.int16, device=dev)
     if fps > 1:
         lb = [torch.stack([lts[(i + k) % pool] for k in range(fps)]) for i in range(pool)]
@@ -367,7 +367,10 @@ def run_product(args, W, H, D, mode, modename):
             ach = bpe * elems / (dom_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
-                    "kernel_ms": dom_ms, "share_of_step": dom_ms * fps / (ms / args.steps),
+                    "kernel_ms": dom_ms,
+                    # share of the step for one-frame steps; with frames side by side the kernels of the lanes
+                    # overlap, so the share is taken of one frame's summed kernel time
+                    "share_of_step": dom_ms / (ms / args.steps) if fps == 1 else dom_ms / sum(v["ms"] for v in stages.values()),
                     "algorithmic_bytes_per_launch": bpe * elems}
             # whole pipeline: sum of the stages' algorithmic bytes over the step time
             pipe_bpe = {0: 16, 1: 22, 2: 16, 3: 22}[mode]
@@ -439,7 +442,7 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--pool", type=int, default=4, help="distinct synthetic pairs per GPU visited round-robin")
-    ap.add_argument("--frames-per-step", type=int, default=0, help="pairs per compute() call (0: 2 for <= 1080p, else 1)")
+    ap.add_argument("--frames-per-step", type=int, default=0, help="pairs per compute() call (0: 6 for <= 1080p, else 1)")
     args = ap.parse_args()
     W, H, D, mode, modename, _ = WORKLOADS[args.workload]
     if args.impl == "reference":

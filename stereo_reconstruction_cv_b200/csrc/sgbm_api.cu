@@ -64,24 +64,26 @@ enum { ST_START = 0, ST_PREFILTER, ST_COST, ST_COST_ALT, ST_HORIZONTAL, ST_INIT,
 static const char *const kStageNames[ST_COUNT] = {"start", "prefilter", "cost", "cost_alt", "horizontal", "init",
                                                   "vertical_fwd", "vertical_wta", "lrcheck", "median", "speckle"};
 struct ProfMark { int stage; cudaEvent_t ev; unsigned long long launches; };
+#define SGBM_MAX_LANES 3             // frames a batch call runs side by side (each on numSMs / lanes SMs)
+#define SGBM_MAX_SLOTS (2 * SGBM_MAX_LANES)
 
 struct sgbm_handle {
     sgbm_params p{};
     int numSMs = 0;
     // device workspace (grown on demand); lane 1 exists only while batches run two frames side by side
-    void *ws[2] = {nullptr, nullptr};
-    size_t wsBytes[2] = {0, 0};
-    int lanesWanted = 2;             // SGBM_LANES=1 switches the two-lane batch schedule off
-    cudaStream_t laneStream = nullptr;
-    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    void *ws[SGBM_MAX_LANES] = {};
+    size_t wsBytes[SGBM_MAX_LANES] = {};
+    int lanesWanted = SGBM_MAX_LANES;   // SGBM_LANES=1 switches the side-by-side batch schedule off
+    cudaStream_t laneStream[SGBM_MAX_LANES] = {};   // [0] unused: lane 0 runs on the caller's / the handle's stream
+    cudaEvent_t evFork = nullptr, evJoin[SGBM_MAX_LANES] = {};
     // pinned + device staging for the _host entry point: two slots so that the host copies and the
     // PCIe transfers of frame b+1 / b-1 overlap the kernels of frame b
-    void *hostIn[4] = {}, *hostOut[4] = {}, *devIn[4] = {}, *devOut[4] = {};
-    size_t hostInBytes[4] = {}, hostOutBytes[4] = {}, devInBytes[4] = {}, devOutBytes[4] = {};
+    void *hostIn[SGBM_MAX_SLOTS] = {}, *hostOut[SGBM_MAX_SLOTS] = {}, *devIn[SGBM_MAX_SLOTS] = {}, *devOut[SGBM_MAX_SLOTS] = {};
+    size_t hostInBytes[SGBM_MAX_SLOTS] = {}, hostOutBytes[SGBM_MAX_SLOTS] = {}, devInBytes[SGBM_MAX_SLOTS] = {}, devOutBytes[SGBM_MAX_SLOTS] = {};
     cudaStream_t ownStream = nullptr, inStream = nullptr, outStream = nullptr;
-    cudaEvent_t evIn[4] = {}, evComp[4] = {}, evOut[4] = {};
-    unsigned int *watch = nullptr;   // pinned copy of the sweep watchdog words, [2 lanes][8]
-    unsigned int *watchDev[2] = {nullptr, nullptr};
+    cudaEvent_t evIn[SGBM_MAX_SLOTS] = {}, evComp[SGBM_MAX_SLOTS] = {}, evOut[SGBM_MAX_SLOTS] = {};
+    unsigned int *watch = nullptr;   // pinned copy of the sweep watchdog words, [lanes][8]
+    unsigned int *watchDev[SGBM_MAX_LANES] = {};
     // debug
     int keep = 0;
     Geo lastGeo{};
@@ -235,7 +237,7 @@ extern "C" int sgbm_create(const sgbm_params *p, sgbm_handle **out)
     SGBM_CUDA_CHECK(cudaGetDevice(&dev));
     SGBM_CUDA_CHECK(cudaDeviceGetAttribute(&h->numSMs, cudaDevAttrMultiProcessorCount, dev));
     if (const char *e = getenv("SGBM_SM_LIMIT")) { const int v = atoi(e); if (v >= 1 && v < h->numSMs) h->numSMs = v; }
-    if (const char *e = getenv("SGBM_LANES")) h->lanesWanted = atoi(e) >= 2 ? 2 : 1;
+    if (const char *e = getenv("SGBM_LANES")) { const int v = atoi(e); h->lanesWanted = v < 1 ? 1 : (v > SGBM_MAX_LANES ? SGBM_MAX_LANES : v); }
     *out = h;
     return 0;
 }
@@ -243,13 +245,14 @@ extern "C" int sgbm_create(const sgbm_params *p, sgbm_handle **out)
 extern "C" int sgbm_destroy(sgbm_handle *h)
 {
     if (!h) return 0;
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < SGBM_MAX_LANES; i++) {
         if (h->ws[i]) cudaFree(h->ws[i]);
+        if (h->laneStream[i]) cudaStreamDestroy(h->laneStream[i]);
+        if (h->evJoin[i]) cudaEventDestroy(h->evJoin[i]);
+    }
     if (h->watch) cudaFreeHost(h->watch);
-    if (h->laneStream) cudaStreamDestroy(h->laneStream);
     if (h->evFork) cudaEventDestroy(h->evFork);
-    if (h->evJoin) cudaEventDestroy(h->evJoin);
-    for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < SGBM_MAX_SLOTS; i++) {
         if (h->devIn[i]) cudaFree(h->devIn[i]);
         if (h->devOut[i]) cudaFree(h->devOut[i]);
         if (h->hostIn[i]) cudaFreeHost(h->hostIn[i]);
@@ -316,7 +319,7 @@ static int ensure_ws(sgbm_handle *h, int lane, size_t bytes, cudaStream_t st)
 static int check_watch(sgbm_handle *h, cudaStream_t st)
 {
     if (!h->watch) return 0;
-    for (int lane = 0; lane < 2; lane++) {
+    for (int lane = 0; lane < SGBM_MAX_LANES; lane++) {
         unsigned int *w = h->watch + 8 * lane;
         if (w[0] == 0u) continue;
         const unsigned strip = w[1], warp = w[2], id = w[3], row = w[4];
@@ -328,22 +331,28 @@ static int check_watch(sgbm_handle *h, cudaStream_t st)
     return 0;
 }
 
-// Two frames side by side, each on half of the SMs: the sweeps are bound by per-row hand-off latency, not
-// by throughput, when their strips are narrow (1080p and below), so two half-width launches finish two
-// frames in little more than the time of one.  Only where the half-GPU sweep holds the geometry.
+// Frames side by side, each on numSMs / lanes SMs: the sweeps are bound by per-row hand-off latency, not by
+// throughput, when their strips are narrow (1440p and below), so two or three narrower launches finish
+// their frames in little more than the time of one (720p D=128: 84 -> 133 -> 179 GDE/s with 1 / 2 / 3
+// lanes; four lanes are slower again).  As many lanes as the persistent sweep still holds the geometry for.
 static int lanes_for(const sgbm_handle *h, const Geo &g, int batch)
 {
-    if (batch < 2 || h->lanesWanted < 2 || h->prof || h->keep || h->numSMs < 2) return 1;
+    if (batch < 2 || h->lanesWanted < 2 || h->prof || h->keep) return 1;
     if (h->p.mode != SGBM_MODE_SGBM && h->p.mode != SGBM_MODE_HH) return 1;
-    return sgbm_sweep_fits(g, h->numSMs / 2, h->p.mode) ? 2 : 1;
+    int lanes = h->lanesWanted < batch ? h->lanesWanted : batch;
+    for (; lanes >= 2; lanes--)
+        if (h->numSMs / lanes >= 1 && sgbm_sweep_fits(g, h->numSMs / lanes, h->p.mode)) return lanes;
+    return 1;
 }
 
-static int ensure_lane_stream(sgbm_handle *h)
+static int ensure_lane_streams(sgbm_handle *h, int lanes)
 {
-    if (h->laneStream) return 0;
-    SGBM_CUDA_CHECK(cudaStreamCreateWithFlags(&h->laneStream, cudaStreamNonBlocking));
-    SGBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
-    SGBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming));
+    if (!h->evFork) SGBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
+    for (int i = 1; i < lanes; i++) {
+        if (h->laneStream[i]) continue;
+        SGBM_CUDA_CHECK(cudaStreamCreateWithFlags(&h->laneStream[i], cudaStreamNonBlocking));
+        SGBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->evJoin[i], cudaEventDisableTiming));
+    }
     return 0;
 }
 
@@ -360,8 +369,8 @@ static int compute_frame(sgbm_handle *h, int lane, int sweepSMs, const Geo &g, c
     unsigned int *d2key = (unsigned int *)(base + L.d2key);
     int rc;
     if (!h->watch) {
-        SGBM_CUDA_CHECK(cudaMallocHost((void **)&h->watch, 64));
-        memset(h->watch, 0, 64);
+        SGBM_CUDA_CHECK(cudaMallocHost((void **)&h->watch, 32 * SGBM_MAX_LANES));
+        memset(h->watch, 0, 32 * SGBM_MAX_LANES);
     }
     h->watchDev[lane] = (unsigned int *)(base + L.watch);
     if ((rc = check_watch(h, st))) return rc;               // a previous frame's sweep gave up
@@ -492,25 +501,26 @@ extern "C" int sgbm_compute(sgbm_handle *h, const uint8_t *left, const uint8_t *
     ws_layout(g, h->p, h->numSMs, h->keep, L);
     const int lanes = lanes_for(h, g, batch);
     if ((rc = ensure_ws(h, 0, L.total, st))) return rc;
-    if (lanes == 2) {
-        // odd frames run on an internal stream forked from the caller's stream and joined before returning:
-        // to the caller everything is still ordered on `cuda_stream`
-        if ((rc = ensure_lane_stream(h))) return rc;
-        if ((rc = ensure_ws(h, 1, L.total, st))) return rc;
+    if (lanes > 1) {
+        // frames b % lanes != 0 run on internal streams forked from the caller's stream and joined before
+        // returning: to the caller everything is still ordered on `cuda_stream`
+        if ((rc = ensure_lane_streams(h, lanes))) return rc;
+        for (int i = 1; i < lanes; i++)
+            if ((rc = ensure_ws(h, i, L.total, st))) return rc;
         SGBM_CUDA_CHECK(cudaEventRecord(h->evFork, st));
-        SGBM_CUDA_CHECK(cudaStreamWaitEvent(h->laneStream, h->evFork, 0));
+        for (int i = 1; i < lanes; i++) SGBM_CUDA_CHECK(cudaStreamWaitEvent(h->laneStream[i], h->evFork, 0));
     }
-    const int sweepSMs = lanes == 2 ? h->numSMs / 2 : h->numSMs;
+    const int sweepSMs = h->numSMs / lanes;
     for (int b = 0; b < batch; b++) {
-        const int lane = lanes == 2 ? (b & 1) : 0;
+        const int lane = b % lanes;
         rc = compute_frame(h, lane, sweepSMs, g, L, left + (size_t)b * pitch_bytes * H, right + (size_t)b * pitch_bytes * H,
                            pitch_bytes, (int16_t *)((uint8_t *)disp_out + (size_t)b * out_pitch_bytes * H), out_pitch_bytes / 2,
-                           lane ? h->laneStream : st);
+                           lane ? h->laneStream[lane] : st);
         if (rc) break;
     }
-    if (lanes == 2) {
-        SGBM_CUDA_CHECK(cudaEventRecord(h->evJoin, h->laneStream));
-        SGBM_CUDA_CHECK(cudaStreamWaitEvent(st, h->evJoin, 0));
+    for (int i = 1; i < lanes; i++) {
+        SGBM_CUDA_CHECK(cudaEventRecord(h->evJoin[i], h->laneStream[i]));
+        SGBM_CUDA_CHECK(cudaStreamWaitEvent(st, h->evJoin[i], 0));
     }
     return rc;
 }
@@ -539,7 +549,7 @@ extern "C" int sgbm_compute_host(sgbm_handle *h, const uint8_t *left, const uint
         SGBM_CUDA_CHECK(cudaStreamCreateWithFlags(&h->ownStream, cudaStreamNonBlocking));
         SGBM_CUDA_CHECK(cudaStreamCreateWithFlags(&h->inStream, cudaStreamNonBlocking));
         SGBM_CUDA_CHECK(cudaStreamCreateWithFlags(&h->outStream, cudaStreamNonBlocking));
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < SGBM_MAX_SLOTS; i++) {
             SGBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->evIn[i], cudaEventDisableTiming));
             SGBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->evComp[i], cudaEventDisableTiming));
             SGBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->evOut[i], cudaEventDisableTiming));
@@ -568,12 +578,13 @@ extern "C" int sgbm_compute_host(sgbm_handle *h, const uint8_t *left, const uint
         if ((rc = ensure_buf(&h->devOut[i], &h->devOutBytes[i], frameOut, false))) return rc;
     }
     if ((rc = ensure_ws(h, 0, L.total, st))) return rc;
-    if (lanes == 2) {                                     // odd frames compute on their own stream and workspace
-        if ((rc = ensure_lane_stream(h))) return rc;
-        if ((rc = ensure_ws(h, 1, L.total, st))) return rc;
-        SGBM_CUDA_CHECK(cudaStreamSynchronize(st));       // (its first-use memset was enqueued on st)
+    if (lanes > 1) {                                      // the other lanes compute on their own streams and workspaces
+        if ((rc = ensure_lane_streams(h, lanes))) return rc;
+        for (int i = 1; i < lanes; i++)
+            if ((rc = ensure_ws(h, i, L.total, st))) return rc;
+        SGBM_CUDA_CHECK(cudaStreamSynchronize(st));       // (their first-use memsets were enqueued on st)
     }
-    const int sweepSMs = lanes == 2 ? h->numSMs / 2 : h->numSMs;
+    const int sweepSMs = h->numSMs / lanes;
     // Three kinds of streams: H2D, kernels (one per lane), D2H; while the kernels of frame b run, later
     // frames go in and earlier ones come out (and, for pageable buffers, the host copies them into / out
     // of the other staging slots).
@@ -607,8 +618,8 @@ extern "C" int sgbm_compute_host(sgbm_handle *h, const uint8_t *left, const uint
             }
             SGBM_CUDA_CHECK(cudaMemcpyAsync(h->devIn[sl], h->hostIn[sl], 2 * frameIn, cudaMemcpyHostToDevice, h->inStream));
         }
-        const int lane = lanes == 2 ? (b & 1) : 0;
-        cudaStream_t cs = lane ? h->laneStream : st;
+        const int lane = b % lanes;
+        cudaStream_t cs = lane ? h->laneStream[lane] : st;
         SGBM_CUDA_CHECK(cudaEventRecord(h->evIn[sl], h->inStream));
         SGBM_CUDA_CHECK(cudaStreamWaitEvent(cs, h->evIn[sl], 0));
         rc = compute_frame(h, lane, sweepSMs, g, L, (const uint8_t *)h->devIn[sl],
@@ -625,7 +636,7 @@ extern "C" int sgbm_compute_host(sgbm_handle *h, const uint8_t *left, const uint
     for (int b = batch > nslots ? batch - nslots : 0; b < batch; b++)
         if ((rc = drain(b))) return rc;
     SGBM_CUDA_CHECK(cudaStreamSynchronize(st));
-    if (lanes == 2) SGBM_CUDA_CHECK(cudaStreamSynchronize(h->laneStream));
+    for (int i = 1; i < lanes; i++) SGBM_CUDA_CHECK(cudaStreamSynchronize(h->laneStream[i]));
     return check_watch(h, st);
 }
 

@@ -354,17 +354,17 @@ def test_handoff_watchdog_reports_and_recovers(sg, monkeypatch):
 
 
 @pytest.mark.parametrize("mode", [0, 1])
-def test_batch_two_lane_schedule(sg, monkeypatch, mode):
-    """Batched calls run two frames side by side on half of the SMs each (when the half-GPU sweeps hold the
-    geometry): every frame must equal the oracle, for device tensors and host arrays, odd batch sizes,
-    repeated calls, and with the schedule switched off (SGBM_LANES=1)."""
+def test_batch_side_by_side_schedule(sg, monkeypatch, mode):
+    """Batched calls run two or three frames side by side, each on its share of the SMs (when the narrower
+    sweeps hold the geometry): every frame must equal the oracle, for device tensors and host arrays, odd
+    batch sizes, repeated calls, and with the schedule restricted (SGBM_LANES=2) or off (SGBM_LANES=1)."""
     import torch
     W, H, D, B = 1100, 72, 64, 5
     pairs = [make_pair(W, H, D, seed=40 + i)[:2] for i in range(B)]
     p = OracleParams(0, D, 5, 200, 800, 1, 63, 10, 100, 32, mode)
     ref = np.stack([oracle.compute(p, l, r) for l, r in pairs])
     ls = np.stack([l for l, _ in pairs]); rs = np.stack([r for _, r in pairs])
-    for lanes in ("2", "1"):
+    for lanes in ("3", "2", "1"):
         monkeypatch.setenv("SGBM_LANES", lanes)
         st = sg.StereoSGBM_create(**_kw(p))
         for rep in range(4):
