@@ -331,18 +331,26 @@ static int check_watch(sgbm_handle *h, cudaStream_t st)
     return 0;
 }
 
-// Frames side by side, each on numSMs / lanes SMs: the sweeps are bound by per-row hand-off latency, not by
+// Frames side by side.  Small frames, each on numSMs / lanes SMs: the sweeps are bound by per-row hand-off latency, not by
 // throughput, when their strips are narrow (1440p and below), so two or three narrower launches finish
 // their frames in little more than the time of one (720p D=128: 84 -> 133 -> 179 GDE/s with 1 / 2 / 3
 // lanes; four lanes are slower again).  As many lanes as the persistent sweep still holds the geometry for.
-static int lanes_for(const sgbm_handle *h, const Geo &g, int batch)
+static int lanes_for(const sgbm_handle *h, const Geo &g, int batch, int *sweepSMs)
 {
+    *sweepSMs = h->numSMs;
     if (batch < 2 || h->lanesWanted < 2 || h->prof || h->keep) return 1;
-    if (h->p.mode != SGBM_MODE_SGBM && h->p.mode != SGBM_MODE_HH) return 1;
-    int lanes = h->lanesWanted < batch ? h->lanesWanted : batch;
-    for (; lanes >= 2; lanes--)
-        if (h->numSMs / lanes >= 1 && sgbm_sweep_fits(g, h->numSMs / lanes, h->p.mode)) return lanes;
-    return 1;
+    if (h->p.mode == SGBM_MODE_SGBM || h->p.mode == SGBM_MODE_HH) {
+        int lanes = h->lanesWanted < batch ? h->lanesWanted : batch;
+        for (; lanes >= 2; lanes--)
+            if (h->numSMs / lanes >= 1 && sgbm_sweep_fits(g, h->numSMs / lanes, h->p.mode)) {
+                *sweepSMs = h->numSMs / lanes;
+                return lanes;
+            }
+    }
+    // Large frames (or the modes without persistent sweeps): two frames in flight on two streams, every
+    // kernel on the whole GPU.  The sweeps of the two frames take turns, the other kernels and all the
+    // launch tails overlap (4K D=256: MODE_HH 180 -> 188 GDE/s, MODE_SGBM_3WAY 285 -> 317 GDE/s).
+    return 2;
 }
 
 static int ensure_lane_streams(sgbm_handle *h, int lanes)
@@ -499,7 +507,8 @@ extern "C" int sgbm_compute(sgbm_handle *h, const uint8_t *left, const uint8_t *
     cudaStream_t st = (cudaStream_t)cuda_stream;
     WsLayout L;
     ws_layout(g, h->p, h->numSMs, h->keep, L);
-    const int lanes = lanes_for(h, g, batch);
+    int sweepSMs = h->numSMs;
+    const int lanes = lanes_for(h, g, batch, &sweepSMs);
     if ((rc = ensure_ws(h, 0, L.total, st))) return rc;
     if (lanes > 1) {
         // frames b % lanes != 0 run on internal streams forked from the caller's stream and joined before
@@ -510,7 +519,6 @@ extern "C" int sgbm_compute(sgbm_handle *h, const uint8_t *left, const uint8_t *
         SGBM_CUDA_CHECK(cudaEventRecord(h->evFork, st));
         for (int i = 1; i < lanes; i++) SGBM_CUDA_CHECK(cudaStreamWaitEvent(h->laneStream[i], h->evFork, 0));
     }
-    const int sweepSMs = h->numSMs / lanes;
     for (int b = 0; b < batch; b++) {
         const int lane = b % lanes;
         rc = compute_frame(h, lane, sweepSMs, g, L, left + (size_t)b * pitch_bytes * H, right + (size_t)b * pitch_bytes * H,
@@ -559,7 +567,8 @@ extern "C" int sgbm_compute_host(sgbm_handle *h, const uint8_t *left, const uint
     const size_t rowIn = (size_t)W * channels, frameIn = rowIn * H, frameOut = (size_t)W * H * 2;
     WsLayout L;
     ws_layout(g, h->p, h->numSMs, h->keep, L);
-    const int lanes = lanes_for(h, g, batch);
+    int sweepSMs = h->numSMs;
+    const int lanes = lanes_for(h, g, batch, &sweepSMs);
     // staging slots: two per lane, so that every lane always has its next frame queued behind the running one
     const int nslots = batch > 1 ? (2 * lanes < batch ? 2 * lanes : batch) : 1;
     // Page-locked caller buffers (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) with dense rows
@@ -584,7 +593,6 @@ extern "C" int sgbm_compute_host(sgbm_handle *h, const uint8_t *left, const uint
             if ((rc = ensure_ws(h, i, L.total, st))) return rc;
         SGBM_CUDA_CHECK(cudaStreamSynchronize(st));       // (their first-use memsets were enqueued on st)
     }
-    const int sweepSMs = h->numSMs / lanes;
     // Three kinds of streams: H2D, kernels (one per lane), D2H; while the kernels of frame b run, later
     // frames go in and earlier ones come out (and, for pageable buffers, the host copies them into / out
     // of the other staging slots).
