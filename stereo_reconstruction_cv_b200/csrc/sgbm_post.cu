@@ -66,12 +66,24 @@ __device__ __forceinline__ int uf_find(const int *L, int i)
     while (p != i) { i = p; p = ((volatile const int *)L)[i]; }
     return i;
 }
+// Find with path halving.  Parents only ever decrease (union by smaller index), so shortening a link with
+// atomicMin can never undo a concurrent union; the result is the same root, later finds are shorter.
+__device__ __forceinline__ int uf_find_halve(int *L, int i)
+{
+    int p = ((volatile int *)L)[i];
+    while (p != i) {
+        const int gp = ((volatile int *)L)[p];
+        if (gp != p) atomicMin(&L[i], gp);
+        i = p; p = gp;
+    }
+    return i;
+}
 __device__ __forceinline__ void uf_union(int *L, int a, int b)
 {
     bool done;
     do {
-        a = uf_find(L, a);
-        b = uf_find(L, b);
+        a = uf_find_halve(L, a);
+        b = uf_find_halve(L, b);
         if (a < b) { int old = atomicMin(&L[b], a); done = (old == b); b = old; }
         else if (b < a) { int old = atomicMin(&L[a], b); done = (old == a); a = old; }
         else done = true;
@@ -157,6 +169,7 @@ __global__ void k_cc_count(const int16_t *img, int *label, int *size, int W, int
     const int s = runStart ? i : label[i];               // non-start pixels keep pointing at their run start
     const int r = uf_find(label, s);
     atomicAdd(&size[r], i - s + 1);
+    if (r != s) atomicMin(&label[s], r);                  // flatten: k_cc_apply reaches the root in two loads
 }
 
 __global__ void k_cc_apply(int16_t *img, const int *label, const int *size, int n, int newVal, int maxSize)
