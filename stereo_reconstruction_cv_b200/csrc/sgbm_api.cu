@@ -508,14 +508,14 @@ extern "C" int sgbm_compute(sgbm_handle *h, const uint8_t *left, const uint8_t *
     WsLayout L;
     ws_layout(g, h->p, h->numSMs, h->keep, L);
     int sweepSMs = h->numSMs;
-    const int lanes = lanes_for(h, g, batch, &sweepSMs);
+    int lanes = lanes_for(h, g, batch, &sweepSMs);
     if ((rc = ensure_ws(h, 0, L.total, st))) return rc;
+    for (int i = 1; i < lanes; i++)
+        if (ensure_ws(h, i, L.total, st)) { lanes = 1; sweepSMs = h->numSMs; break; }   // no memory for a second workspace
     if (lanes > 1) {
         // frames b % lanes != 0 run on internal streams forked from the caller's stream and joined before
         // returning: to the caller everything is still ordered on `cuda_stream`
         if ((rc = ensure_lane_streams(h, lanes))) return rc;
-        for (int i = 1; i < lanes; i++)
-            if ((rc = ensure_ws(h, i, L.total, st))) return rc;
         SGBM_CUDA_CHECK(cudaEventRecord(h->evFork, st));
         for (int i = 1; i < lanes; i++) SGBM_CUDA_CHECK(cudaStreamWaitEvent(h->laneStream[i], h->evFork, 0));
     }
@@ -568,7 +568,10 @@ extern "C" int sgbm_compute_host(sgbm_handle *h, const uint8_t *left, const uint
     WsLayout L;
     ws_layout(g, h->p, h->numSMs, h->keep, L);
     int sweepSMs = h->numSMs;
-    const int lanes = lanes_for(h, g, batch, &sweepSMs);
+    int lanes = lanes_for(h, g, batch, &sweepSMs);
+    if ((rc = ensure_ws(h, 0, L.total, st))) return rc;
+    for (int i = 1; i < lanes; i++)
+        if (ensure_ws(h, i, L.total, st)) { lanes = 1; sweepSMs = h->numSMs; break; }   // no memory for a second workspace
     // staging slots: two per lane, so that every lane always has its next frame queued behind the running one
     const int nslots = batch > 1 ? (2 * lanes < batch ? 2 * lanes : batch) : 1;
     // Page-locked caller buffers (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) with dense rows
@@ -586,11 +589,8 @@ extern "C" int sgbm_compute_host(sgbm_handle *h, const uint8_t *left, const uint
         if ((rc = ensure_buf(&h->devIn[i], &h->devInBytes[i], 2 * frameIn, false))) return rc;
         if ((rc = ensure_buf(&h->devOut[i], &h->devOutBytes[i], frameOut, false))) return rc;
     }
-    if ((rc = ensure_ws(h, 0, L.total, st))) return rc;
     if (lanes > 1) {                                      // the other lanes compute on their own streams and workspaces
         if ((rc = ensure_lane_streams(h, lanes))) return rc;
-        for (int i = 1; i < lanes; i++)
-            if ((rc = ensure_ws(h, i, L.total, st))) return rc;
         SGBM_CUDA_CHECK(cudaStreamSynchronize(st));       // (their first-use memsets were enqueued on st)
     }
     // Three kinds of streams: H2D, kernels (one per lane), D2H; while the kernels of frame b run, later
