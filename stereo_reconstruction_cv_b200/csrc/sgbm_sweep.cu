@@ -17,9 +17,14 @@
 // are mbarrier full/empty pairs, so the roles drift apart by up to K rows and no warp ever waits at
 // a block-wide barrier.
 //
+// In the last sweep of MODE_SGBM / MODE_HH a fourth role W (WROLE kernels) takes the winner-take-all off
+// role C: C writes the finished S back into the slot, W reads it, and setmaxnreg moves registers from
+// the W / producer warpgroups to the path warpgroups.  k_rowstep at the end of this file is the
+// row-at-a-time fallback for geometries no persistent kernel holds.
+//
 // Strips exchange diagonal state every R rows (a "super-step"): at its end, role A publishes the
-// state of the strip's last R columns, role C that of its first R columns (global memory, one
-// release flag per column).  At the next super-step R chains per role restart from the
+// state of the strip's last R columns, role C that of its first R columns (global memory, a ring of
+// 64 / R super-step slots with one release flag per ring entry).  At the next super-step R chains per role restart from the
 // neighbour's published columns, R-1 of them in halo columns outside the strip (the redundant
 // triangle that pays for syncing every R rows instead of every row).  Group (b, i) -- batch b,
 // index i -- restarts at super-steps n == b (mod NB) at halo position i, so at every row each
