@@ -132,8 +132,10 @@ __device__ __forceinline__ void load_vec_cg(uint32_t (&v)[NREG], const uint16_t 
 // Register budget: ~5*NREG live packed registers + 3*NREG prefetch => cap the CTA size per NREG.
 template <int NREG> struct VertMaxThreads { static const int value = NREG >= 16 ? 384 : (NREG >= 12 ? 512 : (NREG >= 8 ? 640 : 1024)); };
 
+// NDIR = 1 (independent columns, 128 threads per CTA) is a pure streaming kernel: four CTAs per SM keep
+// more loads in flight than three at 152 registers
 template <int NREG, int LPC, int NDIR>
-__global__ void __launch_bounds__(VertMaxThreads<NREG>::value, 1) k_vertical(VertArgs a)
+__global__ void __launch_bounds__(NDIR == 1 ? 128 : VertMaxThreads<NREG>::value, NDIR == 1 ? 4 : 1) k_vertical(VertArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const Geo &g = a.g;
