@@ -467,7 +467,9 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
             }
             __syncwarp();
             if (pub && lg == 0) {
-                __threadfence();
+                // st.release.gpu is itself a release fence: cumulative over the group's stores, which the
+                // __syncwarp above has ordered before this lane (a separate __threadfence() doubled the
+                // MEMBAR / CCTL.IVALL cost of every publication)
                 st_release_u32(flagOut + (n % HS) * R + pi, (unsigned)(n + 1));
             }
         }
