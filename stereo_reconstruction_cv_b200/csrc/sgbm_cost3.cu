@@ -425,6 +425,7 @@ int sgbm_launch_cost3(const Geo &g, const uint8_t *planes, uint16_t *out, int y0
 #ifndef COST3_NO_HOT
     COST3_HOT(1, 64, 448) COST3_HOT(1, 96, 448) COST3_HOT(1, 128, 448)
     COST3_HOT(2, 64, 416) COST3_HOT(2, 96, 384) COST3_HOT(2, 128, 384)
+    COST3_HOT(3, 64, 288) COST3_HOT(3, 96, 288) COST3_HOT(3, 128, 256)
 #endif
 #undef COST3_HOT
 #define COST3_CASE(RR)                                                                                  \
