@@ -33,6 +33,7 @@ if ROOT not in sys.path:
 
 WORKLOADS = {
     # name: (W, H, D, mode, modename, BASELINE.json config index)
+    "cfg1": (3840, 2160, 16, 0, "MODE_SGBM", 0),      # the notebook's literal call (main.ipynb:655-666, 781) at the dataset's size
     "cfg2": (1280, 720, 128, 0, "MODE_SGBM", 1),
     "cfg3": (3840, 2160, 256, 1, "MODE_HH", 2),
     "cfg4": (1920, 1080, 192, 0, "MODE_SGBM", 3),
@@ -40,6 +41,8 @@ WORKLOADS = {
 }
 PARAMS = dict(minDisparity=0, blockSize=5, P1=200, P2=800, disp12MaxDiff=1, preFilterCap=63, uniquenessRatio=10,
               speckleWindowSize=100, speckleRange=32)
+# per-workload overrides: cfg1 uses the notebook's parameters (blockSize 11, 3-channel P1 / P2 recipe)
+WORKLOAD_PARAMS = {"cfg1": dict(blockSize=11, P1=8 * 3 * 11 ** 2, P2=32 * 3 * 11 ** 2)}
 NOTEBOOK_Q = np.array([[1, 0, 0, -1909.9754], [0, 1, 0, -1057.74529], [0, 0, 0, 2045.48384], [0, 0, -1, 0]],
                       np.float64)                                          # main.ipynb:598-607
 
@@ -113,9 +116,13 @@ def make_inputs(W, H, D, seed):
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's own implementation (cv2.StereoSGBM on host cores)
 # ------------------------------------------------------------------------------------------------
-def _ref_compute_fn(D, mode):
+def params_for(workload):
+    return dict(PARAMS, **WORKLOAD_PARAMS.get(workload, {}))
+
+
+def _ref_compute_fn(D, mode, workload="cfg3"):
     from oracle import cv2_ref
-    kw = dict(PARAMS, numDisparities=D, mode=mode)
+    kw = dict(params_for(workload), numDisparities=D, mode=mode)
     if cv2_ref.available():
         import cv2
         cv2.setNumThreads(1)
@@ -139,7 +146,7 @@ def run_reference(args, W, H, D, mode, modename):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    fn, kind, what = _ref_compute_fn(D, mode)
+    fn, kind, what = _ref_compute_fn(D, mode, args.workload)
     rows = cpu_sample_rows(H, D, mode)
     ncpu = os.cpu_count() or 1
     try:
@@ -179,8 +186,8 @@ def run_reference(args, W, H, D, mode, modename):
     emit(out)
 
 
-def cpu_baseline_single(W, H, D, mode, modename):
-    fn, kind, what = _ref_compute_fn(D, mode)
+def cpu_baseline_single(W, H, D, mode, modename, workload="cfg3"):
+    fn, kind, what = _ref_compute_fn(D, mode, workload)
     rows = cpu_sample_rows(H, D, mode)
     l, r = make_inputs(W, H, D, 0)
     y0 = (H - rows) // 2
@@ -224,7 +231,7 @@ def run_product(args, W, H, D, mode, modename):
     l, r = frames[0]
     lts = [torch.from_numpy(f[0]).to(dev) for f in frames]
     rts = [torch.from_numpy(f[1]).to(dev) for f in frames]
-    st = sg.StereoSGBM_create(numDisparities=D, mode=mode, **PARAMS)
+    st = sg.StereoSGBM_create(numDisparities=D, mode=mode, **params_for(args.workload))
     with_reproject = args.workload == "cfg5"
     # Frames per step: the video-sized workloads (BASELINE cfg2 / cfg4, "batch of ... pairs") hand the engine
     # six pairs per call, which lets it run two or three of them side by side, each on its share of the
@@ -388,14 +395,14 @@ def run_product(args, W, H, D, mode, modename):
                        "microbenchmarked)", "frac": a_ach / mix, "ops_per_elem": ops_per_elem}
             except Exception as ex:                          # pragma: no cover
                 alu = {"error": str(ex)}
-        cpu = cpu_baseline_single(W, H, D, mode, modename) if world == 1 or rank == 0 else None
+        cpu = cpu_baseline_single(W, H, D, mode, modename, args.workload) if world == 1 or rank == 0 else None
         outj = {"metric": "MDE/s", "value": value, "unit": "MDE/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
                 "config": {"workload": "%s (BASELINE.json configs[%d]): %s synthetic %dx%d rectified pair%s per GPU per step, "
-                                       "D=%d, blockSize=5, %s, speckle filter + LR check on%s"
+                                       "D=%d, blockSize=%d, %s, speckle filter + LR check on%s"
                                        % (args.workload, WORKLOADS[args.workload][5], "one" if fps == 1 else str(fps), W, H,
-                                          "" if fps == 1 else "s (one batched call)", D, modename,
+                                          "" if fps == 1 else "s (one batched call)", D, params_for(args.workload)["blockSize"], modename,
                                           ", + fused reprojectImageTo3D/compaction" if with_reproject else ""),
                            "frames_per_step": fps,
                            "frames_per_s": args.steps * fps * world / (ms_max * 1e-3),
