@@ -16,7 +16,11 @@
 // Horizontal paths
 // =================================================================================================
 #define HZ_THREADS 128
-#define HZ_K 4                       // columns per staging chunk
+// columns per staging chunk: ~8 KB per warp and stage (4 columns at 8 lanes x 16 registers, 16 at 2 x 4)
+template <int NREG, int LPC> struct HzK {
+    static const int raw = 4096 / ((32 / LPC) * 2 * NREG * LPC);
+    static const int value = raw < 4 ? 4 : (raw > 16 ? 16 : raw);
+};
 #define HZ_NS 3                      // chunks in flight per warp
 
 // One lane group per image row and direction.  The cost rows are streamed through a per-warp ring
@@ -30,6 +34,7 @@ __global__ void __launch_bounds__(HZ_THREADS) k_horizontal(Geo g, const uint16_t
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int GPW = 32 / LPC;                         // lane groups (rows) per warp
     constexpr int NW = HZ_THREADS / 32;
+    constexpr int HZ_K = HzK<NREG, LPC>::value;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / LPC, lg = lane % LPC;
     const int W1 = g.W1, Dp = g.Dp, lastLane = g.lanesUsed - 1;
@@ -511,7 +516,7 @@ template <int NREG, int LPC>
 static int launch_horizontal_t(const Geo &g, const uint16_t *C, uint16_t *LhA, uint16_t *LhB, int y0, int nrows,
                                cudaStream_t st)
 {
-    constexpr int GPW = 32 / LPC, NW = HZ_THREADS / 32;
+    constexpr int GPW = 32 / LPC, NW = HZ_THREADS / 32, HZ_K = HzK<NREG, LPC>::value;
     const size_t smem = (size_t)NW * HZ_NS * GPW * HZ_K * g.Dp * 2 + (size_t)NW * HZ_NS * 8;
     static bool attrDone = false;
     if (!attrDone) {
