@@ -66,6 +66,7 @@ static const char *const kStageNames[ST_COUNT] = {"start", "prefilter", "cost", 
 struct ProfMark { int stage; cudaEvent_t ev; unsigned long long launches; };
 #define SGBM_MAX_LANES 3             // frames a batch call runs side by side (each on numSMs / lanes SMs)
 #define SGBM_MAX_SLOTS (2 * SGBM_MAX_LANES)
+#define SGBM_MAX_BANDS 8
 
 struct sgbm_handle {
     sgbm_params p{};
@@ -76,6 +77,10 @@ struct sgbm_handle {
     int lanesWanted = SGBM_MAX_LANES;   // SGBM_LANES=1 switches the side-by-side batch schedule off
     cudaStream_t laneStream[SGBM_MAX_LANES] = {};   // [0] unused: lane 0 runs on the caller's / the handle's stream
     cudaEvent_t evFork = nullptr, evJoin[SGBM_MAX_LANES] = {};
+    // row bands inside one frame: the horizontal kernel of band b runs beside the cost kernel of band b + 1
+    cudaStream_t bandStream[SGBM_MAX_LANES][SGBM_MAX_BANDS] = {};
+    cudaEvent_t evBand[SGBM_MAX_LANES][SGBM_MAX_BANDS] = {}, evBandJoin[SGBM_MAX_LANES][SGBM_MAX_BANDS] = {};
+    int bandsWanted = -1;               // SGBM_BANDS; -1 = decide by frame size
     // pinned + device staging for the _host entry point: two slots so that the host copies and the
     // PCIe transfers of frame b+1 / b-1 overlap the kernels of frame b
     void *hostIn[SGBM_MAX_SLOTS] = {}, *hostOut[SGBM_MAX_SLOTS] = {}, *devIn[SGBM_MAX_SLOTS] = {}, *devOut[SGBM_MAX_SLOTS] = {};
@@ -234,10 +239,14 @@ extern "C" int sgbm_create(const sgbm_params *p, sgbm_handle **out)
     if (!h) return sgbm_fail(SGBM_E_NOMEM, "out of host memory");
     h->p = *p;
     int dev = 0;
-    SGBM_CUDA_CHECK(cudaGetDevice(&dev));
-    SGBM_CUDA_CHECK(cudaDeviceGetAttribute(&h->numSMs, cudaDevAttrMultiProcessorCount, dev));
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess ||
+        (e = cudaDeviceGetAttribute(&h->numSMs, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) {
+        delete h;
+        return sgbm_fail_cuda(e, "querying the device", __FILE__, __LINE__);
+    }
     if (const char *e = getenv("SGBM_SM_LIMIT")) { const int v = atoi(e); if (v >= 1 && v < h->numSMs) h->numSMs = v; }
     if (const char *e = getenv("SGBM_LANES")) { const int v = atoi(e); h->lanesWanted = v < 1 ? 1 : (v > SGBM_MAX_LANES ? SGBM_MAX_LANES : v); }
+    if (const char *e = getenv("SGBM_BANDS")) { const int v = atoi(e); h->bandsWanted = v < 1 ? 1 : (v > SGBM_MAX_BANDS ? SGBM_MAX_BANDS : v); }
     *out = h;
     return 0;
 }
@@ -249,6 +258,11 @@ extern "C" int sgbm_destroy(sgbm_handle *h)
         if (h->ws[i]) cudaFree(h->ws[i]);
         if (h->laneStream[i]) cudaStreamDestroy(h->laneStream[i]);
         if (h->evJoin[i]) cudaEventDestroy(h->evJoin[i]);
+        for (int b = 0; b < SGBM_MAX_BANDS; b++) {
+            if (h->bandStream[i][b]) cudaStreamDestroy(h->bandStream[i][b]);
+            if (h->evBand[i][b]) cudaEventDestroy(h->evBand[i][b]);
+            if (h->evBandJoin[i][b]) cudaEventDestroy(h->evBandJoin[i][b]);
+        }
     }
     if (h->watch) cudaFreeHost(h->watch);
     if (h->evFork) cudaEventDestroy(h->evFork);
@@ -364,6 +378,21 @@ static int ensure_lane_streams(sgbm_handle *h, int lanes)
     return 0;
 }
 
+static int ensure_band_streams(sgbm_handle *h, int lane, int bands)
+{
+    int lo = 0, hi = 0;
+    SGBM_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    for (int b = 0; b < bands; b++) {
+        if (h->bandStream[lane][b]) continue;
+        // high priority: a band's few horizontal CTAs are placed as soon as they are ready, the cost kernel
+        // of the following band fills the rest of the GPU
+        SGBM_CUDA_CHECK(cudaStreamCreateWithPriority(&h->bandStream[lane][b], cudaStreamNonBlocking, hi));
+        SGBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->evBand[lane][b], cudaEventDisableTiming));
+        SGBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->evBandJoin[lane][b], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
 // One frame: the kernel schedule for each mode.
 static int compute_frame(sgbm_handle *h, int lane, int sweepSMs, const Geo &g, const WsLayout &L, const uint8_t *left,
                          const uint8_t *right, long long pitch, int16_t *out, long long outPitchElems, cudaStream_t st)
@@ -386,6 +415,7 @@ static int compute_frame(sgbm_handle *h, int lane, int sweepSMs, const Geo &g, c
     // second-generation prefilter + cost kernels (sgbm_cost2.cu); the first generation stays as the
     // fallback for geometries the new kernel does not hold (rc == 1) and for A/B runs (SGBM_COST2=0)
     bool cost2 = true, cost3 = true;
+    int bands = 1, bandRows = g.H;
     if (const char *e = getenv("SGBM_COST2")) cost2 = atoi(e) != 0;
     if (const char *e = getenv("SGBM_COST3")) cost3 = atoi(e) != 0;
     if (!cost2) cost3 = false;
@@ -398,8 +428,29 @@ static int compute_frame(sgbm_handle *h, int lane, int sweepSMs, const Geo &g, c
         if ((rc = sgbm_launch_prefilter2(g, left, right, pitch, planes, cost3 ? sgbm_cost3_eshift(g) : 0, cost3 ? 1 : 0, st))) return rc;
         if ((rc = prof_mark(h, ST_PREFILTER, st))) return rc;
         // third generation (sgbm_cost3.cu): register-resident pixel costs; 1-channel, blockSize <= 11
-        if (cost3 && (rc = sgbm_launch_cost3(g, planes, C, 0, g.H, 0, st)))
-            return rc < 0 ? rc : sgbm_fail(SGBM_E_UNSUPPORTED, "cost kernel geometry changed between plan and launch");
+        // Row bands (large frames, whole-GPU schedule): a row of the horizontal paths needs only its own cost
+        // row, so band b's horizontal kernel runs on a side stream beside band b + 1's cost kernel.  The two
+        // cannot share an SM (the cost kernel's ring takes 211 KB of shared memory), so the gain is tail
+        // filling only: 4K D=256 MODE_HH 11.39 -> 11.13 ms with two bands, 11.30 with four or eight.
+        if (cost3) {
+            bands = h->bandsWanted > 0 ? h->bandsWanted : (sweepSMs == h->numSMs && (long long)g.W1 * g.H * g.Dp >= (1ll << 30) ? 2 : 1);
+            if (p.mode == SGBM_MODE_HH4) bands = 1;                    // (its zeroed last rows are written after the cost kernel)
+            bandRows = ((g.H + bands - 1) / bands + 15) / 16 * 16;
+            bands = (g.H + bandRows - 1) / bandRows;
+            if (bands > 1 && (rc = ensure_band_streams(h, lane, bands))) return rc;
+        }
+        for (int b = 0; cost3 && b < bands; b++) {
+            const int y0 = b * bandRows, nr = g.H - y0 < bandRows ? g.H - y0 : bandRows;
+            if ((rc = sgbm_launch_cost3(g, planes, C + (size_t)y0 * g.rowStride, y0, nr, 0, st)))
+                return rc < 0 ? rc : sgbm_fail(SGBM_E_UNSUPPORTED, "cost kernel geometry changed between plan and launch");
+            if (bands > 1) {
+                cudaStream_t bs = h->bandStream[lane][b];
+                SGBM_CUDA_CHECK(cudaEventRecord(h->evBand[lane][b], st));
+                SGBM_CUDA_CHECK(cudaStreamWaitEvent(bs, h->evBand[lane][b], 0));
+                if ((rc = sgbm_launch_horizontal(g, C, LhA, LhB, y0, nr, bs))) return rc;
+                SGBM_CUDA_CHECK(cudaEventRecord(h->evBandJoin[lane][b], bs));
+            }
+        }
         if (cost3 && p.mode == SGBM_MODE_HH4 && g.r > 0) {            // A.9: the last r rows carry C = 0
             const int nz = g.r < g.H ? g.r : g.H;
             SGBM_CUDA_CHECK(cudaMemsetAsync(C + (size_t)(g.H - nz) * g.rowStride, 0, (size_t)nz * g.rowStride * 2, st));
@@ -433,7 +484,9 @@ static int compute_frame(sgbm_handle *h, int lane, int sweepSMs, const Geo &g, c
         }
     }
     if (p.mode == SGBM_MODE_SGBM_3WAY && (rc = prof_mark(h, ST_COST_ALT, st))) return rc;
-    if ((rc = sgbm_launch_horizontal(g, C, LhA, LhB, 0, g.H, st))) return rc;
+    if (bands > 1) {
+        for (int b = 0; b < bands; b++) SGBM_CUDA_CHECK(cudaStreamWaitEvent(st, h->evBandJoin[lane][b], 0));
+    } else if ((rc = sgbm_launch_horizontal(g, C, LhA, LhB, 0, g.H, st))) return rc;
     if ((rc = prof_mark(h, ST_HORIZONTAL, st))) return rc;
     if ((rc = sgbm_launch_fill_i16(raw, (size_t)g.W * g.H, g.INV, st))) return rc;
     SGBM_CUDA_CHECK(cudaMemsetAsync(d2key, 0xFF, (size_t)g.W * g.H * 4, st));
@@ -543,8 +596,30 @@ static int ensure_buf(void **p, size_t *have, size_t need, bool pinned)
     return 0;
 }
 
+static int compute_host_impl(sgbm_handle *h, const uint8_t *left, const uint8_t *right, int W, int H, int channels,
+                             ptrdiff_t pitch_bytes, int batch, int16_t *disp_out, ptrdiff_t out_pitch_bytes);
+
 extern "C" int sgbm_compute_host(sgbm_handle *h, const uint8_t *left, const uint8_t *right, int W, int H, int channels,
                                  ptrdiff_t pitch_bytes, int batch, int16_t *disp_out, ptrdiff_t out_pitch_bytes)
+{
+    const int rc = compute_host_impl(h, left, right, W, H, channels, pitch_bytes, batch, disp_out, out_pitch_bytes);
+    if (rc && h) {
+        // an error in the middle of a batch: nothing may still be reading or writing the caller's
+        // (possibly page-locked, directly DMA'd) buffers once this call has returned
+        char keep[sizeof(g_err)];
+        memcpy(keep, g_err, sizeof(keep));
+        cudaStream_t all[3 + SGBM_MAX_LANES] = {h->inStream, h->ownStream, h->outStream};
+        for (int i = 1; i < SGBM_MAX_LANES; i++) all[2 + i] = h->laneStream[i];
+        for (cudaStream_t s : all)
+            if (s) cudaStreamSynchronize(s);
+        cudaGetLastError();
+        memcpy(g_err, keep, sizeof(keep));
+    }
+    return rc;
+}
+
+static int compute_host_impl(sgbm_handle *h, const uint8_t *left, const uint8_t *right, int W, int H, int channels,
+                             ptrdiff_t pitch_bytes, int batch, int16_t *disp_out, ptrdiff_t out_pitch_bytes)
 {
     if (!h || !left || !right || !disp_out) return sgbm_fail(SGBM_E_INVALID_ARG, "null argument");
     if (batch <= 0) return sgbm_fail(SGBM_E_INVALID_ARG, "batch must be >= 1");
