@@ -429,9 +429,9 @@ static int compute_frame(sgbm_handle *h, int lane, int sweepSMs, const Geo &g, c
         if ((rc = prof_mark(h, ST_PREFILTER, st))) return rc;
         // third generation (sgbm_cost3.cu): register-resident pixel costs; 1-channel, blockSize <= 11
         // Row bands (large frames, whole-GPU schedule): a row of the horizontal paths needs only its own cost
-        // row, so band b's horizontal kernel runs on a side stream beside band b + 1's cost kernel.  The two
-        // cannot share an SM (the cost kernel's ring takes 211 KB of shared memory), so the gain is tail
-        // filling only: 4K D=256 MODE_HH 11.39 -> 11.13 ms with two bands, 11.30 with four or eight.
+        // row, so band b's horizontal kernel runs on a side stream beside band b + 1's cost kernel.  Both lean
+        // on the shared-memory data pipe, so the gain is mostly tail filling: 4K D=256 MODE_HH 11.39 -> 11.13 ms
+        // with two bands, 11.30 with four or eight.
         if (cost3) {
             bands = h->bandsWanted > 0 ? h->bandsWanted : (sweepSMs == h->numSMs && (long long)g.W1 * g.H * g.Dp >= (1ll << 30) ? 2 : 1);
             if (p.mode == SGBM_MODE_HH4) bands = 1;                    // (its zeroed last rows are written after the cost kernel)
