@@ -372,3 +372,24 @@ def test_batch_side_by_side_schedule(sg, monkeypatch, mode):
             assert got.shape == (B, H, W) and _mismatch(got.cpu().numpy(), ref) == 0, (lanes, rep, "device")
         assert _mismatch(st.compute_batch(ls, rs), ref) == 0, (lanes, "host")
         assert _mismatch(st.compute(ls[0], rs[0]), ref[0]) == 0
+
+
+@pytest.mark.parametrize("bands", ["2", "3", "8"])
+def test_row_band_schedule(sg, monkeypatch, bands):
+    """Large frames are cut into row bands so that a band's horizontal kernel runs beside the next band's
+    cost kernel (SGBM_BANDS forces the band count on a small frame): heights that are not a multiple of
+    the band granularity, every mode (MODE_HH4 keeps one band), repeated frames and batches."""
+    import torch
+    monkeypatch.setenv("SGBM_BANDS", bands)
+    W, D = 600, 64
+    for H in (83, 48, 17):
+        pairs = [make_pair(W, H, D, seed=60 + i)[:2] for i in range(3)]
+        ls = np.stack([l for l, _ in pairs]); rs = np.stack([r for _, r in pairs])
+        for mode in (0, 1, 2, 3):
+            p = OracleParams(0, D, 5, 200, 800, 1, 63, 10, 100, 32, mode)
+            ref = np.stack([oracle.compute(p, l, r) for l, r in pairs])
+            st = sg.StereoSGBM_create(**_kw(p))
+            for rep in range(3):
+                assert _mismatch(st.compute(ls[rep], rs[rep]), ref[rep]) == 0, (bands, H, mode, rep)
+            got = st.compute(torch.from_numpy(ls).cuda(), torch.from_numpy(rs).cuda())
+            assert _mismatch(got.cpu().numpy(), ref) == 0, (bands, H, mode, "batch")
