@@ -128,6 +128,40 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity)
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// The same operations on a barrier named by its 32-bit shared-memory address: kernels that touch many
+// barriers per row (sgbm_sweep.cu) keep those instead of generic pointers -- no generic->shared conversion
+// at every use, one register per barrier array instead of two.
+struct SmemBar {
+    uint32_t addr;
+    __device__ __forceinline__ SmemBar operator[](int i) const { return SmemBar{addr + 8u * (uint32_t)i}; }
+};
+__device__ __forceinline__ void mbar_init(SmemBar bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar.addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(SmemBar bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar.addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, SmemBar bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(bar.addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(SmemBar bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar.addr), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_test_wait(SmemBar bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar.addr), "r"(parity) : "memory");
+    return ok != 0;
+}
 // Blocking wait.  The retry passes a suspend-time hint so that a waiting warp sleeps in hardware
 // instead of burning issue slots in a poll loop; ~80 s without progress traps (protocol error; the
 // bound is generous because profilers that patch the kernel slow it down by orders of magnitude).

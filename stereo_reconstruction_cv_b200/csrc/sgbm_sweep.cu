@@ -69,9 +69,9 @@ struct SweepArgs {
 #endif
 
 
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+__device__ __forceinline__ void mbar_arrive(SmemBar bar)
 {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar.addr) : "memory");
 }
 // Bounded waits of the sweep.  A hand-off that makes no progress for ~2 s (a protocol error: it never
 // happens in the validated configurations) does not trap -- that would poison the CUDA context -- but
@@ -97,7 +97,7 @@ __device__ __noinline__ void sweep_timeout(unsigned int *dbg, int id, int t)
 #endif
     }
 }
-__device__ __forceinline__ void sweep_wait(const SweepArgs &a, uint64_t *bar, uint32_t parity, int id, int t)
+__device__ __forceinline__ void sweep_wait(const SweepArgs &a, SmemBar bar, uint32_t parity, int id, int t)
 {
     if (mbar_try_wait(bar, parity)) return;
     // the retry loop stays inline PTX (no call, two scratch registers): waiting here is the normal case
@@ -121,7 +121,7 @@ __device__ __forceinline__ void sweep_wait(const SweepArgs &a, uint64_t *bar, ui
         "@q bra SGBM_SW_WAIT;\n\t"
         "mov.u32 %0, 1;\n"
         "SGBM_SW_DONE:\n\t"
-        "}" : "=r"(to) : "r"(smem_u32(bar)), "r"(parity), "l"(a.dbg) : "memory");
+        "}" : "=r"(to) : "r"(bar.addr), "r"(parity), "l"(a.dbg) : "memory");
     if (to) sweep_timeout(a.dbg, id, t);
 }
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p)
@@ -147,7 +147,7 @@ __device__ __forceinline__ void load_vec_l2(uint32_t (&v)[NREG], const uint16_t 
 
 struct SweepSmem {
     uint16_t *stgC, *stgI, *P, *ssm;
-    uint64_t *fullC, *emptyC, *fullI, *emptyI, *fullV, *fullM, *freeP, *fullW;
+    SmemBar fullC, emptyC, fullI, emptyI, fullV, fullM, freeP, fullW;     // 32-bit shared addresses
 };
 __device__ __forceinline__ SweepSmem sweep_carve(const SweepArgs &a, uint8_t *smem)
 {
@@ -156,14 +156,14 @@ __device__ __forceinline__ SweepSmem sweep_carve(const SweepArgs &a, uint8_t *sm
     s.stgI = reinterpret_cast<uint16_t *>(smem + a.stgIOff);     // [NSI][nAB][SW][Dp]
     s.P = reinterpret_cast<uint16_t *>(smem + a.pOff);           // [K][SW][Dp]
     s.ssm = reinterpret_cast<uint16_t *>(smem + a.ssmOff);       // [groups of role C][Dp]  (WTA scratch)
-    uint64_t *b = reinterpret_cast<uint64_t *>(smem + a.barOff);
-    s.fullC = b; b += a.NSC;
-    s.emptyC = b; b += a.NSC;
-    s.fullI = b; b += a.NSI;
-    s.emptyI = b; b += a.NSI;
-    s.fullV = b; b += a.K;
-    s.fullM = b; b += a.K;
-    s.freeP = b; b += a.K;
+    SmemBar b{smem_u32(smem) + (uint32_t)a.barOff};
+    s.fullC = b; b = b[a.NSC];
+    s.emptyC = b; b = b[a.NSC];
+    s.fullI = b; b = b[a.NSI];
+    s.emptyI = b; b = b[a.NSI];
+    s.fullV = b; b = b[a.K];
+    s.fullM = b; b = b[a.K];
+    s.freeP = b; b = b[a.K];
     s.fullW = b;
     return s;
 }
@@ -182,16 +182,16 @@ __device__ __forceinline__ void sweep_producer(const SweepArgs &a, const SweepSm
     for (int t = 0; t < nRows; t++) {
         const int y = yBegin + t * yStep;
         SWEEP_TR(3, 0, true);
-        if (t >= a.NSC) sweep_wait(a, &s.emptyC[sc], pc ^ 1u, 1, t);
+        if (t >= a.NSC) sweep_wait(a, s.emptyC[sc], pc ^ 1u, 1, t);
         SWEEP_TR(3, 1, true);
-        mbar_expect_tx(&s.fullC[sc], bytesC);
+        mbar_expect_tx(s.fullC[sc], bytesC);
         bulk_g2s(s.stgC + ((size_t)sc * ngC + (clo - scol0)) * Dp, a.C + (size_t)y * g.rowStride + (size_t)clo * Dp, bytesC,
-                 &s.fullC[sc]);
-        if (t >= a.NSI) sweep_wait(a, &s.emptyI[si], pi ^ 1u, 2, t);
+                 s.fullC[sc]);
+        if (t >= a.NSI) sweep_wait(a, s.emptyI[si], pi ^ 1u, 2, t);
         const size_t off = (size_t)y * g.rowStride + (size_t)xs * Dp;
-        mbar_expect_tx(&s.fullI[si], bytesI * (uint32_t)a.nAB);
-        bulk_g2s(s.stgI + (size_t)(si * a.nAB + 0) * a.SW * Dp, a.inA + off, bytesI, &s.fullI[si]);
-        if (a.nAB > 1) bulk_g2s(s.stgI + (size_t)(si * a.nAB + 1) * a.SW * Dp, a.inB + off, bytesI, &s.fullI[si]);
+        mbar_expect_tx(s.fullI[si], bytesI * (uint32_t)a.nAB);
+        bulk_g2s(s.stgI + (size_t)(si * a.nAB + 0) * a.SW * Dp, a.inA + off, bytesI, s.fullI[si]);
+        if (a.nAB > 1) bulk_g2s(s.stgI + (size_t)(si * a.nAB + 1) * a.SW * Dp, a.inB + off, bytesI, s.fullI[si]);
         SWEEP_TR(3, 2, true);
         if (++sc == a.NSC) { sc = 0; pc ^= 1u; }
         if (++si == a.NSI) { si = 0; pi ^= 1u; }
@@ -231,20 +231,20 @@ __device__ __forceinline__ void sweep_role_v(const SweepArgs &a, const SweepSmem
         uint32_t S[NREG];
         SWEEP_PROG(0, rwarp == 0);
         SWEEP_TR(0, 0, rwarp == 0);
-        if (!okC) sweep_wait(a, &s.fullC[sc], pc, 3, t);
+        if (!okC) sweep_wait(a, s.fullC[sc], pc, 3, t);
         SWEEP_TR(0, 1, rwarp == 0);
         // probes whose latency hides behind the path step
-        const bool okI = mbar_test_wait(&s.fullI[si], pi);
-        const bool okP = t >= K ? mbar_test_wait(&s.freeP[k], pk ^ 1u) : true;
+        const bool okI = mbar_test_wait(s.fullI[si], pi);
+        const bool okP = t >= K ? mbar_test_wait(s.freeP[k], pk ^ 1u) : true;
         {
             uint32_t Cc[NREG];
             load_vec<NREG, LPC>(Cc, s.stgC + cOff, lg);
             const int scN = sc + 1 == NSC ? 0 : sc + 1;
-            okC = t + 1 < nRows ? mbar_test_wait(&s.fullC[scN], scN ? pc : pc ^ 1u) : true;
+            okC = t + 1 < nRows ? mbar_test_wait(s.fullC[scN], scN ? pc : pc ^ 1u) : true;
             mB = path_step<NREG, LPC>(LB, LB, mB, Cc, P1p, P2mP1p, lg, lastLane);   // in place (reads run ahead of writes)
         }
         SWEEP_TR(0, 2, rwarp == 0);
-        if (!okI) sweep_wait(a, &s.fullI[si], pi, 4, t);
+        if (!okI) sweep_wait(a, s.fullI[si], pi, 4, t);
         load_vec<NREG, LPC>(S, s.stgI + iOff, lg);
 #pragma unroll
         for (int j = 0; j < NREG; j++) S[j] = sacc<SAT>(S[j], LB[j]);
@@ -255,14 +255,14 @@ __device__ __forceinline__ void sweep_role_v(const SweepArgs &a, const SweepSmem
             for (int j = 0; j < NREG; j++) S[j] = sacc<SAT>(S[j], Bv[j]);
         }
         SWEEP_TR(0, 3, rwarp == 0);
-        if (!okP) sweep_wait(a, &s.freeP[k], pk ^ 1u, 5, t);
+        if (!okP) sweep_wait(a, s.freeP[k], pk ^ 1u, 5, t);
         SWEEP_TR(0, 4, rwarp == 0);
         if (own) store_vec<NREG, LPC>(S, s.P + pOff, lg);
         __syncwarp();
         if (lane == 0) {
-            if (!(a.dbgStall && t == 5 && blockIdx.x == 0)) mbar_arrive(&s.fullV[k]);
-            mbar_arrive(&s.emptyC[sc]);
-            mbar_arrive(&s.emptyI[si]);
+            if (!(a.dbgStall && t == 5 && blockIdx.x == 0)) mbar_arrive(s.fullV[k]);
+            mbar_arrive(s.emptyC[sc]);
+            mbar_arrive(s.emptyI[si]);
         }
         SWEEP_TR(0, 5, rwarp == 0);
         cOff += cStride; iOff += iStride; pOff += pStride;
@@ -440,14 +440,14 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
             m = 0;
         }
         // WROLE: the finished S goes back into the slot and the winner-take-all warps release it
-        uint64_t *waitBar = FINAL ? s.fullM : s.fullV, *doneBar = FINAL ? (WROLE ? s.fullW : s.freeP) : s.fullM;
+        const SmemBar waitBar = FINAL ? s.fullM : s.fullV, doneBar = FINAL ? (WROLE ? s.fullW : s.freeP) : s.fullM;
         SWEEP_TR(DIR > 0 ? 1 : 2, 0, rwarp == a.nwA / 2);
-        if (!okC) sweep_wait(a, &s.fullC[sc], pc, DIR > 0 ? 8 : 9, t);
+        if (!okC) sweep_wait(a, s.fullC[sc], pc, DIR > 0 ? 8 : 9, t);
         SWEEP_TR(DIR > 0 ? 1 : 2, 1, rwarp == a.nwA / 2);
-        const bool okS = mbar_test_wait(&waitBar[k], pk);  // latency hides behind the path step
+        const bool okS = mbar_test_wait(waitBar[k], pk);  // latency hides behind the path step
         {
             const int scN = sc + 1 == NSC ? 0 : sc + 1;
-            okC = t + 1 < nRows ? mbar_test_wait(&s.fullC[scN], scN ? pc : pc ^ 1u) : true;
+            okC = t + 1 < nRows ? mbar_test_wait(s.fullC[scN], scN ? pc : pc ^ 1u) : true;
         }
         if (__any_sync(0xFFFFFFFFu, active)) {           // inactive groups compute garbage that is never used
             uint32_t Cc[NREG];
@@ -475,7 +475,7 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
         }
         // ---- S slot of this row ---------------------------------------------------------------------
         SWEEP_TR(DIR > 0 ? 1 : 2, 2, rwarp == a.nwA / 2);
-        if (!okS) sweep_wait(a, &waitBar[k], pk, DIR > 0 ? 10 : 11, t);
+        if (!okS) sweep_wait(a, waitBar[k], pk, DIR > 0 ? 10 : 11, t);
         SWEEP_TR(DIR > 0 ? 1 : 2, 3, rwarp == a.nwA / 2);
         uint32_t S[NREG];
         if (own) {
@@ -490,8 +490,8 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
         }
         __syncwarp();
         if (lane == 0) {
-            mbar_arrive(&doneBar[k]);
-            mbar_arrive(&s.emptyC[sc]);
+            mbar_arrive(doneBar[k]);
+            mbar_arrive(s.emptyC[sc]);
         }
         SWEEP_TR(DIR > 0 ? 1 : 2, 4, rwarp == a.nwA / 2);
         if (FINAL && !WROLE && __any_sync(0xFFFFFFFFu, own)) {
@@ -613,7 +613,7 @@ __device__ __forceinline__ void sweep_role_w(const SweepArgs &a, const SweepSmem
     for (int t = 0; t < nRows; t++) {
         const int y = yBegin + t * yStep;
         SWEEP_PROG(5, wwarp == 0);
-        sweep_wait(a, &s.fullW[k], pk, 12, t);
+        sweep_wait(a, s.fullW[k], pk, 12, t);
         for (int it = 0; it < a.wPass; it++) {
             const int gi = (it * a.nwW + wwarp) * GPW + lane / LPC;
             const bool own = gi < SW;
@@ -623,7 +623,7 @@ __device__ __forceinline__ void sweep_role_w(const SweepArgs &a, const SweepSmem
             sweep_wta_slot<NREG, LPC, SAT>(a, s.P + pOff + ci * Dp, lg, own, xs + ci, y);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s.freeP[k]);
+        if (lane == 0) mbar_arrive(s.freeP[k]);
         pOff += pStride;
         if (++k == K) { k = 0; pk ^= 1u; pOff = 0; }
     }
@@ -644,11 +644,11 @@ __global__ void __launch_bounds__((SweepMaxThreads<NREG, WROLE>::value), 1) k_sw
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         const int nCons = a.nwV + 2 * a.nwA;
-        for (int q = 0; q < a.NSC; q++) { mbar_init(&s.fullC[q], 1); mbar_init(&s.emptyC[q], nCons); }
-        for (int q = 0; q < a.NSI; q++) { mbar_init(&s.fullI[q], 1); mbar_init(&s.emptyI[q], a.nwV); }
+        for (int q = 0; q < a.NSC; q++) { mbar_init(s.fullC[q], 1); mbar_init(s.emptyC[q], nCons); }
+        for (int q = 0; q < a.NSI; q++) { mbar_init(s.fullI[q], 1); mbar_init(s.emptyI[q], a.nwV); }
         for (int q = 0; q < a.K; q++) {
-            mbar_init(&s.fullV[q], a.nwV); mbar_init(&s.fullM[q], a.nwA);
-            mbar_init(&s.freeP[q], WROLE ? a.nwW : a.nwA); mbar_init(&s.fullW[q], a.nwA);
+            mbar_init(s.fullV[q], a.nwV); mbar_init(s.fullM[q], a.nwA);
+            mbar_init(s.freeP[q], WROLE ? a.nwW : a.nwA); mbar_init(s.fullW[q], a.nwA);
         }
         mbar_fence_init();
     }
