@@ -64,6 +64,9 @@ const char *sgbm_version(void);
 /* Number of SMs / device name of the current CUDA device (diagnostics for bench.py). */
 int sgbm_device_info(int *sm_count, int *cc_major, int *cc_minor, char *name, int name_len);
 
+/* A handle belongs to the CUDA device that is current when it is created (its workspace, streams and
+ * events live there): make the same device current for every later call on it, or the call returns
+ * SGBM_E_INVALID_ARG.  A process may hold handles on several devices. */
 int sgbm_create(const sgbm_params *p, sgbm_handle **out);
 int sgbm_destroy(sgbm_handle *h);
 int sgbm_set_params(sgbm_handle *h, const sgbm_params *p);

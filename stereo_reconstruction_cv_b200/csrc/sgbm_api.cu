@@ -71,6 +71,7 @@ struct ProfMark { int stage; cudaEvent_t ev; unsigned long long launches; };
 struct sgbm_handle {
     sgbm_params p{};
     int numSMs = 0;
+    int device = 0;                     // the device that was current at sgbm_create: workspace, streams and events live there
     // device workspace (grown on demand); lane 1 exists only while batches run two frames side by side
     void *ws[SGBM_MAX_LANES] = {};
     size_t wsBytes[SGBM_MAX_LANES] = {};
@@ -119,6 +120,15 @@ static int prof_mark(sgbm_handle *h, int stage, cudaStream_t st)
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int check_device(const sgbm_handle *h)
+{
+    int dev = -1;
+    SGBM_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev != h->device)
+        return sgbm_fail(SGBM_E_INVALID_ARG, "handle was created on CUDA device %d but device %d is current", h->device, dev);
+    return 0;
+}
 
 // Effective parameters and geometry (A.0) + lane mapping.  Returns 0 or an error code.
 static int make_geo(const sgbm_params &p, int W, int H, int cn, Geo &g)
@@ -244,6 +254,7 @@ extern "C" int sgbm_create(const sgbm_params *p, sgbm_handle **out)
         delete h;
         return sgbm_fail_cuda(e, "querying the device", __FILE__, __LINE__);
     }
+    h->device = dev;
     if (const char *e = getenv("SGBM_SM_LIMIT")) { const int v = atoi(e); if (v >= 1 && v < h->numSMs) h->numSMs = v; }
     if (const char *e = getenv("SGBM_LANES")) { const int v = atoi(e); h->lanesWanted = v < 1 ? 1 : (v > SGBM_MAX_LANES ? SGBM_MAX_LANES : v); }
     if (const char *e = getenv("SGBM_BANDS")) { const int v = atoi(e); h->bandsWanted = v < 1 ? 1 : (v > SGBM_MAX_BANDS ? SGBM_MAX_BANDS : v); }
@@ -552,6 +563,7 @@ extern "C" int sgbm_compute(sgbm_handle *h, const uint8_t *left, const uint8_t *
 {
     if (!h || !left || !right || !disp_out) return sgbm_fail(SGBM_E_INVALID_ARG, "null argument");
     if (batch <= 0) return sgbm_fail(SGBM_E_INVALID_ARG, "batch must be >= 1");
+    if (int rcDev = check_device(h)) return rcDev;
     if (pitch_bytes < (ptrdiff_t)W * channels || out_pitch_bytes < (ptrdiff_t)W * 2 || (out_pitch_bytes & 1))
         return sgbm_fail(SGBM_E_INVALID_ARG, "bad pitch (in %td, out %td) for width %d", pitch_bytes, out_pitch_bytes, W);
     Geo g;
@@ -623,6 +635,7 @@ static int compute_host_impl(sgbm_handle *h, const uint8_t *left, const uint8_t 
 {
     if (!h || !left || !right || !disp_out) return sgbm_fail(SGBM_E_INVALID_ARG, "null argument");
     if (batch <= 0) return sgbm_fail(SGBM_E_INVALID_ARG, "batch must be >= 1");
+    if (int rcDev = check_device(h)) return rcDev;
     if (pitch_bytes < (ptrdiff_t)W * channels || out_pitch_bytes < (ptrdiff_t)W * 2)
         return sgbm_fail(SGBM_E_INVALID_ARG, "bad pitch");
     Geo g;

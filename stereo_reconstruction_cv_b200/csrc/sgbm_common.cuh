@@ -90,6 +90,18 @@ __device__ __forceinline__ void store_vec(const uint32_t (&v)[NREG], uint16_t *c
 }
 
 
+// Host: true the first time it is called with this mask on the current device (cudaFuncSetAttribute is
+// per device; a process may hold handles on several).
+static inline bool sgbm_first_use_on_device(unsigned long long &mask)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return true;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+}
+
 // ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers ------------------------------
 // One elected lane arms an mbarrier with the byte count and issues global->shared bulk copies; the
 // consumers wait on the barrier's phase parity.  Waits are bounded: a protocol error traps instead

@@ -225,10 +225,9 @@ int sgbm_launch_prefilter(const Geo &g, const uint8_t *left, const uint8_t *righ
 template <int NREG, int XPT>
 static int launch_cost_t(CostArgs &a, int threads, size_t smem, dim3 grid, int maxSmem, cudaStream_t st)
 {
-    static bool attrDone = false;
-    if (!attrDone) {
+    static unsigned long long attrDone = 0;   // one bit per device: function attributes are per device
+    if (sgbm_first_use_on_device(attrDone)) {
         SGBM_CUDA_CHECK(cudaFuncSetAttribute(k_cost<NREG, XPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
-        attrDone = true;
     }
     k_cost<NREG, XPT><<<grid, threads, smem, st>>>(a);
     sgbm_count_launch(1);

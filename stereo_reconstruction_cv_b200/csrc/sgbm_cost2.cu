@@ -384,10 +384,9 @@ static bool cost2_layout(Cost2Args &a, int TX, size_t maxSmem, size_t *total)
 template <int NREG, int LPC, int XPT>
 static int launch_cost2_t(Cost2Args &a, int threads, size_t smem, dim3 grid, int maxSmem, cudaStream_t st)
 {
-    static bool attrDone = false;
-    if (!attrDone) {
+    static unsigned long long attrDone = 0;   // one bit per device: function attributes are per device
+    if (sgbm_first_use_on_device(attrDone)) {
         SGBM_CUDA_CHECK(cudaFuncSetAttribute(k_cost2<NREG, LPC, XPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
-        attrDone = true;
     }
     k_cost2<NREG, LPC, XPT><<<grid, threads, smem, st>>>(a);
     sgbm_count_launch(1);

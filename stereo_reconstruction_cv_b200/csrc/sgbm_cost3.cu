@@ -362,10 +362,9 @@ int sgbm_cost3_supported(const Geo &g)
 template <int R, int PAR, int DWT, int NTT>
 static int launch_cost3_t(Cost3Args &a, int threads, size_t smem, dim3 grid, int maxSmem, cudaStream_t st)
 {
-    static bool attrDone = false;
-    if (!attrDone) {
+    static unsigned long long attrDone = 0;   // one bit per device: function attributes are per device
+    if (sgbm_first_use_on_device(attrDone)) {
         SGBM_CUDA_CHECK(cudaFuncSetAttribute(k_cost3<R, PAR, DWT, NTT>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
-        attrDone = true;
     }
     k_cost3<R, PAR, DWT, NTT><<<grid, threads, smem, st>>>(a);
     sgbm_count_launch(1);

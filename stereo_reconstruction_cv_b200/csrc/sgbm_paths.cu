@@ -518,10 +518,9 @@ static int launch_horizontal_t(const Geo &g, const uint16_t *C, uint16_t *LhA, u
 {
     constexpr int GPW = 32 / LPC, NW = HZ_THREADS / 32, HZ_K = HzK<NREG, LPC>::value;
     const size_t smem = (size_t)NW * HZ_NS * GPW * HZ_K * g.Dp * 2 + (size_t)NW * HZ_NS * 8;
-    static bool attrDone = false;
-    if (!attrDone) {
+    static unsigned long long attrDone = 0;   // one bit per device: function attributes are per device
+    if (sgbm_first_use_on_device(attrDone)) {
         SGBM_CUDA_CHECK(cudaFuncSetAttribute(k_horizontal<NREG, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attrDone = true;
     }
     const int rowsPerCta = NW * GPW;
     dim3 grid((nrows + rowsPerCta - 1) / rowsPerCta, 2);
@@ -538,14 +537,13 @@ static int launch_vertical_t(VertArgs &a, int numSMs, cudaStream_t st)
 {
     const Geo &g = a.g;
     auto kern = k_vertical<NREG, LPC, NDIR>;
-    static bool attrDone = false;
+    static unsigned long long attrDone = 0;   // one bit per device: function attributes are per device
     static int maxSmem = 0;
-    if (!attrDone) {
+    if (sgbm_first_use_on_device(attrDone)) {
         int dev = 0;
         SGBM_CUDA_CHECK(cudaGetDevice(&dev));
         SGBM_CUDA_CHECK(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         SGBM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
-        attrDone = true;
     }
     int nstgWant = 3;
     if (const char *e = getenv("SGBM_NSTG")) nstgWant = atoi(e) >= 2 && atoi(e) <= 4 ? atoi(e) : 3;

@@ -785,14 +785,13 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
     constexpr int GPW = 32 / LPC;
     const Geo &g = va.g;
     auto kern = k_sweep<NREG, LPC, SAT, WROLE>;
-    static bool attrDone = false;
+    static unsigned long long attrDone = 0;   // one bit per device: function attributes are per device
     static int maxSmem = 0;
-    if (!attrDone) {
+    if (sgbm_first_use_on_device(attrDone)) {
         int dev = 0;
         SGBM_CUDA_CHECK(cudaGetDevice(&dev));
         SGBM_CUDA_CHECK(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         SGBM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
-        attrDone = true;
     }
     SweepArgs a;
     memset(&a, 0, sizeof(a));
