@@ -16,8 +16,15 @@
  * success or a negative SGBM_E_* code; sgbm_last_error() returns a thread-local message.  No
  * exception crosses the ABI.  Unless the name ends in _host, image/disparity pointers are DEVICE
  * pointers and all work is enqueued on `cuda_stream` (a cudaStream_t passed as void*) without a
- * host synchronisation; the caller owns all buffers, the handle owns its workspace.  A handle is
- * not thread-safe; distinct handles are.
+ * host synchronisation; the caller owns all buffers, the handle owns its workspace.
+ *
+ * Threads and streams.  Calls on ONE handle are serialised by the library (a mutex around the enqueue)
+ * and ordered on the device: a call waits, on its own stream, for the end of the handle's previous call,
+ * whatever stream that ran on, because the workspace belongs to the handle.  Distinct handles are
+ * independent and may be driven from different threads, streams and devices concurrently.
+ *
+ * Environment knobs (SGBM_*; tuning and A/B tests) are read once, by sgbm_create, and stay with the
+ * handle; nothing reads the environment afterwards.  The release library has no result-changing hook.
  */
 #ifndef SGBM_B200_H
 #define SGBM_B200_H
@@ -72,8 +79,9 @@ int sgbm_destroy(sgbm_handle *h);
 int sgbm_set_params(sgbm_handle *h, const sgbm_params *p);
 int sgbm_get_params(const sgbm_handle *h, sgbm_params *p);
 
-/* Bytes of device workspace compute() needs for one W x H frame (volumes C, L_h, S, ...). */
-int sgbm_workspace_bytes(const sgbm_handle *h, int W, int H, int channels, size_t *out);
+/* Bytes of device workspace the handle allocates for calls with `batch` W x H frames (volumes C, L_h,
+ * S, ... of every frame it keeps in flight: one for batch = 1, up to three side by side for batches). */
+int sgbm_workspace_bytes(const sgbm_handle *h, int W, int H, int channels, int batch, size_t *out);
 
 /*
  * Disparity for `batch` independent rectified pairs (frames are processed one after another on
@@ -108,6 +116,17 @@ int sgbm_reproject_f32(const float *disp, const double *Q, int W, int H, float *
                        uint8_t *valid_or_null, void *cuda_stream);
 int sgbm_reproject_i16(const int16_t *disp, const double *Q, int W, int H, float *xyz,
                        uint8_t *valid_or_null, void *cuda_stream);
+
+/*
+ * The full cv2.reprojectImageTo3D(disparity, Q, handleMissingValues, ddepth) surface.  disp_depth and
+ * ddepth are cv2 depth codes: 0 = CV_8U, 3 = CV_16S, 4 = CV_32S, 5 = CV_32F (ddepth -1 = CV_32F).
+ * Integer disparities are converted to float32 and used as they are (no /16), like cv2.
+ * handle_missing_values: Z = 10000 where |d - min(disparity)| <= FLT_EPSILON; needs scratch16 (16 bytes
+ * of device memory).  Integer ddepth: cvRound (half to even; what does not fit an int32, NaN and +-inf
+ * included, becomes INT_MIN), CV_16S saturates.  out: H x W x 3 of the ddepth type.
+ */
+int sgbm_reproject_ex(const void *disp, int disp_depth, const double *Q, int W, int H, int handle_missing_values,
+                      int ddepth, void *out, void *scratch16, void *cuda_stream);
 
 /*
  * Fused tail of the notebook (main.ipynb:668-670, 697, 726-737): int16 disparity x16 ->

@@ -5,6 +5,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsgbm_b200.so")
+# Same sources built with -DSGBM_DEBUG_HOOKS (hand-off fault injection): loaded by one test only, never by the package.
+DEBUG_LIB_PATH = os.path.join(_HERE, "libsgbm_b200_dbg.so")
 _LIB = None
 
 # every symbol include/sgbm_b200.h declares
@@ -15,7 +17,7 @@ SYMBOLS = [
     "sgbm_reproject_compact_scratch_bytes", "sgbm_filter_speckles", "sgbm_median3x3",
     "sgbm_debug_keep", "sgbm_debug_fetch", "sgbm_microbench_int16", "sgbm_kernel_launches",
     "sgbm_profile_enable", "sgbm_profile_read", "sgbm_init_rectify_map", "sgbm_remap_linear_u8",
-    "sgbm_status",
+    "sgbm_status", "sgbm_reproject_ex",
 ]
 
 
@@ -33,14 +35,12 @@ class error(Exception):
         self.code = code
 
 
-def lib():
-    global _LIB
-    if _LIB is not None:
-        return _LIB
-    if not os.path.exists(LIB_PATH):
+def load(path):
+    """dlopen a build of the library and declare the prototypes of include/sgbm_b200.h."""
+    if not os.path.exists(path):
         raise ImportError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-                          "(nvcc, sm_100a). This engine has no CPU fallback." % LIB_PATH)
-    L = C.CDLL(LIB_PATH)
+                          "(nvcc, sm_100a). This engine has no CPU fallback." % path)
+    L = C.CDLL(path)
     vp, i, sz, pd = C.c_void_p, C.c_int, C.c_size_t, C.c_ssize_t
     L.sgbm_last_error.restype = C.c_char_p
     L.sgbm_version.restype = C.c_char_p
@@ -49,7 +49,7 @@ def lib():
     L.sgbm_destroy.argtypes = [vp]
     L.sgbm_set_params.argtypes = [vp, C.POINTER(SgbmParams)]
     L.sgbm_get_params.argtypes = [vp, C.POINTER(SgbmParams)]
-    L.sgbm_workspace_bytes.argtypes = [vp, i, i, i, C.POINTER(sz)]
+    L.sgbm_workspace_bytes.argtypes = [vp, i, i, i, i, C.POINTER(sz)]
     L.sgbm_compute.argtypes = [vp, vp, vp, i, i, i, pd, i, vp, pd, vp]
     L.sgbm_compute_host.argtypes = [vp, vp, vp, i, i, i, pd, i, vp, pd]
     L.sgbm_disp_to_float.argtypes = [vp, i, i, vp, vp]
@@ -62,15 +62,24 @@ def lib():
     L.sgbm_init_rectify_map.argtypes = [vp, vp, i, vp, vp, i, i, i, vp, vp, vp]
     L.sgbm_remap_linear_u8.argtypes = [vp, i, i, i, pd, vp, vp, i, i, vp, pd, vp]
     L.sgbm_status.argtypes = [vp]
+    L.sgbm_reproject_ex.argtypes = [vp, i, vp, i, i, i, i, vp, vp, vp]
+    L.sgbm_kernel_launches.argtypes = []
+    L.sgbm_kernel_launches.restype = C.c_ulonglong
     L.sgbm_debug_keep.argtypes = [vp, i]
     L.sgbm_debug_fetch.argtypes = [vp, i, vp, sz]
     L.sgbm_microbench_int16.argtypes = [i, C.POINTER(C.c_double)]
     for name in SYMBOLS:
         fn = getattr(L, name)
-        if fn.restype is C.c_int or fn.restype is None:
+        if name not in ("sgbm_last_error", "sgbm_version", "sgbm_kernel_launches"):
             fn.restype = C.c_int
-    _LIB = L
     return L
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = load(LIB_PATH)
+    return _LIB
 
 
 def check(rc):

@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <atomic>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -31,6 +32,8 @@ int sgbm_launch_speckles(int16_t *img, int W, int H, int newVal, int maxSize, in
 int sgbm_launch_disp_to_float(const int16_t *d, float *out, size_t n, cudaStream_t st);
 int sgbm_launch_reproject(const void *disp, int isFloat, const double *Qh, int W, int H, float *xyz, uint8_t *valid, cudaStream_t st);
 size_t sgbm_compact_scratch_bytes(int W, int H);
+int sgbm_launch_reproject_ex(const void *disp, int dispDepth, const double *Qh, int W, int H, int handleMissing, int ddepth,
+                             void *out, void *scratch, cudaStream_t st);
 int sgbm_launch_compact(const int16_t *disp, const double *Qh, int W, int H, const uint8_t *bgr, int bgrCn, long long bgrPitch,
                         float *xyz, uint8_t *rgb, unsigned long long *nOut, void *scratch, cudaStream_t st);
 int sgbm_run_microbench(int which, double *out);
@@ -70,6 +73,10 @@ struct ProfMark { int stage; cudaEvent_t ev; unsigned long long launches; };
 
 struct sgbm_handle {
     sgbm_params p{};
+    SgbmKnobs knobs{};                  // environment knobs + device facts, read once in sgbm_create
+    std::mutex mu;                      // calls on one handle are serialised (and ordered by evLast on the device)
+    cudaEvent_t evLast = nullptr;       // end of the handle's previous call: the next call's stream waits for it
+    bool evLastValid = false;
     int numSMs = 0;
     int device = 0;                     // the device that was current at sgbm_create: workspace, streams and events live there
     // device workspace (grown on demand); lane 1 exists only while batches run two frames side by side
@@ -121,6 +128,49 @@ static int prof_mark(sgbm_handle *h, int stage, cudaStream_t st)
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// ---- knobs of the running call ---------------------------------------------------------------------
+static thread_local const SgbmKnobs *g_knobs = nullptr;
+static const SgbmKnobs g_defaultKnobs{};
+const SgbmKnobs &sgbm_knobs() { return g_knobs ? *g_knobs : g_defaultKnobs; }
+std::mutex &sgbm_setup_mutex() { static std::mutex m; return m; }
+struct KnobScope {
+    const SgbmKnobs *prev;
+    explicit KnobScope(const sgbm_handle *h) : prev(g_knobs) { g_knobs = &h->knobs; }
+    ~KnobScope() { g_knobs = prev; }
+};
+
+static int env_int(const char *name, int dflt)
+{
+    const char *e = getenv(name);
+    return e && *e ? atoi(e) : dflt;
+}
+
+// The one place the environment is read: sgbm_create.
+static void read_knobs(SgbmKnobs &k)
+{
+    k.nreg = env_int("SGBM_NREG", 0);
+    k.vr = env_int("SGBM_VR", 0);
+    k.sweepK = env_int("SGBM_SWEEP_K", 0); k.sweepNSC = env_int("SGBM_SWEEP_NSC", 0);
+    k.sweepNSI = env_int("SGBM_SWEEP_NSI", 0); k.sweepNWW = env_int("SGBM_SWEEP_NWW", 0);
+    k.sweepW = env_int("SGBM_SWEEP_W", 1) != 0;
+    k.sweep = env_int("SGBM_SWEEP", 1) != 0;
+    k.rowstep = env_int("SGBM_ROWSTEP", 0) != 0;
+    k.cost2 = env_int("SGBM_COST2", 1) != 0;
+    k.cost3 = env_int("SGBM_COST3", 1) != 0;
+    k.cost3NXG = env_int("SGBM_COST3_NXG", 0); k.cost3RB = env_int("SGBM_COST3_RB", 0);
+    k.nstg = env_int("SGBM_NSTG", 0);
+    k.sweepSat = env_int("SGBM_SWEEP_SAT", 0) != 0;
+    k.smallD = env_int("SGBM_SMALLD", 1) != 0;
+    k.verbose = env_int("SGBM_VERBOSE", 0) != 0;
+#ifdef SGBM_DEBUG_HOOKS
+    k.dbgNoSync = getenv("SGBM_DBG_NOSYNC") ? 1 : 0;
+    k.dbgStall = getenv("SGBM_DBG_STALL") ? 1 : 0;
+#endif
+#ifdef SGBM_SWEEP_TRACING
+    if (const char *e = getenv("SGBM_SWEEP_TRACE")) { strncpy(k.tracePath, e, sizeof(k.tracePath) - 1); }
+#endif
+}
+
 static int check_device(const sgbm_handle *h)
 {
     int dev = -1;
@@ -133,6 +183,7 @@ static int check_device(const sgbm_handle *h)
 // Effective parameters and geometry (A.0) + lane mapping.  Returns 0 or an error code.
 static int make_geo(const sgbm_params &p, int W, int H, int cn, Geo &g)
 {
+    const SgbmKnobs &kn = sgbm_knobs();
     memset(&g, 0, sizeof(g));
     if (W <= 0 || H <= 0) return sgbm_fail(SGBM_E_INVALID_ARG, "empty image %dx%d", W, H);
     if (cn != 1 && cn != 3) return sgbm_fail(SGBM_E_INVALID_ARG, "channels must be 1 or 3 (got %d)", cn);
@@ -167,8 +218,7 @@ static int make_geo(const sgbm_params &p, int W, int H, int cn, Geo &g)
     // lane mapping: D = 2*nreg*lanesUsed, lpc = pow2 >= lanesUsed (>= 2); maximise lanesUsed/lpc
     static const int prefBig[4] = {16, 12, 8, 4}, prefSmall[4] = {8, 12, 16, 4};
     const int *pref = g.D >= 192 ? prefBig : prefSmall;
-    const char *env = getenv("SGBM_NREG");
-    int forced = env ? atoi(env) : 0;
+    const int forced = kn.nreg;
     double bestEff = -1;
     for (int i = 0; i < 4; i++) {
         int nreg = pref[i];
@@ -255,9 +305,17 @@ extern "C" int sgbm_create(const sgbm_params *p, sgbm_handle **out)
         return sgbm_fail_cuda(e, "querying the device", __FILE__, __LINE__);
     }
     h->device = dev;
-    if (const char *e = getenv("SGBM_SM_LIMIT")) { const int v = atoi(e); if (v >= 1 && v < h->numSMs) h->numSMs = v; }
-    if (const char *e = getenv("SGBM_LANES")) { const int v = atoi(e); h->lanesWanted = v < 1 ? 1 : (v > SGBM_MAX_LANES ? SGBM_MAX_LANES : v); }
-    if (const char *e = getenv("SGBM_BANDS")) { const int v = atoi(e); h->bandsWanted = v < 1 ? 1 : (v > SGBM_MAX_BANDS ? SGBM_MAX_BANDS : v); }
+    read_knobs(h->knobs);
+    h->knobs.device = dev;
+    h->knobs.numSMs = h->numSMs;
+    if ((e = cudaDeviceGetAttribute(&h->knobs.maxSmemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&h->evLast, cudaEventDisableTiming)) != cudaSuccess) {
+        delete h;
+        return sgbm_fail_cuda(e, "setting up the handle", __FILE__, __LINE__);
+    }
+    { const int v = env_int("SGBM_SM_LIMIT", 0); if (v >= 1 && v < h->numSMs) h->numSMs = v; }
+    if (getenv("SGBM_LANES")) { const int v = env_int("SGBM_LANES", 0); h->lanesWanted = v < 1 ? 1 : (v > SGBM_MAX_LANES ? SGBM_MAX_LANES : v); }
+    if (getenv("SGBM_BANDS")) { const int v = env_int("SGBM_BANDS", 0); h->bandsWanted = v < 1 ? 1 : (v > SGBM_MAX_BANDS ? SGBM_MAX_BANDS : v); }
     *out = h;
     return 0;
 }
@@ -277,6 +335,7 @@ extern "C" int sgbm_destroy(sgbm_handle *h)
     }
     if (h->watch) cudaFreeHost(h->watch);
     if (h->evFork) cudaEventDestroy(h->evFork);
+    if (h->evLast) cudaEventDestroy(h->evLast);
     for (int i = 0; i < SGBM_MAX_SLOTS; i++) {
         if (h->devIn[i]) cudaFree(h->devIn[i]);
         if (h->devOut[i]) cudaFree(h->devOut[i]);
@@ -309,15 +368,22 @@ extern "C" int sgbm_get_params(const sgbm_handle *h, sgbm_params *p)
     return 0;
 }
 
-extern "C" int sgbm_workspace_bytes(const sgbm_handle *h, int W, int H, int channels, size_t *out)
+static int lanes_for(const sgbm_handle *h, const Geo &g, int batch, int *sweepSMs);
+
+// Device workspace the handle allocates for frames of this size: one workspace per frame it keeps in
+// flight (batch > 1: up to SGBM_MAX_LANES, see lanes_for).  Needs the handle's device to be current.
+extern "C" int sgbm_workspace_bytes(const sgbm_handle *h, int W, int H, int channels, int batch, size_t *out)
 {
     if (!h || !out) return sgbm_fail(SGBM_E_INVALID_ARG, "null argument");
+    if (batch <= 0) return sgbm_fail(SGBM_E_INVALID_ARG, "batch must be >= 1");
+    KnobScope ks(h);
     Geo g;
     int rc = make_geo(h->p, W, H, channels, g);
     if (rc) return rc;
     WsLayout L;
     ws_layout(g, h->p, h->numSMs, h->keep, L);
-    *out = L.total;
+    int sweepSMs = 0;
+    *out = L.total * (size_t)lanes_for(h, g, batch, &sweepSMs);
     return 0;
 }
 
@@ -425,10 +491,8 @@ static int compute_frame(sgbm_handle *h, int lane, int sweepSMs, const Geo &g, c
     if ((rc = prof_mark(h, ST_START, st))) return rc;
     // second-generation prefilter + cost kernels (sgbm_cost2.cu); the first generation stays as the
     // fallback for geometries the new kernel does not hold (rc == 1) and for A/B runs (SGBM_COST2=0)
-    bool cost2 = true, cost3 = true;
+    bool cost2 = h->knobs.cost2 != 0, cost3 = h->knobs.cost3 != 0;
     int bands = 1, bandRows = g.H;
-    if (const char *e = getenv("SGBM_COST2")) cost2 = atoi(e) != 0;
-    if (const char *e = getenv("SGBM_COST3")) cost3 = atoi(e) != 0;
     if (!cost2) cost3 = false;
     if (cost3) {
         rc = sgbm_cost3_supported(g);
@@ -511,7 +575,7 @@ static int compute_frame(sgbm_handle *h, int lane, int sweepSMs, const Geo &g, c
     a.ss = ss; a.ov = ov;
     a.watchDev = h->watchDev[lane]; a.watchHost = h->watch + 8 * lane;
     a.rowState = (uint16_t *)(base + L.rowState);
-    a.dbgNoSync = getenv("SGBM_DBG_NOSYNC") ? 1 : 0;
+    a.dbgNoSync = SGBM_DBG_HOOK(h->knobs.dbgNoSync);
     a.sdbg = h->keep ? (uint16_t *)(base + L.sdbg) : nullptr;
     switch (p.mode) {
     case SGBM_MODE_SGBM:
@@ -566,10 +630,16 @@ extern "C" int sgbm_compute(sgbm_handle *h, const uint8_t *left, const uint8_t *
     if (int rcDev = check_device(h)) return rcDev;
     if (pitch_bytes < (ptrdiff_t)W * channels || out_pitch_bytes < (ptrdiff_t)W * 2 || (out_pitch_bytes & 1))
         return sgbm_fail(SGBM_E_INVALID_ARG, "bad pitch (in %td, out %td) for width %d", pitch_bytes, out_pitch_bytes, W);
+    // One call at a time per handle; on the device this call is ordered behind the handle's previous call
+    // whatever stream that ran on (the workspace, the lane / band streams and the watchdog words are the
+    // handle's, not the stream's).
+    std::lock_guard<std::mutex> lock(h->mu);
+    KnobScope ks(h);
     Geo g;
     int rc = make_geo(h->p, W, H, channels, g);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (h->evLastValid) SGBM_CUDA_CHECK(cudaStreamWaitEvent(st, h->evLast, 0));
     WsLayout L;
     ws_layout(g, h->p, h->numSMs, h->keep, L);
     int sweepSMs = h->numSMs;
@@ -595,6 +665,8 @@ extern "C" int sgbm_compute(sgbm_handle *h, const uint8_t *left, const uint8_t *
         SGBM_CUDA_CHECK(cudaEventRecord(h->evJoin[i], h->laneStream[i]));
         SGBM_CUDA_CHECK(cudaStreamWaitEvent(st, h->evJoin[i], 0));
     }
+    SGBM_CUDA_CHECK(cudaEventRecord(h->evLast, st));
+    h->evLastValid = true;
     return rc;
 }
 
@@ -638,6 +710,8 @@ static int compute_host_impl(sgbm_handle *h, const uint8_t *left, const uint8_t 
     if (int rcDev = check_device(h)) return rcDev;
     if (pitch_bytes < (ptrdiff_t)W * channels || out_pitch_bytes < (ptrdiff_t)W * 2)
         return sgbm_fail(SGBM_E_INVALID_ARG, "bad pitch");
+    std::lock_guard<std::mutex> lock(h->mu);
+    KnobScope ks(h);
     Geo g;
     int rc = make_geo(h->p, W, H, channels, g);
     if (rc) return rc;
@@ -652,6 +726,7 @@ static int compute_host_impl(sgbm_handle *h, const uint8_t *left, const uint8_t 
         }
     }
     cudaStream_t st = h->ownStream;
+    if (h->evLastValid) SGBM_CUDA_CHECK(cudaEventSynchronize(h->evLast));         // a device-pointer call still in flight
     const size_t rowIn = (size_t)W * channels, frameIn = rowIn * H, frameOut = (size_t)W * H * 2;
     WsLayout L;
     ws_layout(g, h->p, h->numSMs, h->keep, L);
@@ -759,6 +834,20 @@ extern "C" int sgbm_reproject_i16(const int16_t *disp, const double *Q, int W, i
 {
     if (!disp || !Q || !xyz || W <= 0 || H <= 0) return sgbm_fail(SGBM_E_INVALID_ARG, "bad argument");
     return sgbm_launch_reproject(disp, 0, Q, W, H, xyz, valid_or_null, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int sgbm_reproject_ex(const void *disp, int disp_depth, const double *Q, int W, int H, int handle_missing_values,
+                                 int ddepth, void *out, void *scratch16, void *cuda_stream)
+{
+    if (!disp || !Q || !out || W <= 0 || H <= 0) return sgbm_fail(SGBM_E_INVALID_ARG, "bad argument");
+    if (disp_depth != 0 && disp_depth != 3 && disp_depth != 4 && disp_depth != 5)
+        return sgbm_fail(SGBM_E_INVALID_ARG, "disparity must be uint8, int16, int32 or float32 (cv2: stereo_geom.cpp:17)");
+    if (ddepth == -1) ddepth = 5;
+    if (ddepth != 3 && ddepth != 4 && ddepth != 5)
+        return sgbm_fail(SGBM_E_INVALID_ARG, "ddepth must be -1, CV_16S, CV_32S or CV_32F");
+    if (handle_missing_values && !scratch16) return sgbm_fail(SGBM_E_INVALID_ARG, "handleMissingValues needs 16 bytes of device scratch");
+    return sgbm_launch_reproject_ex(disp, disp_depth, Q, W, H, handle_missing_values ? 1 : 0, ddepth, out, scratch16,
+                                    (cudaStream_t)cuda_stream);
 }
 
 extern "C" int sgbm_reproject_compact_scratch_bytes(int W, int H, size_t *out)

@@ -14,6 +14,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 
 #define SGBM_MAX_S 0x7FFF7FFFu      // packed saturation value 32767 (A.4)
 #define SGBM_INF2  0xFFFFFFFFu      // packed +inf for out-of-range disparity neighbours
@@ -90,17 +91,56 @@ __device__ __forceinline__ void store_vec(const uint32_t (&v)[NREG], uint16_t *c
 }
 
 
-// Host: true the first time it is called with this mask on the current device (cudaFuncSetAttribute is
-// per device; a process may hold handles on several).
-static inline bool sgbm_first_use_on_device(unsigned long long &mask)
-{
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return true;
-    const unsigned long long bit = 1ull << (dev & 63);
-    if (mask & bit) return false;
-    mask |= bit;
-    return true;
-}
+// ---- host-side knobs and per-device set-up --------------------------------------------------------
+// Tuning / test knobs.  They are read from the environment ONCE, in sgbm_create, and live in the handle;
+// the launchers see the knobs of the handle whose call is running on this thread (sgbm_knobs()).  Nothing
+// reads the environment per frame.  The two hooks that make results INVALID on purpose (dbgNoSync,
+// dbgStall) exist only in builds with -DSGBM_DEBUG_HOOKS (libsgbm_b200_dbg.so, used by one test).
+struct SgbmKnobs {
+    int nreg = 0;                        // SGBM_NREG: force the registers-per-lane of the lane mapping (0 = auto)
+    int vr = 0;                          // SGBM_VR: rows per super-step of the sweeps (0 = default)
+    int sweepK = 0, sweepNSC = 0, sweepNSI = 0, sweepNWW = 0;   // SGBM_SWEEP_K / _NSC / _NSI / _NWW ring depths, WTA warps
+    int sweepW = 1;                      // SGBM_SWEEP_W=0: winner-take-all on role C instead of the W role
+    int sweep = 1;                       // SGBM_SWEEP=0: lock-step k_vertical instead of the role-specialised sweep
+    int rowstep = 0;                     // SGBM_ROWSTEP=1: row-at-a-time fallback
+    int cost2 = 1, cost3 = 1;            // SGBM_COST2=0 / SGBM_COST3=0: older cost-kernel generations
+    int cost3NXG = 0, cost3RB = 0;       // SGBM_COST3_NXG / _RB
+    int nstg = 0;                        // SGBM_NSTG: staging depth of k_vertical
+    int sweepSat = 0;                    // SGBM_SWEEP_SAT=1: force the saturating S accumulation
+    int smallD = 1;                      // SGBM_SMALLD=0: do not use the whole-vector-per-lane kernels for small numDisparities
+    int verbose = 0;                     // SGBM_VERBOSE: print launch geometries to stderr
+    int dbgNoSync = 0, dbgStall = 0;     // SGBM_DBG_NOSYNC / SGBM_DBG_STALL (debug-hook builds only)
+    char tracePath[256] = "";            // SGBM_SWEEP_TRACE (tracing builds only)
+    // facts about the device the handle lives on
+    int device = 0, numSMs = 0, maxSmemOptin = 0;
+};
+const SgbmKnobs &sgbm_knobs();           // sgbm_api.cu: knobs of the call running on this thread
+
+#ifdef SGBM_DEBUG_HOOKS
+#define SGBM_DBG_HOOK(x) (x)
+#else
+#define SGBM_DBG_HOOK(x) 0
+#endif
+
+// Per-device one-time set-up of a kernel (cudaFuncSetAttribute is per device; one process may hold handles
+// on several devices and drive them from several threads).  Usage:
+//   static unsigned long long done = 0;
+//   { SgbmDeviceOnce once(done); if (once.first) { SGBM_CUDA_CHECK(cudaFuncSetAttribute(...)); once.done(); } }
+// The lock is held until the set-up has finished, so no thread launches before the attribute is set.
+std::mutex &sgbm_setup_mutex();          // sgbm_api.cu
+struct SgbmDeviceOnce {
+    std::unique_lock<std::mutex> lk;
+    unsigned long long &mask;
+    unsigned long long bit = 1;
+    bool first = true;
+    explicit SgbmDeviceOnce(unsigned long long &m) : lk(sgbm_setup_mutex()), mask(m)
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) bit = 1ull << (dev & 63);
+        first = !(mask & bit);
+    }
+    void done() { mask |= bit; }
+};
 
 // ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers ------------------------------
 // One elected lane arms an mbarrier with the byte count and issues global->shared bulk copies; the

@@ -226,8 +226,12 @@ template <int NREG, int XPT>
 static int launch_cost_t(CostArgs &a, int threads, size_t smem, dim3 grid, int maxSmem, cudaStream_t st)
 {
     static unsigned long long attrDone = 0;   // one bit per device: function attributes are per device
-    if (sgbm_first_use_on_device(attrDone)) {
-        SGBM_CUDA_CHECK(cudaFuncSetAttribute(k_cost<NREG, XPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+    {
+        SgbmDeviceOnce once(attrDone);
+        if (once.first) {
+            SGBM_CUDA_CHECK(cudaFuncSetAttribute(k_cost<NREG, XPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+            once.done();
+        }
     }
     k_cost<NREG, XPT><<<grid, threads, smem, st>>>(a);
     sgbm_count_launch(1);
@@ -240,12 +244,7 @@ int sgbm_launch_cost(const Geo &g, const uint8_t *planes, uint16_t *out, int y0,
                      int zeroTail, cudaStream_t st)
 {
     if (nrows <= 0) return 0;
-    static int maxSmem = -1;
-    if (maxSmem < 0) {
-        int dev = 0;
-        SGBM_CUDA_CHECK(cudaGetDevice(&dev));
-        SGBM_CUDA_CHECK(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    }
+    const int maxSmem = sgbm_knobs().maxSmemOptin;
     const int Dw = g.Dp / 2;
     if (Dw > 512) return sgbm_fail(-3, "cost kernel: numDisparities too large (Dp=%d)", g.Dp);
     // threads = Dw * NXG (<= 512, >= 128 when possible); TX = NXG * XPT

@@ -385,8 +385,12 @@ template <int NREG, int LPC, int XPT>
 static int launch_cost2_t(Cost2Args &a, int threads, size_t smem, dim3 grid, int maxSmem, cudaStream_t st)
 {
     static unsigned long long attrDone = 0;   // one bit per device: function attributes are per device
-    if (sgbm_first_use_on_device(attrDone)) {
-        SGBM_CUDA_CHECK(cudaFuncSetAttribute(k_cost2<NREG, LPC, XPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+    {
+        SgbmDeviceOnce once(attrDone);
+        if (once.first) {
+            SGBM_CUDA_CHECK(cudaFuncSetAttribute(k_cost2<NREG, LPC, XPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+            once.done();
+        }
     }
     k_cost2<NREG, LPC, XPT><<<grid, threads, smem, st>>>(a);
     sgbm_count_launch(1);
@@ -400,12 +404,7 @@ int sgbm_launch_cost2(const Geo &g, const uint8_t *planes, uint16_t *out, int y0
                       cudaStream_t st)
 {
     if (nrows <= 0) return 0;
-    static int maxSmem = -1;
-    if (maxSmem < 0) {
-        int dev = 0;
-        SGBM_CUDA_CHECK(cudaGetDevice(&dev));
-        SGBM_CUDA_CHECK(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    }
+    const int maxSmem = sgbm_knobs().maxSmemOptin;
     const int Dw = g.Dp / 2;
     if (Dw > 512) return 1;
     if (32 % g.nreg != 0 && ((g.nreg / 4) % 2 == 0)) return 1;      // padded natural order needs NREG | 32 (12: no padding)

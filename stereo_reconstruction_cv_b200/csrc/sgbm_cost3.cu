@@ -321,7 +321,7 @@ static bool cost3_plan(const Geo &g, int maxSmem, Cost3Args &a, int *threadsOut,
     if (cap < 1) cap = 1;
     const int need = (g.W1 + COST3_XPT - 1) / COST3_XPT;
     if (cap > need) cap = need;
-    if (const char *e = getenv("SGBM_COST3_NXG")) { const int v = atoi(e); if (v >= 1 && v < cap) cap = v; }
+    if (const int v = sgbm_knobs().cost3NXG) { if (v >= 1 && v < cap) cap = v; }
     for (int minStages = 3; minStages >= 2; minStages--)
         for (int NXG = cap; NXG >= 1; NXG--) {
             a.NXG = NXG;
@@ -338,13 +338,7 @@ static bool cost3_plan(const Geo &g, int maxSmem, Cost3Args &a, int *threadsOut,
 
 static int cost3_max_smem(int *out)
 {
-    static int maxSmem = -1;
-    if (maxSmem < 0) {
-        int dev = 0;
-        SGBM_CUDA_CHECK(cudaGetDevice(&dev));
-        SGBM_CUDA_CHECK(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    }
-    *out = maxSmem;
+    *out = sgbm_knobs().maxSmemOptin;
     return 0;
 }
 
@@ -363,8 +357,12 @@ template <int R, int PAR, int DWT, int NTT>
 static int launch_cost3_t(Cost3Args &a, int threads, size_t smem, dim3 grid, int maxSmem, cudaStream_t st)
 {
     static unsigned long long attrDone = 0;   // one bit per device: function attributes are per device
-    if (sgbm_first_use_on_device(attrDone)) {
-        SGBM_CUDA_CHECK(cudaFuncSetAttribute(k_cost3<R, PAR, DWT, NTT>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+    {
+        SgbmDeviceOnce once(attrDone);
+        if (once.first) {
+            SGBM_CUDA_CHECK(cudaFuncSetAttribute(k_cost3<R, PAR, DWT, NTT>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+            once.done();
+        }
     }
     k_cost3<R, PAR, DWT, NTT><<<grid, threads, smem, st>>>(a);
     sgbm_count_launch(1);
@@ -392,12 +390,7 @@ int sgbm_launch_cost3(const Geo &g, const uint8_t *planes, uint16_t *out, int y0
     // number of waves (one CTA per SM) times that cost is smallest
     const int TX = a.NXG * COST3_XPT;
     const int tilesX = (g.W1 + TX - 1) / TX;
-    static int numSMs = 0;
-    if (!numSMs) {
-        int dev = 0;
-        SGBM_CUDA_CHECK(cudaGetDevice(&dev));
-        SGBM_CUDA_CHECK(cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int numSMs = sgbm_knobs().numSMs;
     {
         long long best = -1;
         for (int rb = 16; rb <= 192; rb++) {
@@ -409,11 +402,11 @@ int sgbm_launch_cost3(const Geo &g, const uint8_t *planes, uint16_t *out, int y0
             if (best < 0 || cost < best) { best = cost; a.RB = rbe; }
         }
     }
-    if (const char *e = getenv("SGBM_COST3_RB")) { const int v = atoi(e); if (v >= 1) a.RB = v; }
+    if (const int v = sgbm_knobs().cost3RB) { if (v >= 1) a.RB = v; }
     if (a.RB > nrows) a.RB = nrows;
     dim3 grid(tilesX, (nrows + a.RB - 1) / a.RB);
     const int par = (g.minX1 - R - g.minD - 1) & 1;       // parity of the first walked column's right position
-    if (getenv("SGBM_COST3_VERBOSE"))
+    if (sgbm_knobs().verbose)
         fprintf(stderr, "cost3: R=%d Dw=%d NXG=%d threads=%d smem=%zu nstg=%d RB=%d grid=%dx%d par=%d eshift=%d\n", R, Dw, a.NXG,
                 threads, smem, a.nstg, a.RB, grid.x, grid.y, par, a.eshift);
     // blockSize 3 / 5 / 7 at the lane mappings of numDisparities = 128 / 192 / 256: compile-time strides

@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(NDIR == 1 ? 128 : VertMaxThreads<NREG>::value,
         const int pp = (t + 1) & 1, pc = t & 1;          // previous / current row parity
         // ---- super-step start: receive the neighbours' published columns ------------------------
         if (NDIR == 3 && k == 0 && t > 0) {
-            if (!a.dbgNoSync) {
+            if (!SGBM_DBG_HOOK(a.dbgNoSync)) {
                 if (rcvL && lg == 0) while (ld_acquire(a.flagA + strip - 1) < (unsigned)sidx) { }
                 if (rcvR && lg == 0) while (ld_acquire(a.flagA + strip + 1) < (unsigned)sidx) { }
             }
@@ -519,8 +519,12 @@ static int launch_horizontal_t(const Geo &g, const uint16_t *C, uint16_t *LhA, u
     constexpr int GPW = 32 / LPC, NW = HZ_THREADS / 32, HZ_K = HzK<NREG, LPC>::value;
     const size_t smem = (size_t)NW * HZ_NS * GPW * HZ_K * g.Dp * 2 + (size_t)NW * HZ_NS * 8;
     static unsigned long long attrDone = 0;   // one bit per device: function attributes are per device
-    if (sgbm_first_use_on_device(attrDone)) {
-        SGBM_CUDA_CHECK(cudaFuncSetAttribute(k_horizontal<NREG, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    {
+        SgbmDeviceOnce once(attrDone);
+        if (once.first) {
+            SGBM_CUDA_CHECK(cudaFuncSetAttribute(k_horizontal<NREG, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            once.done();
+        }
     }
     const int rowsPerCta = NW * GPW;
     dim3 grid((nrows + rowsPerCta - 1) / rowsPerCta, 2);
@@ -537,16 +541,17 @@ static int launch_vertical_t(VertArgs &a, int numSMs, cudaStream_t st)
 {
     const Geo &g = a.g;
     auto kern = k_vertical<NREG, LPC, NDIR>;
+    const SgbmKnobs &kn = sgbm_knobs();
+    const int maxSmem = kn.maxSmemOptin;
     static unsigned long long attrDone = 0;   // one bit per device: function attributes are per device
-    static int maxSmem = 0;
-    if (sgbm_first_use_on_device(attrDone)) {
-        int dev = 0;
-        SGBM_CUDA_CHECK(cudaGetDevice(&dev));
-        SGBM_CUDA_CHECK(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        SGBM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+    {
+        SgbmDeviceOnce once(attrDone);
+        if (once.first) {
+            SGBM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+            once.done();
+        }
     }
-    int nstgWant = 3;
-    if (const char *e = getenv("SGBM_NSTG")) nstgWant = atoi(e) >= 2 && atoi(e) <= 4 ? atoi(e) : 3;
+    const int nstgWant = kn.nstg >= 2 && kn.nstg <= 4 ? kn.nstg : 3;
     if (NDIR == 1) {
         // independent columns: ordinary grid, 128 threads per CTA
         const int threads = 128;
@@ -565,7 +570,7 @@ static int launch_vertical_t(VertArgs &a, int numSMs, cudaStream_t st)
     // R rows per super-step (env SGBM_VR overrides); every strip must own >= R columns.
     const int maxThreads = VertMaxThreads<NREG>::value;
     int R = 9;
-    if (const char *e = getenv("SGBM_VR")) R = atoi(e) > 0 ? atoi(e) : 1;
+    if (kn.vr > 0) R = kn.vr;
     if (R > 16) R = 16;
     int nstrips = numSMs, SWmax = 1, threads = 32, nstg = 2;
     size_t smem = 0;
@@ -627,9 +632,8 @@ int sgbm_launch_vertical(VertArgs &a, int ndir, int numSMs, cudaStream_t st)
     if (ndir == 3) {
         // role-specialised sweep (sgbm_sweep.cu); the lock-step kernel below remains as the fallback for
         // geometries it cannot hold (and for A/B runs with SGBM_SWEEP=0)
-        const char *e = getenv("SGBM_SWEEP");
-        if (const char *rs = getenv("SGBM_ROWSTEP")) { if (atoi(rs) != 0) return sgbm_launch_rowstep(a, st); }
-        if (!e || atoi(e) != 0) {
+        if (sgbm_knobs().rowstep) return sgbm_launch_rowstep(a, st);
+        if (sgbm_knobs().sweep) {
             const int rc = sgbm_launch_sweep(a, numSMs, st);
             if (rc <= 0) return rc;
         }

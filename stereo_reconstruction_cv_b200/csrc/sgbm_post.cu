@@ -228,6 +228,57 @@ __global__ void k_reproject(const T *disp, QMat Q, int W, int H, float *xyz, uin
     if (valid) valid[i] = (isfinite(X) && d > 0.0) ? 1 : 0;
 }
 
+// ---- reprojectImageTo3D with handleMissingValues / ddepth (A.8) ---------------------------------------
+// cv2: Z = 10000 where |d - min(disp)| <= FLT_EPSILON (d and the minimum as doubles); ddepth CV_16S / CV_32S
+// round the float32 result half-to-even like cvRound (cvtss2si: anything that does not fit an int32,
+// NaN and +-inf included, becomes INT_MIN) and CV_16S then saturates to [-32768, 32767].
+// The minimum goes through an order-preserving key so that one atomicMin does floats of either sign.
+__device__ __forceinline__ unsigned int order_key_f32(float f)
+{
+    const unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float order_key_inv_f32(unsigned int k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+template <typename T>
+__global__ void k_disp_min(const T *disp, size_t n, unsigned int *keyOut)
+{
+    unsigned int k = 0xFFFFFFFFu;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float f = (float)disp[i];                 // cv2 converts integer disparities to float32 first
+        if (!(f != f)) k = min(k, order_key_f32(f));    // minMaxIdx ignores nothing, but NaN never compares smaller
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) k = min(k, __shfl_xor_sync(0xFFFFFFFFu, k, o));
+    if ((threadIdx.x & 31) == 0) atomicMin(keyOut, k);
+}
+__device__ __forceinline__ int cv_round_f32(float v)
+{
+    const float r = rintf(v);                           // half to even, like cvtss2si under the default MXCSR
+    return (r >= -2147483648.0f && r < 2147483648.0f) ? (int)r : (int)0x80000000;
+}
+// DD: 5 = float32, 3 = int16, 4 = int32 (cv2 depth codes)
+template <typename T, int DD>
+__global__ void k_reproject_ex(const T *disp, QMat Q, int W, int H, void *out, const unsigned int *minKey)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= W) return;
+    size_t i = (size_t)y * W + x;
+    const double d = (double)(float)disp[i];
+    float v[3];
+    reproject_px(Q, x, y, d, v[0], v[1], v[2]);
+    if (minKey && fabs(d - (double)order_key_inv_f32(*minKey)) <= 1.1920928955078125e-07) v[2] = 10000.0f;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        if (DD == 5) ((float *)out)[3 * i + c] = v[c];
+        else if (DD == 4) ((int *)out)[3 * i + c] = cv_round_f32(v[c]);
+        else { const int r = cv_round_f32(v[c]); ((int16_t *)out)[3 * i + c] = (int16_t)max(-32768, min(32767, r)); }
+    }
+}
+
 // ---- fused tail: /16, mask, reproject, validity, ordered compaction ---------------------------------
 #define CP_THREADS 256
 #define CP_ITEMS 4                      // pixels per thread, CP_THREADS*CP_ITEMS pixels per block
@@ -398,6 +449,43 @@ int sgbm_launch_reproject(const void *disp, int isFloat, const double *Qh, int W
     sgbm_count_launch(1);
     SGBM_CUDA_CHECK(cudaGetLastError());
     return 0;
+}
+
+template <typename T>
+static int launch_reproject_ex_t(const T *disp, const QMat &Q, int W, int H, int handleMissing, int ddepth, void *out,
+                                 unsigned int *scratch, cudaStream_t st)
+{
+    dim3 grid((W + 255) / 256, H);
+    unsigned int *key = handleMissing ? scratch : nullptr;
+    if (key) {
+        SGBM_CUDA_CHECK(cudaMemsetAsync(key, 0xFF, 4, st));
+        const size_t n = (size_t)W * H;
+        const unsigned blocks = (unsigned)((n + 256 * 8 - 1) / (256 * 8));
+        k_disp_min<T><<<blocks < 4096u ? blocks : 4096u, 256, 0, st>>>(disp, n, key);
+        sgbm_count_launch(1);
+    }
+    if (ddepth == 3) k_reproject_ex<T, 3><<<grid, 256, 0, st>>>(disp, Q, W, H, out, key);
+    else if (ddepth == 4) k_reproject_ex<T, 4><<<grid, 256, 0, st>>>(disp, Q, W, H, out, key);
+    else k_reproject_ex<T, 5><<<grid, 256, 0, st>>>(disp, Q, W, H, out, key);
+    sgbm_count_launch(1);
+    SGBM_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// dispDepth / ddepth: cv2 depth codes (0 = uint8, 3 = int16, 4 = int32, 5 = float32)
+int sgbm_launch_reproject_ex(const void *disp, int dispDepth, const double *Qh, int W, int H, int handleMissing, int ddepth,
+                             void *out, void *scratch, cudaStream_t st)
+{
+    QMat Q;
+    for (int i = 0; i < 16; i++) Q.q[i] = Qh[i];
+    unsigned int *sc = (unsigned int *)scratch;
+    switch (dispDepth) {
+    case 0: return launch_reproject_ex_t((const uint8_t *)disp, Q, W, H, handleMissing, ddepth, out, sc, st);
+    case 3: return launch_reproject_ex_t((const int16_t *)disp, Q, W, H, handleMissing, ddepth, out, sc, st);
+    case 4: return launch_reproject_ex_t((const int *)disp, Q, W, H, handleMissing, ddepth, out, sc, st);
+    case 5: return launch_reproject_ex_t((const float *)disp, Q, W, H, handleMissing, ddepth, out, sc, st);
+    }
+    return sgbm_fail(-1, "unsupported disparity depth %d", dispDepth);
 }
 
 size_t sgbm_compact_scratch_bytes(int W, int H)

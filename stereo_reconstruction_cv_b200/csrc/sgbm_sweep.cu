@@ -260,7 +260,7 @@ __device__ __forceinline__ void sweep_role_v(const SweepArgs &a, const SweepSmem
         if (own) store_vec<NREG, LPC>(S, s.P + pOff, lg);
         __syncwarp();
         if (lane == 0) {
-            if (!(a.dbgStall && t == 5 && blockIdx.x == 0)) mbar_arrive(s.fullV[k]);
+            if (!(SGBM_DBG_HOOK(a.dbgStall) && t == 5 && blockIdx.x == 0)) mbar_arrive(s.fullV[k]);
             mbar_arrive(s.emptyC[sc]);
             mbar_arrive(s.emptyI[si]);
         }
@@ -409,7 +409,7 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
             const bool restart = exists && nm == b;
             if (restart) p = i;
             if (hasNbr) {
-                if (restart && lg == 0 && !a.dbgNoSync) {
+                if (restart && lg == 0 && !SGBM_DBG_HOOK(a.dbgNoSync)) {
                     const long long t0 = clock64();
                     const unsigned int *fl = flagIn + ((n - 1) % HS) * R;
                     while (ld_acquire_u32(fl) < (unsigned)n) {
@@ -711,13 +711,14 @@ static bool sweep_plan(const Geo &g, int numSMs, bool wrole, bool wta, int maxTh
     // Rows per super-step (every value is covered by tests/test_gpu_parity.py::test_sweep_rows_per_superstep
     // and a repeatability run; 8 is the fastest at every size measured).
     const int Rmin = 1;
+    const SgbmKnobs &kn = sgbm_knobs();
     int R = 8;
-    if (const char *e = getenv("SGBM_VR")) R = atoi(e) >= Rmin ? atoi(e) : Rmin;
+    if (kn.vr > 0) R = kn.vr >= Rmin ? kn.vr : Rmin;
     if (R > 16) R = 16;
     int Kwant = 5, NSCwant = 5, NSIwant = 3;
-    if (const char *e = getenv("SGBM_SWEEP_K")) Kwant = atoi(e) >= 1 && atoi(e) <= 8 ? atoi(e) : Kwant;
-    if (const char *e = getenv("SGBM_SWEEP_NSC")) NSCwant = atoi(e) >= 2 && atoi(e) <= 8 ? atoi(e) : NSCwant;
-    if (const char *e = getenv("SGBM_SWEEP_NSI")) NSIwant = atoi(e) >= 2 && atoi(e) <= 8 ? atoi(e) : NSIwant;
+    if (kn.sweepK >= 1 && kn.sweepK <= 8) Kwant = kn.sweepK;
+    if (kn.sweepNSC >= 2 && kn.sweepNSC <= 8) NSCwant = kn.sweepNSC;
+    if (kn.sweepNSI >= 2 && kn.sweepNSI <= 8) NSIwant = kn.sweepNSI;
     for (; R >= Rmin; R--) {
         int nstrips = numSMs;
         const int minCols = R > 2 ? R : 2;                // every strip owns >= R (and >= 2) columns
@@ -733,7 +734,7 @@ static bool sweep_plan(const Geo &g, int numSMs, bool wrole, bool wta, int maxTh
         if (wrole) {
             a.aA = (a.nwA + 3) & ~3; a.aV = (a.nwV + 3) & ~3;
             a.nwW = a.nwV < 7 ? a.nwV : 7;                // 8 warps: WTA warps, the producer, idle
-            if (const char *e = getenv("SGBM_SWEEP_NWW")) { const int v = atoi(e); if (v >= 1 && v <= 7) a.nwW = v; }
+            if (kn.sweepNWW >= 1 && kn.sweepNWW <= 7) a.nwW = kn.sweepNWW;
             a.wPass = (SWmax + a.nwW * GPW - 1) / (a.nwW * GPW);
             threads = (a.aV + 2 * a.aA + 8) * 32;
         } else {
@@ -759,9 +760,7 @@ static bool sweep_plan(const Geo &g, int numSMs, bool wrole, bool wta, int maxTh
 // batch entry points ask before they run two frames side by side, each on half of the GPU.
 bool sgbm_sweep_fits(const Geo &g, int numSMs, int mode)
 {
-    int dev = 0, maxSmem = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return false;
-    if (cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return false;
+    const int maxSmem = sgbm_knobs().maxSmemOptin;
     SweepArgs a;
     int threads = 0;
     size_t smem = 0;
@@ -785,20 +784,22 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
     constexpr int GPW = 32 / LPC;
     const Geo &g = va.g;
     auto kern = k_sweep<NREG, LPC, SAT, WROLE>;
+    const SgbmKnobs &kn = sgbm_knobs();
+    const int maxSmem = kn.maxSmemOptin;
     static unsigned long long attrDone = 0;   // one bit per device: function attributes are per device
-    static int maxSmem = 0;
-    if (sgbm_first_use_on_device(attrDone)) {
-        int dev = 0;
-        SGBM_CUDA_CHECK(cudaGetDevice(&dev));
-        SGBM_CUDA_CHECK(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        SGBM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+    {
+        SgbmDeviceOnce once(attrDone);
+        if (once.first) {
+            SGBM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+            once.done();
+        }
     }
     SweepArgs a;
     memset(&a, 0, sizeof(a));
     a.g = g; a.C = va.C; a.inA = va.inA; a.inB = va.inB; a.sout = va.sout; a.sdbg = va.sdbg; a.raw = va.raw;
     a.d2key = va.d2key; a.backward = va.backward; a.haloA = va.haloA; a.haloC = va.haloC; a.flagA = va.flagA;
     a.flagC = va.flagC; a.dbgNoSync = va.dbgNoSync;
-    a.dbgStall = getenv("SGBM_DBG_STALL") ? 1 : 0;
+    a.dbgStall = SGBM_DBG_HOOK(kn.dbgStall);
     a.nAB = va.inB ? 2 : 1;
     a.urMagic = g.UR < 99 ? 0xFFFFFFFFu / (unsigned)(100 - g.UR) + 1u : 0u;
     const bool wta = va.sout == nullptr;
@@ -814,7 +815,7 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
     SGBM_CUDA_CHECK(cudaMemsetAsync(a.flagA, 0, sizeof(unsigned int) * 2 * (size_t)a.nstrips * 64, st));
     a.flagC = a.flagA + (size_t)a.nstrips * 64;
     a.dbg = va.watchDev;                                  // sticky: zeroed with the workspace and after a report
-    const char *tracePath = getenv("SGBM_SWEEP_TRACE");       // debug: dump one strip's time stamps to a file
+    const char *tracePath = kn.tracePath[0] ? kn.tracePath : nullptr;   // debug: dump one strip's time stamps to a file
 #ifndef SGBM_SWEEP_TRACING
     if (tracePath) { fprintf(stderr, "SGBM_SWEEP_TRACE needs a build with make TRACE=1\n"); tracePath = nullptr; }
 #endif
@@ -824,7 +825,7 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
         SGBM_CUDA_CHECK(cudaMemsetAsync(a.trace, 0, traceBytes, st));
         a.traceStrip = a.nstrips / 2;
     }
-    if (getenv("SGBM_SWEEP_VERBOSE"))
+    if (kn.verbose)
         fprintf(stderr, "sweep: wrole=%d wta=%d strips=%d SW=%d R=%d NB=%d nwV=%d nwA=%d nwW=%d wPass=%d K=%d NSC=%d NSI=%d threads=%d smem=%zu\n",
                 (int)WROLE, (int)wta, a.nstrips, a.SW, a.R, a.NB, a.nwV, a.nwA, a.nwW, a.wPass, a.K, a.NSC, a.NSI, threads, smem);
     void *args[] = {&a};
@@ -850,9 +851,7 @@ template <int NREG, int LPC, bool SAT>
 static int launch_sweep_any(const VertArgs &va, int numSMs, cudaStream_t st)
 {
     if (va.sout == nullptr) {
-        bool w = true;
-        if (const char *e = getenv("SGBM_SWEEP_W")) w = atoi(e) != 0;
-        if (w) {
+        if (sgbm_knobs().sweepW) {
             const int rc = launch_sweep_t<NREG, LPC, SAT, true>(va, numSMs, st);
             if (rc <= 0) return rc;
         }
@@ -977,7 +976,7 @@ int sgbm_launch_sweep(const VertArgs &a, int numSMs, cudaStream_t st)
     const long long cMax = (long long)g.cn * (2 * g.r + 1) * (2 * g.r + 1) * pixMax;
     const int npaths = g.mode == 1 ? 8 : 5;
     bool sat = npaths * (cMax + g.P2) > 65535;
-    if (const char *e = getenv("SGBM_SWEEP_SAT")) sat = sat || atoi(e) != 0;
+    sat = sat || sgbm_knobs().sweepSat != 0;
     SWEEP_DISPATCH(4, 2) SWEEP_DISPATCH(4, 4) SWEEP_DISPATCH(4, 8) SWEEP_DISPATCH(4, 16) SWEEP_DISPATCH(4, 32)
     SWEEP_DISPATCH(8, 2) SWEEP_DISPATCH(8, 4) SWEEP_DISPATCH(8, 8) SWEEP_DISPATCH(8, 16) SWEEP_DISPATCH(8, 32)
     SWEEP_DISPATCH(12, 2) SWEEP_DISPATCH(12, 4) SWEEP_DISPATCH(12, 8) SWEEP_DISPATCH(12, 16) SWEEP_DISPATCH(12, 32)

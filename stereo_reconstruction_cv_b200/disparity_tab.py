@@ -114,7 +114,9 @@ def create_disparity_tab(gui, ndisp=16, mindis=0):
 
     def visualize_3d():
         r = rectified()
-        if r is None or not gui.disparity_results:
+        if r is None:
+            return
+        if not gui.disparity_results:
             messagebox.showerror("Error", "Run Disparity first")
             return
         d = gui.disparity_results["Disparity"]

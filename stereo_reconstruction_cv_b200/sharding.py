@@ -30,7 +30,19 @@ def compute_shard(stereo, lefts, rights, world_size=1, rank=0, out=None):
     Returns (start, stop, list_or_tensor_of_disparities).  CUDA tensors stay on the device."""
     start, stop = shard_range(len(lefts), world_size, rank)
     if hasattr(lefts, "is_cuda") and lefts.is_cuda and lefts.dim() >= 3:
+        if start == stop:                                 # more ranks than frames: an empty block, not an error
+            import torch
+            return start, stop, torch.empty((0,) + tuple(lefts.shape[1:3]), dtype=torch.int16, device=lefts.device)
         return start, stop, stereo.compute(lefts[start:stop], rights[start:stop], out)
+    if start == stop:
+        return start, stop, []
+    # host arrays: ONE call of the batched host entry point for the whole block, so that the H2D / D2H
+    # copies of neighbouring frames overlap the kernels and small frames run side by side
+    if hasattr(stereo, "compute_batch"):
+        lb = np.stack([np.asarray(lefts[i]) for i in range(start, stop)])
+        rb = np.stack([np.asarray(rights[i]) for i in range(start, stop)])
+        res = stereo.compute_batch(lb, rb, out)
+        return start, stop, [res[i] for i in range(stop - start)]
     return start, stop, [stereo.compute(lefts[i], rights[i]) for i in range(start, stop)]
 
 

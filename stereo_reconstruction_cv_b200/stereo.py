@@ -90,9 +90,9 @@ class StereoSGBM:
     def getMode(self): return self._p.mode
     def setMode(self, v): self._set("mode", v)
 
-    def workspaceBytes(self, W, H, channels=1):
+    def workspaceBytes(self, W, H, channels=1, batch=1):
         out = C.c_size_t()
-        check(_lib.lib().sgbm_workspace_bytes(self._h, W, H, channels, C.byref(out)))
+        check(_lib.lib().sgbm_workspace_bytes(self._h, W, H, channels, batch, C.byref(out)))
         return out.value
 
     # -- compute -----------------------------------------------------------------------------------
@@ -209,38 +209,48 @@ def _q16(Q):
     return Q
 
 
+CV_8U, CV_16S, CV_32S = 0, 3, 4    # cv2 depth codes (CV_32F = 5 above)
+
+
 def reprojectImageTo3D(disparity, Q, _3dImage=None, handleMissingValues=False, ddepth=-1):
-    """cv2.reprojectImageTo3D (main.ipynb:697): float32 HxWx3.  Integer disparities are used as is."""
-    if handleMissingValues or ddepth not in (-1, 5):
-        raise error(-3, "handleMissingValues / integer ddepth are not implemented")
+    """cv2.reprojectImageTo3D (main.ipynb:697): HxWx3, float32 unless ddepth asks for CV_16S / CV_32S.
+
+    disparity: uint8 / int16 / int32 / float32, HxW; integer disparities are used as they are (no /16).
+    handleMissingValues=True sets Z = 10000 where the disparity equals its minimum (A.8).  numpy in ->
+    numpy out, CUDA tensor in -> CUDA tensor out."""
     Q = _q16(Q)
     L = _lib.lib()
     torch = _torch()
+    if ddepth not in (-1, CV_16S, CV_32S, CV_32F):
+        raise error(-1, "ddepth must be -1, CV_16S, CV_32S or CV_32F (cv2: stereo_geom.cpp)")
     if _is_tensor(disparity):
         d = disparity.contiguous()
         if not d.is_cuda or d.dim() != 2:
             raise error(-1, "disparity tensor must be a 2-D CUDA tensor")
+        depth = {torch.uint8: CV_8U, torch.int16: CV_16S, torch.int32: CV_32S, torch.float32: CV_32F}.get(d.dtype)
+        if depth is None:
+            raise error(-1, "disparity must be uint8, int16, int32 or float32 (cv2: stereo_geom.cpp:17)")
         H, W = d.shape
-        out = torch.empty((H, W, 3), dtype=torch.float32, device=d.device)
+        odt = {CV_16S: torch.int16, CV_32S: torch.int32}.get(ddepth, torch.float32)
+        out = torch.empty((H, W, 3), dtype=odt, device=d.device)
         with torch.cuda.device(d.device):
-            if d.dtype == torch.float32:
-                check(L.sgbm_reproject_f32(d.data_ptr(), Q.ctypes.data, W, H, out.data_ptr(), None, _stream_ptr(d.device)))
-            elif d.dtype == torch.int16:
-                check(L.sgbm_reproject_i16(d.data_ptr(), Q.ctypes.data, W, H, out.data_ptr(), None, _stream_ptr(d.device)))
+            if not handleMissingValues and odt is torch.float32 and depth in (CV_16S, CV_32F):
+                fn = L.sgbm_reproject_f32 if depth == CV_32F else L.sgbm_reproject_i16
+                check(fn(d.data_ptr(), Q.ctypes.data, W, H, out.data_ptr(), None, _stream_ptr(d.device)))
             else:
-                raise error(-1, "disparity must be float32 or int16")
+                scratch = torch.empty((16,), dtype=torch.uint8, device=d.device)
+                check(L.sgbm_reproject_ex(d.data_ptr(), depth, Q.ctypes.data, W, H, 1 if handleMissingValues else 0,
+                                          ddepth, out.data_ptr(), scratch.data_ptr(), _stream_ptr(d.device)))
         return out
     d = np.asarray(disparity)
     if d.ndim != 2:
         raise error(-1, "disparity must be HxW")
     if d.dtype == np.float64:
         raise error(-1, "float64 disparity is not accepted (cv2: stereo_geom.cpp:17)")
-    if d.dtype in (np.uint8, np.int32):
-        d = d.astype(np.float32)          # exact for the value ranges cv2 accepts here
-    if d.dtype not in (np.float32, np.int16):
+    if d.dtype not in (np.float32, np.int16, np.uint8, np.int32):
         raise error(-1, "unsupported disparity dtype %s" % d.dtype)
     dt = torch.from_numpy(np.ascontiguousarray(d)).cuda()
-    res = reprojectImageTo3D(dt, Q).cpu().numpy()
+    res = reprojectImageTo3D(dt, Q, None, handleMissingValues, ddepth).cpu().numpy()
     if _3dImage is not None:
         _3dImage[...] = res
         return _3dImage

@@ -74,13 +74,13 @@ def test_golden_small(sg, golden, golden_meta):
                                   "cfg5_3840x2160_D256_3WAY"])
 def test_golden_digests(sg, golden_meta, name):
     """BASELINE.json configs at full size: SHA-256 of the int16 disparity must equal cv2's."""
-    if name not in golden_meta["digests"]:
-        pytest.skip("digest not generated")
+    assert name in golden_meta["digests"], "digest missing: run tests/golden/make_golden.py --full"
     g = golden_meta["digests"][name]
     l, r, _ = make_pair(g["W"], g["H"], g["D"], seed=g["seed"])
-    if hashlib.sha256(l.tobytes()).hexdigest() != g["left_sha256"] or \
-            hashlib.sha256(r.tobytes()).hexdigest() != g["right_sha256"]:
-        pytest.skip("synthetic generator differs from the one that made the digests")
+    # a different generator (e.g. another cv2 build) must FAIL here, not silently skip the full-size gates
+    assert hashlib.sha256(l.tobytes()).hexdigest() == g["left_sha256"] and \
+        hashlib.sha256(r.tobytes()).hexdigest() == g["right_sha256"], \
+        "the synthetic generator no longer reproduces the inputs the digests were made from: regenerate them"
     st = sg.StereoSGBM_create(minDisparity=0, numDisparities=g["D"], blockSize=5, P1=200, P2=800, disp12MaxDiff=1,
                               preFilterCap=63, uniquenessRatio=10, speckleWindowSize=100, speckleRange=32,
                               mode=g["mode"])
@@ -335,22 +335,46 @@ def test_very_wide_image(sg):
 
 
 def test_handoff_watchdog_reports_and_recovers(sg, monkeypatch):
-    """A sweep hand-off that never happens (test hook: role V of strip 0 withholds one arrival) must not
-    hang the GPU: the kernel drains after ~2 s, the call reports an error, the next call is fine."""
+    """A sweep hand-off that never happens must not hang the GPU: the kernel drains after ~2 s, the call
+    reports an error, the next call is fine.  The fault (role V of strip 0 withholds one arrival) exists only
+    in the debug-hook build libsgbm_b200_dbg.so (-DSGBM_DEBUG_HOOKS), which this test loads by itself through
+    the same C ABI; the product library ignores SGBM_DBG_* (second half of the test)."""
+    import ctypes as C
     import time
+    from stereo_reconstruction_cv_b200 import _lib
     W, H, D = 900, 64, 64
     l, r, _ = make_pair(W, H, D, seed=21)
     p = OracleParams(0, D, 5, 200, 800, 1, 63, 10, 0, 0, 0)
     ref = oracle.compute(p, l, r)
-    st = sg.StereoSGBM_create(**_kw(p))
-    assert _mismatch(st.compute(l, r), ref) == 0
+    dbg = _lib.load(_lib.DEBUG_LIB_PATH)
+
+    def create(L):
+        h = C.c_void_p()
+        prm = _lib.SgbmParams(*[int(getattr(p, n)) for n, _ in _lib.SgbmParams._fields_])
+        assert L.sgbm_create(C.byref(prm), C.byref(h)) == 0, L.sgbm_last_error()
+        return h
+
+    def compute(L, h):
+        out = np.empty((H, W), np.int16)
+        rc = L.sgbm_compute_host(h, l.ctypes.data, r.ctypes.data, W, H, 1, W, 1, out.ctypes.data, 2 * W)
+        return rc, out, L.sgbm_last_error().decode()
+
+    good = create(dbg)                                     # environment read at create: no fault for this handle
+    rc, out, _ = compute(dbg, good)
+    assert rc == 0 and _mismatch(out, ref) == 0
     monkeypatch.setenv("SGBM_DBG_STALL", "1")
+    bad = create(dbg)
     t0 = time.time()
-    with pytest.raises(sg.error, match="hand-off timed out"):
-        st.compute(l, r)
+    rc, _, msg = compute(dbg, bad)
+    assert rc != 0 and "hand-off timed out" in msg, (rc, msg)
     assert time.time() - t0 < 30
+    rc, out, _ = compute(dbg, good)                        # the device and the other handle are fine
+    assert rc == 0 and _mismatch(out, ref) == 0
+    # the product library has no such hook: same environment, correct result
+    assert _mismatch(sg.StereoSGBM_create(**_kw(p)).compute(l, r), ref) == 0
     monkeypatch.delenv("SGBM_DBG_STALL")
-    assert _mismatch(st.compute(l, r), ref) == 0
+    dbg.sgbm_destroy(bad)
+    dbg.sgbm_destroy(good)
 
 
 @pytest.mark.parametrize("mode", [0, 1])

@@ -33,6 +33,43 @@ class _FakeStereo:
         return l.astype(np.int16) - r.astype(np.int16)
 
 
+def test_compute_shard_empty_block_and_batched_host_call():
+    """More ranks than frames: the surplus ranks get an empty block on BOTH paths (they must reach the
+    gather's collectives instead of raising); host blocks go through ONE compute_batch call."""
+    calls = []
+
+    class _Batched(_FakeStereo):
+        def compute_batch(self, lb, rb, out=None):
+            calls.append(lb.shape)
+            return lb.astype(np.int16) - rb.astype(np.int16)
+
+    rng = np.random.default_rng(1)
+    lefts = [rng.integers(0, 255, (4, 6), dtype=np.uint8) for _ in range(3)]
+    rights = [rng.integers(0, 255, (4, 6), dtype=np.uint8) for _ in range(3)]
+    got = {}
+    for rank in range(5):
+        s, e, d = sharding.compute_shard(_Batched(), lefts, rights, 5, rank)
+        assert len(d) == e - s
+        for i in range(s, e):
+            got[i] = d[i - s]
+    assert sorted(got) == [0, 1, 2] and len(calls) == 3 and all(c == (1, 4, 6) for c in calls)
+    for i in range(3):
+        assert np.array_equal(got[i], lefts[i].astype(np.int16) - rights[i].astype(np.int16))
+    s, e, d = sharding.compute_shard(_Batched(), lefts, rights, 1, 0)
+    assert (s, e) == (0, 3) and calls[-1] == (3, 4, 6)
+
+    class _Dev:                                             # shaped like a CUDA tensor batch, never touched when the block is empty
+        is_cuda = True
+        shape = (1, 4, 6)
+        device = "cpu"
+
+        def dim(self): return 3
+        def __len__(self): return 1
+
+    s, e, d = sharding.compute_shard(_FakeStereo(), _Dev(), _Dev(), 4, 0)
+    assert s == e == 0 and tuple(d.shape) == (0, 4, 6) and d.dtype == torch.int16
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
