@@ -152,6 +152,7 @@ static void read_knobs(SgbmKnobs &k)
     k.vr = env_int("SGBM_VR", 0);
     k.sweepK = env_int("SGBM_SWEEP_K", 0); k.sweepNSC = env_int("SGBM_SWEEP_NSC", 0);
     k.sweepNSI = env_int("SGBM_SWEEP_NSI", 0); k.sweepNWW = env_int("SGBM_SWEEP_NWW", 0);
+    k.sweepWRG = env_int("SGBM_SWEEP_WRG", 0);
     k.sweepW = env_int("SGBM_SWEEP_W", 1) != 0;
     k.sweep = env_int("SGBM_SWEEP", 1) != 0;
     k.rowstep = env_int("SGBM_ROWSTEP", 0) != 0;
@@ -161,6 +162,7 @@ static void read_knobs(SgbmKnobs &k)
     k.nstg = env_int("SGBM_NSTG", 0);
     k.sweepSat = env_int("SGBM_SWEEP_SAT", 0) != 0;
     k.smallD = env_int("SGBM_SMALLD", 1) != 0;
+    k.hhSplit = env_int("SGBM_HH_SPLIT", 0) != 0;
     k.verbose = env_int("SGBM_VERBOSE", 0) != 0;
 #ifdef SGBM_DEBUG_HOOKS
     k.dbgNoSync = getenv("SGBM_DBG_NOSYNC") ? 1 : 0;
@@ -583,10 +585,12 @@ static int compute_frame(sgbm_handle *h, int lane, int sweepSMs, const Geo &g, c
         if ((rc = sgbm_launch_vertical(a, 3, sweepSMs, st))) return rc;
         break;
     case SGBM_MODE_HH:
-        a.inA = LhA; a.inB = LhB; a.sout = LhA; a.backward = 0;      // S_fwd overwrites LhA in place
+        // S_fwd overwrites LhA in place.  hhSplit: the forward sweep (HBM-bound) adds only L_hA, the backward
+        // sweep (issue-bound, DRAM mostly idle) reads L_hB beside S_fwd -- same bytes in total, better balance.
+        a.inA = LhA; a.inB = h->knobs.hhSplit ? nullptr : LhB; a.sout = LhA; a.backward = 0;
         if ((rc = sgbm_launch_vertical(a, 3, sweepSMs, st))) return rc;
         if ((rc = prof_mark(h, ST_VERT_FWD, st))) return rc;
-        a.inA = LhA; a.inB = nullptr; a.sout = nullptr; a.backward = 1;
+        a.inA = LhA; a.inB = h->knobs.hhSplit ? LhB : nullptr; a.sout = nullptr; a.backward = 1;
         if ((rc = sgbm_launch_vertical(a, 3, sweepSMs, st))) return rc;
         break;
     case SGBM_MODE_SGBM_3WAY:

@@ -99,7 +99,8 @@ __device__ __forceinline__ void store_vec(const uint32_t (&v)[NREG], uint16_t *c
 struct SgbmKnobs {
     int nreg = 0;                        // SGBM_NREG: force the registers-per-lane of the lane mapping (0 = auto)
     int vr = 0;                          // SGBM_VR: rows per super-step of the sweeps (0 = default)
-    int sweepK = 0, sweepNSC = 0, sweepNSI = 0, sweepNWW = 0;   // SGBM_SWEEP_K / _NSC / _NSI / _NWW ring depths, WTA warps
+    int sweepK = 0, sweepNSC = 0, sweepNSI = 0, sweepNWW = 0;   // SGBM_SWEEP_K / _NSC / _NSI / _NWW ring depths, WTA warps per row
+    int sweepWRG = 0;                    // SGBM_SWEEP_WRG: cap on the row groups of the WTA warps (0 = as many as fit)
     int sweepW = 1;                      // SGBM_SWEEP_W=0: winner-take-all on role C instead of the W role
     int sweep = 1;                       // SGBM_SWEEP=0: lock-step k_vertical instead of the role-specialised sweep
     int rowstep = 0;                     // SGBM_ROWSTEP=1: row-at-a-time fallback
@@ -107,6 +108,7 @@ struct SgbmKnobs {
     int cost3NXG = 0, cost3RB = 0;       // SGBM_COST3_NXG / _RB
     int nstg = 0;                        // SGBM_NSTG: staging depth of k_vertical
     int sweepSat = 0;                    // SGBM_SWEEP_SAT=1: force the saturating S accumulation
+    int hhSplit = 0;                     // SGBM_HH_SPLIT=1: MODE_HH feeds L_hB into the backward sweep instead of the forward one
     int smallD = 1;                      // SGBM_SMALLD=0: do not use the whole-vector-per-lane kernels for small numDisparities
     int verbose = 0;                     // SGBM_VERBOSE: print launch geometries to stderr
     int dbgNoSync = 0, dbgStall = 0;     // SGBM_DBG_NOSYNC / SGBM_DBG_STALL (debug-hook builds only)
@@ -141,6 +143,59 @@ struct SgbmDeviceOnce {
     }
     void done() { mask |= bit; }
 };
+
+// ---- shared memory by 32-bit address --------------------------------------------------------------
+// The sweeps touch several shared-memory rings per row.  With generic pointers the compiler re-derives
+// every address from the kernel arguments, the thread id and the shared window base at each use (the role
+// warps run under a tight register cap and rematerialise instead of keeping the pointer): eight integer
+// instructions in front of every group of LDS / STS.  A 32-bit shared address made opaque once (sm_keep)
+// stays in one register, and [reg + immediate] addressing covers a lane's chunks.
+__device__ __forceinline__ uint32_t sm_keep(uint32_t v)
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+template <int OFF>
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr), "n"(OFF));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.shared.v4.u32 [%0+%1], {%2, %3, %4, %5};" ::"r"(addr), "n"(OFF), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts16(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// One lane's NREG registers of a column whose shared address (lane chunk included) is `addr`.
+template <int NREG, int LPC, int K = 0>
+__device__ __forceinline__ void lds_vec(uint32_t (&v)[NREG], uint32_t addr)
+{
+    if constexpr (K < NREG / 4) {
+        const uint4 q = lds128<16 * LPC * K>(addr);
+        v[4 * K + 0] = q.x; v[4 * K + 1] = q.y; v[4 * K + 2] = q.z; v[4 * K + 3] = q.w;
+        lds_vec<NREG, LPC, K + 1>(v, addr);
+    }
+}
+template <int NREG, int LPC, int K = 0>
+__device__ __forceinline__ void sts_vec(const uint32_t (&v)[NREG], uint32_t addr)
+{
+    if constexpr (K < NREG / 4) {
+        sts128<16 * LPC * K>(addr, v[4 * K + 0], v[4 * K + 1], v[4 * K + 2], v[4 * K + 3]);
+        sts_vec<NREG, LPC, K + 1>(v, addr);
+    }
+}
 
 // ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers ------------------------------
 // One elected lane arms an mbarrier with the byte count and issues global->shared bulk copies; the

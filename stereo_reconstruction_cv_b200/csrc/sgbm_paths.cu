@@ -606,6 +606,9 @@ static int launch_vertical_t(VertArgs &a, int numSMs, cudaStream_t st)
 #define SGBM_DISPATCH(NREG_, LPC_, EXPR)                                              \
     if (g.nreg == NREG_ && g.lpc == LPC_) { constexpr int NREG = NREG_; constexpr int LPC = LPC_; return EXPR; }
 
+#ifdef SGBM_FAST_BUILD      // development builds: only the lane mappings of the BASELINE configurations (make FAST=1)
+#define SGBM_DISPATCH_ALL(EXPR) SGBM_DISPATCH(4, 2, EXPR) SGBM_DISPATCH(8, 8, EXPR) SGBM_DISPATCH(12, 8, EXPR) SGBM_DISPATCH(16, 8, EXPR)
+#else
 #define SGBM_DISPATCH_ALL(EXPR)                                                       \
     SGBM_DISPATCH(4, 2, EXPR) SGBM_DISPATCH(4, 4, EXPR) SGBM_DISPATCH(4, 8, EXPR)     \
     SGBM_DISPATCH(4, 16, EXPR) SGBM_DISPATCH(4, 32, EXPR)                             \
@@ -615,6 +618,7 @@ static int launch_vertical_t(VertArgs &a, int numSMs, cudaStream_t st)
     SGBM_DISPATCH(12, 16, EXPR) SGBM_DISPATCH(12, 32, EXPR)                           \
     SGBM_DISPATCH(16, 2, EXPR) SGBM_DISPATCH(16, 4, EXPR) SGBM_DISPATCH(16, 8, EXPR)  \
     SGBM_DISPATCH(16, 16, EXPR) SGBM_DISPATCH(16, 32, EXPR)
+#endif
 
 int sgbm_launch_horizontal(const Geo &g, const uint16_t *C, uint16_t *LhA, uint16_t *LhB, int y0, int nrows,
                            cudaStream_t st)
@@ -638,10 +642,14 @@ int sgbm_launch_vertical(VertArgs &a, int ndir, int numSMs, cudaStream_t st)
             if (rc <= 0) return rc;
         }
 #define SGBM_TRY3(NREG_, LPC_) if (g.nreg == NREG_ && g.lpc == LPC_) { const int rc = launch_vertical_t<NREG_, LPC_, 3>(a, numSMs, st); if (rc <= 0) return rc; return sgbm_launch_rowstep(a, st); }
+#ifdef SGBM_FAST_BUILD
+        SGBM_TRY3(4, 2) SGBM_TRY3(8, 8) SGBM_TRY3(12, 8) SGBM_TRY3(16, 8)
+#else
         SGBM_TRY3(4, 2) SGBM_TRY3(4, 4) SGBM_TRY3(4, 8) SGBM_TRY3(4, 16) SGBM_TRY3(4, 32)
         SGBM_TRY3(8, 2) SGBM_TRY3(8, 4) SGBM_TRY3(8, 8) SGBM_TRY3(8, 16) SGBM_TRY3(8, 32)
         SGBM_TRY3(12, 2) SGBM_TRY3(12, 4) SGBM_TRY3(12, 8) SGBM_TRY3(12, 16) SGBM_TRY3(12, 32)
         SGBM_TRY3(16, 2) SGBM_TRY3(16, 4) SGBM_TRY3(16, 8) SGBM_TRY3(16, 16) SGBM_TRY3(16, 32)
+#endif
 #undef SGBM_TRY3
     } else {
         SGBM_DISPATCH_ALL((launch_vertical_t<NREG, LPC, 1>(a, numSMs, st)))

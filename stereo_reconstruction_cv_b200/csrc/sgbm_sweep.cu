@@ -43,6 +43,7 @@ struct SweepArgs {
     int SW, nstrips, R, NB;          // max columns per strip, strips, rows per super-step, batches
     int nwA, nwV;                    // warps of each diagonal role / of the vertical role
     int aA, aV, nwW, wPass;          // WROLE: warps allocated per role (multiples of 4), WTA warps, their passes per row
+    int wRG, wPR;                    // WROLE: row groups of the WTA warps (group j takes rows t = j mod wRG), warps per row
     int NSC, NSI, K, nAB;            // ring depths (cost rows, input rows, S slots), input volumes
     unsigned int stgCOff, stgIOff, pOff, ssmOff, barOff;
     int backward;
@@ -51,6 +52,9 @@ struct SweepArgs {
     int dbgNoSync;
     int dbgStall;                    // test hook (SGBM_DBG_STALL=1): role V withholds one hand-off so that the watchdog trips
     unsigned int urMagic;            // floor(2^32 / (100 - uniquenessRatio)) + 1
+    unsigned int P1p, P2mP1p;        // P1 and P2 - P1 in both 16-bit halves
+    // ring geometry in bytes (host-computed so that the row loops add constants instead of multiplying)
+    unsigned int colB, cStrideB, cSpanB, iBB, iStrideB, iSpanB, pStrideB, pSpanB, cBarSpan, iBarSpan, pBarSpan;
     unsigned int *dbg;               // [8] hand-off watchdog: {tripped, strip, warp, wait id, row, ...}, zeroed per launch
     unsigned long long *trace;       // debug: clock64 time stamps of one strip [row][role 4][8] (or null)
     int traceStrip;
@@ -145,27 +149,66 @@ __device__ __forceinline__ void load_vec_l2(uint32_t (&v)[NREG], const uint16_t 
     }
 }
 
+// Barriers.  The stages of a ring keep their barriers side by side, so that a role carries ONE barrier
+// address per ring and reaches the others through immediate offsets:
+//   cost ring   stage q: barC + 16 q   { +0 fullC, +8 emptyC }
+//   input ring  stage q: barI + 16 q   { +0 fullI, +8 emptyI }
+//   S ring      slot  q: barP + 32 q   { +0 fullV, +8 fullM, +16 fullW, +24 freeP }
+#define BAR_FULL 0u
+#define BAR_EMPTY 8u
+#define BAR_FULLV 0u
+#define BAR_FULLM 8u
+#define BAR_FULLW 16u
+#define BAR_FREEP 24u
 struct SweepSmem {
-    uint16_t *stgC, *stgI, *P, *ssm;
-    SmemBar fullC, emptyC, fullI, emptyI, fullV, fullM, freeP, fullW;     // 32-bit shared addresses
+    uint16_t *ssm;                   // [groups of role C][Dp]  WTA scratch of the kernels without the W role
+    uint32_t aC, aI, aP;             // 32-bit shared addresses of the rings: stgC [NSC][SW + 2(R-1)][Dp], stgI [NSI][nAB][SW][Dp], P [K][SW][Dp]
+    uint32_t barC, barI, barP;
 };
 __device__ __forceinline__ SweepSmem sweep_carve(const SweepArgs &a, uint8_t *smem)
 {
     SweepSmem s;
-    s.stgC = reinterpret_cast<uint16_t *>(smem + a.stgCOff);     // [NSC][SW + 2(R-1)][Dp]
-    s.stgI = reinterpret_cast<uint16_t *>(smem + a.stgIOff);     // [NSI][nAB][SW][Dp]
-    s.P = reinterpret_cast<uint16_t *>(smem + a.pOff);           // [K][SW][Dp]
-    s.ssm = reinterpret_cast<uint16_t *>(smem + a.ssmOff);       // [groups of role C][Dp]  (WTA scratch)
-    SmemBar b{smem_u32(smem) + (uint32_t)a.barOff};
-    s.fullC = b; b = b[a.NSC];
-    s.emptyC = b; b = b[a.NSC];
-    s.fullI = b; b = b[a.NSI];
-    s.emptyI = b; b = b[a.NSI];
-    s.fullV = b; b = b[a.K];
-    s.fullM = b; b = b[a.K];
-    s.freeP = b; b = b[a.K];
-    s.fullW = b;
+    s.ssm = reinterpret_cast<uint16_t *>(smem + a.ssmOff);
+    const uint32_t base = smem_u32(smem);
+    s.aC = base + a.stgCOff; s.aI = base + a.stgIOff; s.aP = base + a.pOff;
+    s.barC = base + a.barOff;
+    s.barI = s.barC + 16u * (uint32_t)a.NSC;
+    s.barP = s.barI + 16u * (uint32_t)a.NSI;
     return s;
+}
+
+// A role's position in one ring: everything the row loop needs of it lives in these registers and is
+// advanced by additions -- no per-row multiplications, no re-derivation from the kernel arguments.
+struct RingPos {
+    uint32_t data;                   // shared address of this thread's data in the current stage
+    uint32_t bar;                    // shared address of the current stage's barrier group
+    uint32_t par;                    // phase parity of the current pass over the ring
+    int left;                        // stages until the ring wraps
+};
+__device__ __forceinline__ RingPos ring_start(uint32_t data, uint32_t bar, int depth)
+{
+    RingPos r;
+    r.data = sm_keep(data); r.bar = sm_keep(bar); r.par = 0u; r.left = depth;
+    return r;
+}
+// stride / span = bytes per stage / per ring of the data, barStep / barSpan the same for the barriers
+__device__ __forceinline__ void ring_advance(RingPos &r, uint32_t stride, uint32_t span, uint32_t barStep, uint32_t barSpan, int depth)
+{
+    r.data += stride; r.bar += barStep;
+    if (--r.left == 0) { r.left = depth; r.data -= span; r.bar -= barSpan; r.par ^= 1u; }
+}
+// the same for a role that visits every n-th stage (n <= depth)
+__device__ __forceinline__ void ring_advance_n(RingPos &r, int n, uint32_t stride, uint32_t span, uint32_t barStep, uint32_t barSpan, int depth)
+{
+    r.data += (uint32_t)n * stride; r.bar += (uint32_t)n * barStep; r.left -= n;
+    if (r.left <= 0) { r.left += depth; r.data -= span; r.bar -= barSpan; r.par ^= 1u; }
+}
+__device__ __forceinline__ void bar_arrive(uint32_t addr) { mbar_arrive(SmemBar{addr}); }
+__device__ __forceinline__ bool bar_test(uint32_t addr, uint32_t parity) { return mbar_test_wait(SmemBar{addr}, parity); }
+__device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
 // ---- producer: TMA bulk copies of the cost row and the input rows of every sweep row ---------------
@@ -173,28 +216,32 @@ __device__ __forceinline__ void sweep_producer(const SweepArgs &a, const SweepSm
                                                int yStep, int nRows)
 {
     const Geo &g = a.g;
-    const int Dp = g.Dp, HG = a.R - 1, ngC = a.SW + 2 * HG;
+    const int Dp = g.Dp, HG = a.R - 1;
     const int scol0 = xs - HG;
     const int clo = max(scol0, 0), chi = min(xe + HG, g.W1);
-    const uint32_t bytesC = (uint32_t)(chi - clo) * Dp * 2, bytesI = (uint32_t)(xe - xs) * Dp * 2;
-    int sc = 0, si = 0;
-    uint32_t pc = 0, pi = 0;
+    const uint32_t colB = a.colB;
+    const uint32_t bytesC = (uint32_t)(chi - clo) * colB, bytesI = (uint32_t)(xe - xs) * colB;
+    RingPos rc = ring_start(s.aC + (uint32_t)(clo - scol0) * colB, s.barC, a.NSC);
+    RingPos ri = ring_start(s.aI, s.barI, a.NSI);
+    const uint16_t *srcC = a.C + (size_t)yBegin * g.rowStride + (size_t)clo * Dp;
+    const uint16_t *srcA = a.inA + (size_t)yBegin * g.rowStride + (size_t)xs * Dp;
+    const uint16_t *srcB = a.nAB > 1 ? a.inB + (size_t)yBegin * g.rowStride + (size_t)xs * Dp : nullptr;
+    const long long rowStep = (long long)yStep * g.rowStride;
     for (int t = 0; t < nRows; t++) {
-        const int y = yBegin + t * yStep;
         SWEEP_TR(3, 0, true);
-        if (t >= a.NSC) sweep_wait(a, s.emptyC[sc], pc ^ 1u, 1, t);
+        if (t >= a.NSC) sweep_wait(a, SmemBar{rc.bar + BAR_EMPTY}, rc.par ^ 1u, 1, t);
         SWEEP_TR(3, 1, true);
-        mbar_expect_tx(s.fullC[sc], bytesC);
-        bulk_g2s(s.stgC + ((size_t)sc * ngC + (clo - scol0)) * Dp, a.C + (size_t)y * g.rowStride + (size_t)clo * Dp, bytesC,
-                 s.fullC[sc]);
-        if (t >= a.NSI) sweep_wait(a, s.emptyI[si], pi ^ 1u, 2, t);
-        const size_t off = (size_t)y * g.rowStride + (size_t)xs * Dp;
-        mbar_expect_tx(s.fullI[si], bytesI * (uint32_t)a.nAB);
-        bulk_g2s(s.stgI + (size_t)(si * a.nAB + 0) * a.SW * Dp, a.inA + off, bytesI, s.fullI[si]);
-        if (a.nAB > 1) bulk_g2s(s.stgI + (size_t)(si * a.nAB + 1) * a.SW * Dp, a.inB + off, bytesI, s.fullI[si]);
+        mbar_expect_tx(SmemBar{rc.bar + BAR_FULL}, bytesC);
+        bulk_g2s_a(rc.data, srcC, bytesC, rc.bar + BAR_FULL);
+        if (t >= a.NSI) sweep_wait(a, SmemBar{ri.bar + BAR_EMPTY}, ri.par ^ 1u, 2, t);
+        mbar_expect_tx(SmemBar{ri.bar + BAR_FULL}, bytesI * (uint32_t)a.nAB);
+        bulk_g2s_a(ri.data, srcA, bytesI, ri.bar + BAR_FULL);
+        if (srcB) bulk_g2s_a(ri.data + a.iBB, srcB, bytesI, ri.bar + BAR_FULL);
         SWEEP_TR(3, 2, true);
-        if (++sc == a.NSC) { sc = 0; pc ^= 1u; }
-        if (++si == a.NSI) { si = 0; pi ^= 1u; }
+        ring_advance(rc, a.cStrideB, a.cSpanB, 16u, a.cBarSpan, a.NSC);
+        ring_advance(ri, a.iStrideB, a.iSpanB, 16u, a.iBarSpan, a.NSI);
+        srcC += rowStep; srcA += rowStep;
+        if (srcB) srcB += rowStep;
     }
 }
 
@@ -203,6 +250,39 @@ __device__ __forceinline__ void sweep_producer(const SweepArgs &a, const SweepSm
 template <bool SAT>
 __device__ __forceinline__ uint32_t sacc(uint32_t s, uint32_t x) { return SAT ? paddmin(s, x, SGBM_MAX_S) : s + x; }
 
+// OR-masks of a lane inside its group: all ones where the disparity neighbour below / above the lane's
+// range is outside [0, D) (L(-1) = L(D) = +inf, A.4) and where the whole lane is padding.  Held in registers
+// (made opaque once) so that the row loop does not re-derive them from the thread id.
+struct LaneMasks { uint32_t up, dn, pad; };
+__device__ __forceinline__ LaneMasks lane_masks(int lg, int lastLane)
+{
+    LaneMasks m;
+    m.up = sm_keep(lg == 0 ? 0xFFFFFFFFu : 0u);
+    m.dn = sm_keep(lg >= lastLane ? 0xFFFFFFFFu : 0u);
+    m.pad = sm_keep(lg > lastLane ? 0xFFFFFFFFu : 0u);
+    return m;
+}
+
+// path_step of sgbm_common.cuh, in place, with the lane masks instead of per-row comparisons.
+template <int NREG, int LPC>
+__device__ __forceinline__ uint32_t path_step_m(uint32_t (&L)[NREG], uint32_t mp, const uint32_t (&C)[NREG], uint32_t P1p,
+                                                uint32_t P2mP1p, const LaneMasks &lm)
+{
+    const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, L[NREG - 1], 1, LPC) | lm.up;
+    const uint32_t dn = __shfl_down_sync(0xFFFFFFFFu, L[0], 1, LPC) | lm.dn;
+    const uint32_t k1 = mp + P2mP1p;                       // (m + P2 - P1) in both halves, no carry (<= 65535)
+    uint32_t sPrev = __byte_perm(up, L[0], 0x5432);        // (L[2j-1], L[2j]) for j = 0
+#pragma unroll
+    for (int j = 0; j < NREG; j++) {
+        const uint32_t nxt = (j + 1 < NREG) ? L[j + 1] : dn;
+        const uint32_t sNext = __byte_perm(L[j], nxt, 0x5432);
+        const uint32_t b = paddmin(pmin3(sPrev, sNext, k1), P1p, L[j]);
+        L[j] = b + C[j] - mp;
+        sPrev = sNext;
+    }
+    return group_min<LPC>(local_min<NREG>(L) | lm.pad);
+}
+
 // ---- role V: vertical path, starts the S slot of every row ------------------------------------------
 template <int NREG, int LPC, bool SAT>
 __device__ __forceinline__ void sweep_role_v(const SweepArgs &a, const SweepSmem &s, int rwarp, int SW, int nRows)
@@ -210,65 +290,64 @@ __device__ __forceinline__ void sweep_role_v(const SweepArgs &a, const SweepSmem
     constexpr int GPW = 32 / LPC;
     const Geo &g = a.g;
     const int lane = threadIdx.x & 31, lg = lane % LPC;
-    const int Dp = g.Dp, lastLane = g.lanesUsed - 1, HG = a.R - 1, ngC = a.SW + 2 * HG;
+    const int HG = a.R - 1;
     const int gi = rwarp * GPW + lane / LPC;
-    const bool own = gi < SW;
-    const int ci = own ? gi : SW - 1;
-    const uint32_t P1p = (uint32_t)g.P1 * 0x10001u, P2mP1p = (uint32_t)(g.P2 - g.P1) * 0x10001u;
+    const int ci = gi < SW ? gi : SW - 1;
+    const uint32_t own = sm_keep(gi < SW ? 1u : 0u), lane0 = sm_keep(lane == 0 ? 1u : 0u);
+    const LaneMasks lm = lane_masks(lg, g.lanesUsed - 1);
     const bool hasB = a.nAB > 1;
     const int NSC = a.NSC, NSI = a.NSI, K = a.K;
-    // element offsets of this group's column inside one stage / slot, and the stage strides
-    const int cBase = (HG + ci) * Dp, cStride = ngC * Dp;
-    const int iBase = ci * Dp, iStride = a.nAB * a.SW * Dp, iB = a.SW * Dp;
-    const int pBase = ci * Dp, pStride = a.SW * Dp;
+    // this lane's chunk of its column inside stage 0 of each ring, and the ring geometry in bytes
+    const uint32_t colB = a.colB, laneB = 16u * (uint32_t)lg;
+    RingPos rc = ring_start(s.aC + (uint32_t)(HG + ci) * colB + laneB, s.barC, NSC);
+    RingPos ri = ring_start(s.aI + (uint32_t)ci * colB + laneB, s.barI, NSI);
+    RingPos rp = ring_start(s.aP + (uint32_t)ci * colB + laneB, s.barP, K);
     uint32_t LB[NREG], mB = 0;
 #pragma unroll
     for (int j = 0; j < NREG; j++) LB[j] = 0;
-    int sc = 0, si = 0, k = 0, cOff = cBase, iOff = iBase, pOff = pBase;
-    uint32_t pc = 0, pi = 0, pk = 0;
-    bool okC = false;                                     // early probe of the next row's cost stage
+    bool okC = false;                                     // early probe of the row's cost stage
     for (int t = 0; t < nRows; t++) {
         uint32_t S[NREG];
         SWEEP_PROG(0, rwarp == 0);
         SWEEP_TR(0, 0, rwarp == 0);
-        if (!okC) sweep_wait(a, s.fullC[sc], pc, 3, t);
+        if (!okC) sweep_wait(a, SmemBar{rc.bar + BAR_FULL}, rc.par, 3, t);
         SWEEP_TR(0, 1, rwarp == 0);
         // probes whose latency hides behind the path step
-        const bool okI = mbar_test_wait(s.fullI[si], pi);
-        const bool okP = t >= K ? mbar_test_wait(s.freeP[k], pk ^ 1u) : true;
+        const bool okI = bar_test(ri.bar + BAR_FULL, ri.par);
+        const bool okP = t >= K ? bar_test(rp.bar + BAR_FREEP, rp.par ^ 1u) : true;
         {
             uint32_t Cc[NREG];
-            load_vec<NREG, LPC>(Cc, s.stgC + cOff, lg);
-            const int scN = sc + 1 == NSC ? 0 : sc + 1;
-            okC = t + 1 < nRows ? mbar_test_wait(s.fullC[scN], scN ? pc : pc ^ 1u) : true;
-            mB = path_step<NREG, LPC>(LB, LB, mB, Cc, P1p, P2mP1p, lg, lastLane);   // in place (reads run ahead of writes)
+            lds_vec<NREG, LPC>(Cc, rc.data);
+            mB = path_step_m<NREG, LPC>(LB, mB, Cc, a.P1p, a.P2mP1p, lm);
         }
+        // the cost row is in registers: hand the stage back and look at the next one
+        __syncwarp();
+        if (lane0) bar_arrive(rc.bar + BAR_EMPTY);
+        ring_advance(rc, a.cStrideB, a.cSpanB, 16u, a.cBarSpan, NSC);
+        okC = bar_test(rc.bar + BAR_FULL, rc.par);
         SWEEP_TR(0, 2, rwarp == 0);
-        if (!okI) sweep_wait(a, s.fullI[si], pi, 4, t);
-        load_vec<NREG, LPC>(S, s.stgI + iOff, lg);
+        if (!okI) sweep_wait(a, SmemBar{ri.bar + BAR_FULL}, ri.par, 4, t);
+        lds_vec<NREG, LPC>(S, ri.data);
 #pragma unroll
         for (int j = 0; j < NREG; j++) S[j] = sacc<SAT>(S[j], LB[j]);
         if (hasB) {
             uint32_t Bv[NREG];
-            load_vec<NREG, LPC>(Bv, s.stgI + iOff + iB, lg);
+            lds_vec<NREG, LPC>(Bv, ri.data + a.iBB);
 #pragma unroll
             for (int j = 0; j < NREG; j++) S[j] = sacc<SAT>(S[j], Bv[j]);
         }
         SWEEP_TR(0, 3, rwarp == 0);
-        if (!okP) sweep_wait(a, s.freeP[k], pk ^ 1u, 5, t);
+        if (!okP) sweep_wait(a, SmemBar{rp.bar + BAR_FREEP}, rp.par ^ 1u, 5, t);
         SWEEP_TR(0, 4, rwarp == 0);
-        if (own) store_vec<NREG, LPC>(S, s.P + pOff, lg);
+        if (own) sts_vec<NREG, LPC>(S, rp.data);
         __syncwarp();
-        if (lane == 0) {
-            if (!(SGBM_DBG_HOOK(a.dbgStall) && t == 5 && blockIdx.x == 0)) mbar_arrive(s.fullV[k]);
-            mbar_arrive(s.emptyC[sc]);
-            mbar_arrive(s.emptyI[si]);
+        if (lane0) {
+            if (!(SGBM_DBG_HOOK(a.dbgStall) && t == 5 && blockIdx.x == 0)) bar_arrive(rp.bar + BAR_FULLV);
+            bar_arrive(ri.bar + BAR_EMPTY);
         }
         SWEEP_TR(0, 5, rwarp == 0);
-        cOff += cStride; iOff += iStride; pOff += pStride;
-        if (++sc == NSC) { sc = 0; pc ^= 1u; cOff = cBase; }
-        if (++si == NSI) { si = 0; pi ^= 1u; iOff = iBase; }
-        if (++k == K) { k = 0; pk ^= 1u; pOff = pBase; }
+        ring_advance(ri, a.iStrideB, a.iSpanB, 16u, a.iBarSpan, NSI);
+        ring_advance(rp, a.pStrideB, a.pSpanB, 32u, a.pBarSpan, K);
     }
 }
 
@@ -367,8 +446,7 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
     constexpr bool FINAL = DIR < 0;
     const Geo &g = a.g;
     const int lane = threadIdx.x & 31, lg = lane % LPC;
-    const int Dp = g.Dp, lastLane = g.lanesUsed - 1, R = a.R, HG = R - 1, ngC = a.SW + 2 * HG, NB = a.NB;
-    const uint32_t P1p = (uint32_t)g.P1 * 0x10001u, P2mP1p = (uint32_t)(g.P2 - g.P1) * 0x10001u;
+    const int Dp = g.Dp, lastLane = g.lanesUsed - 1, R = a.R, HG = R - 1, NB = a.NB;
     const int gg = rwarp * GPW + lane / LPC;
     const int b = gg / R, i = gg - b * R;
     const bool exists = b < NB;
@@ -391,16 +469,23 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
     const int hidx = DIR > 0 ? i : R - 1 - i;             // which published column chain i continues
     const uint16_t *haloIn = (DIR > 0 ? a.haloA : a.haloC) + ((size_t)nbr * 64 + hidx) * haloStride;
     const unsigned int *flagIn = (DIR > 0 ? a.flagA : a.flagC) + (size_t)nbr * 64 + hidx;
-    uint16_t *ssm = s.ssm + (size_t)gg * Dp;
+    uint16_t *ssm = s.ssm + (size_t)gg * Dp;          // (kernels without the W role only)
 
     uint32_t L[NREG], m = 0;
 #pragma unroll
     for (int j = 0; j < NREG; j++) L[j] = 0;              // "predecessor outside" == L = 0, m = 0 (A.4)
     const int NSC = a.NSC, K = a.K;
-    const int cStride = ngC * Dp, pStride = a.SW * Dp;
-    int sc = 0, k = 0, kk = 0, n = 0, nm = 0, cOff = 0, pOff = 0;
-    uint32_t pc = 0, pk = 0;
-    bool okC = false;                                     // early probe of the next row's cost stage
+    const LaneMasks lm = lane_masks(lg, lastLane);
+    const uint32_t lane0 = sm_keep(lane == 0 ? 1u : 0u);
+    // this lane's chunk of column 0 of stage 0 of the cost ring / of slot 0 of the S ring, ring geometry in bytes
+    const uint32_t colB = a.colB;
+    RingPos rc = ring_start(s.aC + 16u * (uint32_t)lg, s.barC, NSC);
+    RingPos rp = ring_start(s.aP + 16u * (uint32_t)lg, s.barP, K);
+    // WROLE: the finished S goes back into the slot and the winner-take-all warps release it
+    constexpr uint32_t WAIT_BAR = FINAL ? BAR_FULLM : BAR_FULLV;
+    constexpr uint32_t DONE_BAR = FINAL ? (WROLE ? BAR_FULLW : BAR_FREEP) : BAR_FULLM;
+    int kk = 0, n = 0, nm = 0;
+    bool okC = false;                                     // early probe of the row's cost stage
     for (int t = 0; t < nRows; t++) {
         SWEEP_PROG(DIR > 0 ? 1 : 3, rwarp == 0);
         SWEEP_PROG(DIR > 0 ? 2 : 4, rwarp == a.nwA - 1);
@@ -439,21 +524,20 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
             for (int j = 0; j < NREG; j++) L[j] = 0;
             m = 0;
         }
-        // WROLE: the finished S goes back into the slot and the winner-take-all warps release it
-        const SmemBar waitBar = FINAL ? s.fullM : s.fullV, doneBar = FINAL ? (WROLE ? s.fullW : s.freeP) : s.fullM;
         SWEEP_TR(DIR > 0 ? 1 : 2, 0, rwarp == a.nwA / 2);
-        if (!okC) sweep_wait(a, s.fullC[sc], pc, DIR > 0 ? 8 : 9, t);
+        if (!okC) sweep_wait(a, SmemBar{rc.bar + BAR_FULL}, rc.par, DIR > 0 ? 8 : 9, t);
         SWEEP_TR(DIR > 0 ? 1 : 2, 1, rwarp == a.nwA / 2);
-        const bool okS = mbar_test_wait(waitBar[k], pk);  // latency hides behind the path step
-        {
-            const int scN = sc + 1 == NSC ? 0 : sc + 1;
-            okC = t + 1 < nRows ? mbar_test_wait(s.fullC[scN], scN ? pc : pc ^ 1u) : true;
-        }
+        const bool okS = bar_test(rp.bar + WAIT_BAR, rp.par);   // latency hides behind the path step
         if (__any_sync(0xFFFFFFFFu, active)) {           // inactive groups compute garbage that is never used
             uint32_t Cc[NREG];
-            load_vec<NREG, LPC>(Cc, s.stgC + cOff + sidx * Dp, lg);
-            m = path_step<NREG, LPC>(L, L, m, Cc, P1p, P2mP1p, lg, lastLane);
+            lds_vec<NREG, LPC>(Cc, rc.data + (uint32_t)sidx * colB);
+            m = path_step_m<NREG, LPC>(L, m, Cc, a.P1p, a.P2mP1p, lm);
         }
+        // the cost row is in registers: hand the stage back and look at the next one
+        __syncwarp();
+        if (lane0) bar_arrive(rc.bar + BAR_EMPTY);
+        ring_advance(rc, a.cStrideB, a.cSpanB, 16u, a.cBarSpan, NSC);
+        okC = bar_test(rc.bar + BAR_FULL, rc.par);
         const uint32_t mN = m;
         const uint32_t (&Ln)[NREG] = L;
         // ---- super-step end: publish the columns the neighbour continues ----------------------------
@@ -475,24 +559,21 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
         }
         // ---- S slot of this row ---------------------------------------------------------------------
         SWEEP_TR(DIR > 0 ? 1 : 2, 2, rwarp == a.nwA / 2);
-        if (!okS) sweep_wait(a, waitBar[k], pk, DIR > 0 ? 10 : 11, t);
+        if (!okS) sweep_wait(a, SmemBar{rp.bar + WAIT_BAR}, rp.par, DIR > 0 ? 10 : 11, t);
         SWEEP_TR(DIR > 0 ? 1 : 2, 3, rwarp == a.nwA / 2);
         uint32_t S[NREG];
         if (own) {
-            uint16_t *ps = s.P + pOff + (col - xs) * Dp;
-            load_vec<NREG, LPC>(S, ps, lg);
+            const uint32_t ps = rp.data + (uint32_t)(col - xs) * colB;
+            lds_vec<NREG, LPC>(S, ps);
 #pragma unroll
             for (int j = 0; j < NREG; j++) S[j] = sacc<SAT>(S[j], Ln[j]);
-            if (!FINAL || WROLE) store_vec<NREG, LPC>(S, ps, lg);
-        } else if (FINAL) {
+            if (!FINAL || WROLE) sts_vec<NREG, LPC>(S, ps);
+        } else if (FINAL && !WROLE) {
 #pragma unroll
             for (int j = 0; j < NREG; j++) S[j] = SGBM_MAX_S;
         }
         __syncwarp();
-        if (lane == 0) {
-            mbar_arrive(doneBar[k]);
-            mbar_arrive(s.emptyC[sc]);
-        }
+        if (lane0) bar_arrive(rp.bar + DONE_BAR);
         SWEEP_TR(DIR > 0 ? 1 : 2, 4, rwarp == a.nwA / 2);
         if (FINAL && !WROLE && __any_sync(0xFFFFFFFFu, own)) {
             const int y = yBegin + t * yStep;
@@ -510,9 +591,7 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
         }
         SWEEP_TR(DIR > 0 ? 1 : 2, 5, rwarp == a.nwA / 2);
         p++;
-        cOff += cStride; pOff += pStride;
-        if (++sc == NSC) { sc = 0; pc ^= 1u; cOff = 0; }
-        if (++k == K) { k = 0; pk ^= 1u; pOff = 0; }
+        ring_advance(rp, a.pStrideB, a.pSpanB, 32u, a.pBarSpan, K);
         if (++kk == R) {
             kk = 0; n++;
             if (++nm == NB) nm = 0;
@@ -525,14 +604,16 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
 // of the masked uniqueness re-scan, and releases the slot.  S in the slot is the plain (unclamped) sum
 // when !SAT; the clamp to 32767 (A.4) is applied to what is read.
 template <int NREG, int LPC, bool SAT>
-__device__ __forceinline__ void sweep_wta_slot(const SweepArgs &a, uint16_t *col, int lg, bool own, int x1, int y)
+__device__ __forceinline__ void sweep_wta_slot(const SweepArgs &a, uint32_t colA, int lg, uint32_t padMask, unsigned gmask,
+                                               bool own, int x1, int y)
 {
+    // colA: shared address of the column's vector in the ring slot (lane chunk NOT included)
     const Geo &g = a.g;
-    const int lastLane = g.lanesUsed - 1;
+    const uint32_t laneA = colA + 16u * (uint32_t)lg;
     uint32_t key = 0xFFFFFFFFu;
     {
         uint32_t S[NREG];
-        load_vec<NREG, LPC>(S, col, lg);
+        lds_vec<NREG, LPC>(S, laneA);
         // The clamp to 32767 is monotone, so it commutes with the min reduction; a saturated minimum makes
         // the pixel invalid whichever disparity carries it, so only the debug dump needs clamped vectors.
         if (!SAT && a.sdbg) {
@@ -548,8 +629,7 @@ __device__ __forceinline__ void sweep_wta_slot(const SweepArgs &a, uint16_t *col
             key = __vimin3_u32(key, k0, k1);
         }
     }
-    key += (uint32_t)(lg * 2 * NREG);                                   // lane-local index -> disparity
-    if (lg > lastLane) key = 0xFFFFFFFFu;
+    key = (key + (uint32_t)(lg * 2 * NREG)) | padMask;                  // lane-local index -> disparity; padding lanes drop out
 #pragma unroll
     for (int off = LPC / 2; off >= 1; off >>= 1) key = min(key, __shfl_xor_sync(0xFFFFFFFFu, key, off, LPC));
     const int minS = min((int)(key >> 16), 32767);
@@ -557,8 +637,8 @@ __device__ __forceinline__ void sweep_wta_slot(const SweepArgs &a, uint16_t *col
     int Sm = 0, Sp = 0;
     const bool interior = best > 0 && best < g.D - 1;
     if (lg == 0 && interior) {
-        Sm = min((int)col[sgbm_pos(best - 1, NREG, LPC)], 32767);
-        Sp = min((int)col[sgbm_pos(best + 1, NREG, LPC)], 32767);
+        Sm = min((int)lds16(colA + 2u * (uint32_t)sgbm_pos(best - 1, NREG, LPC)), 32767);
+        Sp = min((int)lds16(colA + 2u * (uint32_t)sgbm_pos(best + 1, NREG, LPC)), 32767);
     }
     bool reject = false;
     if (g.UR > 0) {
@@ -570,18 +650,15 @@ __device__ __forceinline__ void sweep_wta_slot(const SweepArgs &a, uint16_t *col
 #pragma unroll
             for (int dd = -1; dd <= 1; dd++) {
                 const int d = best + dd;
-                if (d >= 0 && d < g.D) col[sgbm_pos(d, NREG, LPC)] = 0xFFFFu;
+                if (d >= 0 && d < g.D) sts16(colA + 2u * (uint32_t)sgbm_pos(d, NREG, LPC), 0xFFFFu);
             }
         }
         __syncwarp();
         uint32_t S2[NREG];
-        load_vec<NREG, LPC>(S2, col, lg);
-        const uint32_t t2 = local_min<NREG>(S2);
-        const bool viol = lg <= lastLane && min((int)(t2 & 0xFFFFu), 32767) < T;
-        const unsigned ball = __ballot_sync(0xFFFFFFFFu, viol);
-        const int lane = threadIdx.x & 31;
-        const unsigned gmask = (LPC == 32 ? 0xFFFFFFFFu : ((1u << LPC) - 1u)) << (lane & ~(LPC - 1));
-        reject = (ball & gmask) != 0u;
+        lds_vec<NREG, LPC>(S2, laneA);
+        const uint32_t t2 = local_min<NREG>(S2) | padMask;
+        const bool viol = padMask == 0u && min((int)(t2 & 0xFFFFu), 32767) < T;
+        reject = (__ballot_sync(0xFFFFFFFFu, viol) & gmask) != 0u;
     }
     if (lg == 0 && own) {
         const int x = x1 + g.minX1;
@@ -607,25 +684,36 @@ __device__ __forceinline__ void sweep_role_w(const SweepArgs &a, const SweepSmem
 {
     constexpr int GPW = 32 / LPC;
     const int lane = threadIdx.x & 31, lg = lane % LPC;
-    const int Dp = a.g.Dp, K = a.K, pStride = a.SW * Dp;
-    int k = 0, pOff = 0;
-    uint32_t pk = 0;
-    for (int t = 0; t < nRows; t++) {
+    const int K = a.K;
+    const uint32_t colB = a.colB;
+    const uint32_t padMask = sm_keep(lg > a.g.lanesUsed - 1 ? 0xFFFFFFFFu : 0u);
+    const unsigned gmask = sm_keep((LPC == 32 ? 0xFFFFFFFFu : ((1u << LPC) - 1u)) << (lane & ~(LPC - 1)));
+    const uint32_t lane0 = sm_keep(lane == 0 ? 1u : 0u);
+    // The winner-take-all of a pixel is one long dependent chain (two reductions, a masked re-scan, a division):
+    // ~1500 cycles per pass whatever the strip width.  With narrow strips that latency, not throughput, would set
+    // the row period of the whole kernel, so the W warps are split into wRG row groups that take alternate rows.
+    const int wRG = a.wRG, wPR = a.wPR;
+    const int rgrp = wwarp / wPR, wq = wwarp - rgrp * wPR;
+    RingPos rp = ring_start(s.aP, s.barP, K);
+    if (rgrp) ring_advance_n(rp, rgrp, a.pStrideB, a.pSpanB, 32u, a.pBarSpan, K);
+    for (int t = rgrp; t < nRows; t += wRG) {
         const int y = yBegin + t * yStep;
         SWEEP_PROG(5, wwarp == 0);
-        sweep_wait(a, s.fullW[k], pk, 12, t);
+        SWEEP_TR(3, 4, wwarp == 0);
+        sweep_wait(a, SmemBar{rp.bar + BAR_FULLW}, rp.par, 12, t);
+        SWEEP_TR(3, 5, wwarp == 0);
         for (int it = 0; it < a.wPass; it++) {
-            const int gi = (it * a.nwW + wwarp) * GPW + lane / LPC;
+            const int gi = (it * wPR + wq) * GPW + lane / LPC;
             const bool own = gi < SW;
             if (!__any_sync(0xFFFFFFFFu, own)) continue;
             const int ci = own ? gi : SW - 1;
             // (groups without a column read column SW-1 along with the warp; all their writes are guarded by own)
-            sweep_wta_slot<NREG, LPC, SAT>(a, s.P + pOff + ci * Dp, lg, own, xs + ci, y);
+            sweep_wta_slot<NREG, LPC, SAT>(a, rp.data + (uint32_t)ci * colB, lg, padMask, gmask, own, xs + ci, y);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(s.freeP[k]);
-        pOff += pStride;
-        if (++k == K) { k = 0; pk ^= 1u; pOff = 0; }
+        SWEEP_TR(3, 6, wwarp == 0);
+        if (lane0) bar_arrive(rp.bar + BAR_FREEP);
+        ring_advance_n(rp, wRG, a.pStrideB, a.pSpanB, 32u, a.pBarSpan, K);
     }
 }
 
@@ -644,11 +732,11 @@ __global__ void __launch_bounds__((SweepMaxThreads<NREG, WROLE>::value), 1) k_sw
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         const int nCons = a.nwV + 2 * a.nwA;
-        for (int q = 0; q < a.NSC; q++) { mbar_init(s.fullC[q], 1); mbar_init(s.emptyC[q], nCons); }
-        for (int q = 0; q < a.NSI; q++) { mbar_init(s.fullI[q], 1); mbar_init(s.emptyI[q], a.nwV); }
+        for (int q = 0; q < a.NSC; q++) { mbar_init(SmemBar{s.barC + 16u * q + BAR_FULL}, 1); mbar_init(SmemBar{s.barC + 16u * q + BAR_EMPTY}, nCons); }
+        for (int q = 0; q < a.NSI; q++) { mbar_init(SmemBar{s.barI + 16u * q + BAR_FULL}, 1); mbar_init(SmemBar{s.barI + 16u * q + BAR_EMPTY}, a.nwV); }
         for (int q = 0; q < a.K; q++) {
-            mbar_init(s.fullV[q], a.nwV); mbar_init(s.fullM[q], a.nwA);
-            mbar_init(s.freeP[q], WROLE ? a.nwW : a.nwA); mbar_init(s.fullW[q], a.nwA);
+            mbar_init(SmemBar{s.barP + 32u * q + BAR_FULLV}, a.nwV); mbar_init(SmemBar{s.barP + 32u * q + BAR_FULLM}, a.nwA);
+            mbar_init(SmemBar{s.barP + 32u * q + BAR_FREEP}, WROLE ? a.wPR : a.nwA); mbar_init(SmemBar{s.barP + 32u * q + BAR_FULLW}, a.nwA);
         }
         mbar_fence_init();
     }
@@ -700,6 +788,10 @@ static size_t sweep_layout(SweepArgs &a, int groupsC, bool scratch)
     a.ssmOff = (unsigned)off; if (scratch) off += (size_t)groupsC * col;
     off = (off + 15) & ~(size_t)15;
     a.barOff = (unsigned)off; off += (size_t)(2 * a.NSC + 2 * a.NSI + 4 * a.K) * 8;
+    a.colB = (unsigned)col;
+    a.cStrideB = (unsigned)((a.SW + 2 * (a.R - 1)) * col); a.cSpanB = a.cStrideB * (unsigned)a.NSC; a.cBarSpan = 16u * (unsigned)a.NSC;
+    a.iBB = (unsigned)(a.SW * col); a.iStrideB = a.iBB * (unsigned)a.nAB; a.iSpanB = a.iStrideB * (unsigned)a.NSI; a.iBarSpan = 16u * (unsigned)a.NSI;
+    a.pStrideB = a.iBB; a.pSpanB = a.pStrideB * (unsigned)a.K; a.pBarSpan = 32u * (unsigned)a.K;
     return off;
 }
 
@@ -733,9 +825,12 @@ static bool sweep_plan(const Geo &g, int numSMs, bool wrole, bool wta, int maxTh
         int threads;
         if (wrole) {
             a.aA = (a.nwA + 3) & ~3; a.aV = (a.nwV + 3) & ~3;
-            a.nwW = a.nwV < 7 ? a.nwV : 7;                // 8 warps: WTA warps, the producer, idle
-            if (kn.sweepNWW >= 1 && kn.sweepNWW <= 7) a.nwW = kn.sweepNWW;
-            a.wPass = (SWmax + a.nwW * GPW - 1) / (a.nwW * GPW);
+            // 8 warps in the last warpgroup: WTA warps, the producer, idle.  wPR warps share a row, the rest of
+            // the seven form further row groups (fixed below, once the S-ring depth is known)
+            a.wPR = a.nwV < 7 ? a.nwV : 7;
+            if (kn.sweepNWW >= 1 && kn.sweepNWW <= 7) a.wPR = kn.sweepNWW;
+            a.wPass = (SWmax + a.wPR * GPW - 1) / (a.wPR * GPW);
+            a.wRG = 1; a.nwW = a.wPR;
             threads = (a.aV + 2 * a.aA + 8) * 32;
         } else {
             threads = (a.nwV + 2 * a.nwA + 1) * 32;
@@ -744,11 +839,17 @@ static bool sweep_plan(const Geo &g, int numSMs, bool wrole, bool wta, int maxTh
         a.SW = SWmax; a.nstrips = nstrips; a.R = R; a.NB = NB;
         // ring depths: shrink until the layout fits
         static const int tries[][3] = {{0, 0, 0}, {0, 0, -1}, {0, -1, -1}, {-1, -1, -1}, {-1, -2, -1}, {-2, -2, -1}, {-2, -3, -1}};
+        int wRGwant = wrole ? 7 / a.wPR : 1;              // row groups of the WTA warps: each holds one S slot while it works
+        if (kn.sweepWRG >= 1 && kn.sweepWRG < wRGwant) wRGwant = kn.sweepWRG;
         for (const auto &tr : tries) {
-            a.K = Kwant + tr[0]; a.NSC = NSCwant + tr[1]; a.NSI = NSIwant + tr[2];
+            a.K = Kwant + (kn.sweepK ? 0 : wRGwant - 1) + tr[0]; a.NSC = NSCwant + tr[1]; a.NSI = NSIwant + tr[2];
             if (a.K < 1) a.K = 1;
             if (a.NSC < 2) a.NSC = 2;
             if (a.NSI < 2) a.NSI = 2;
+            if (wrole) {                                  // the path roles keep at least two slots to themselves
+                a.wRG = wRGwant < a.K - 2 ? wRGwant : (a.K - 2 > 1 ? a.K - 2 : 1);
+                a.nwW = a.wPR * a.wRG;
+            }
             const size_t smem = sweep_layout(a, a.nwA * GPW, wta && !wrole);
             if (smem <= (size_t)maxSmem) { *threadsOut = threads; *smemOut = smem; return true; }
         }
@@ -802,6 +903,7 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
     a.dbgStall = SGBM_DBG_HOOK(kn.dbgStall);
     a.nAB = va.inB ? 2 : 1;
     a.urMagic = g.UR < 99 ? 0xFFFFFFFFu / (unsigned)(100 - g.UR) + 1u : 0u;
+    a.P1p = (unsigned)g.P1 * 0x10001u; a.P2mP1p = (unsigned)(g.P2 - g.P1) * 0x10001u;
     const bool wta = va.sout == nullptr;
     if (WROLE && !wta) return 1;
     const int maxThreads = SweepMaxThreads<NREG, WROLE>::value;
@@ -826,8 +928,8 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
         a.traceStrip = a.nstrips / 2;
     }
     if (kn.verbose)
-        fprintf(stderr, "sweep: wrole=%d wta=%d strips=%d SW=%d R=%d NB=%d nwV=%d nwA=%d nwW=%d wPass=%d K=%d NSC=%d NSI=%d threads=%d smem=%zu\n",
-                (int)WROLE, (int)wta, a.nstrips, a.SW, a.R, a.NB, a.nwV, a.nwA, a.nwW, a.wPass, a.K, a.NSC, a.NSI, threads, smem);
+        fprintf(stderr, "sweep: wrole=%d wta=%d strips=%d SW=%d R=%d NB=%d nwV=%d nwA=%d nwW=%d (x%d row groups) wPass=%d K=%d NSC=%d NSI=%d threads=%d smem=%zu\n",
+                (int)WROLE, (int)wta, a.nstrips, a.SW, a.R, a.NB, a.nwV, a.nwA, a.nwW, a.wRG, a.wPass, a.K, a.NSC, a.NSI, threads, smem);
     void *args[] = {&a};
     SGBM_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)kern, dim3(a.nstrips), dim3(threads), args, smem, st));
     sgbm_count_launch(1);
@@ -956,10 +1058,14 @@ static int launch_rowstep_t(const VertArgs &va, cudaStream_t st)
 int sgbm_launch_rowstep(const VertArgs &a, cudaStream_t st)
 {
     const Geo &g = a.g;
+#ifdef SGBM_FAST_BUILD      // development builds: only the lane mappings of the BASELINE configurations (make FAST=1)
+    ROWSTEP_DISPATCH(4, 2) ROWSTEP_DISPATCH(8, 8) ROWSTEP_DISPATCH(12, 8) ROWSTEP_DISPATCH(16, 8)
+#else
     ROWSTEP_DISPATCH(4, 2) ROWSTEP_DISPATCH(4, 4) ROWSTEP_DISPATCH(4, 8) ROWSTEP_DISPATCH(4, 16) ROWSTEP_DISPATCH(4, 32)
     ROWSTEP_DISPATCH(8, 2) ROWSTEP_DISPATCH(8, 4) ROWSTEP_DISPATCH(8, 8) ROWSTEP_DISPATCH(8, 16) ROWSTEP_DISPATCH(8, 32)
     ROWSTEP_DISPATCH(12, 2) ROWSTEP_DISPATCH(12, 4) ROWSTEP_DISPATCH(12, 8) ROWSTEP_DISPATCH(12, 16) ROWSTEP_DISPATCH(12, 32)
     ROWSTEP_DISPATCH(16, 2) ROWSTEP_DISPATCH(16, 4) ROWSTEP_DISPATCH(16, 8) ROWSTEP_DISPATCH(16, 16) ROWSTEP_DISPATCH(16, 32)
+#endif
     return sgbm_fail(-3, "no kernel for lane mapping nreg=%d lpc=%d", g.nreg, g.lpc);
 }
 
@@ -977,9 +1083,13 @@ int sgbm_launch_sweep(const VertArgs &a, int numSMs, cudaStream_t st)
     const int npaths = g.mode == 1 ? 8 : 5;
     bool sat = npaths * (cMax + g.P2) > 65535;
     sat = sat || sgbm_knobs().sweepSat != 0;
+#ifdef SGBM_FAST_BUILD
+    SWEEP_DISPATCH(4, 2) SWEEP_DISPATCH(8, 8) SWEEP_DISPATCH(12, 8) SWEEP_DISPATCH(16, 8)
+#else
     SWEEP_DISPATCH(4, 2) SWEEP_DISPATCH(4, 4) SWEEP_DISPATCH(4, 8) SWEEP_DISPATCH(4, 16) SWEEP_DISPATCH(4, 32)
     SWEEP_DISPATCH(8, 2) SWEEP_DISPATCH(8, 4) SWEEP_DISPATCH(8, 8) SWEEP_DISPATCH(8, 16) SWEEP_DISPATCH(8, 32)
     SWEEP_DISPATCH(12, 2) SWEEP_DISPATCH(12, 4) SWEEP_DISPATCH(12, 8) SWEEP_DISPATCH(12, 16) SWEEP_DISPATCH(12, 32)
     SWEEP_DISPATCH(16, 2) SWEEP_DISPATCH(16, 4) SWEEP_DISPATCH(16, 8) SWEEP_DISPATCH(16, 16) SWEEP_DISPATCH(16, 32)
+#endif
     return 1;
 }
