@@ -108,7 +108,7 @@ struct SgbmKnobs {
     int cost3NXG = 0, cost3RB = 0;       // SGBM_COST3_NXG / _RB
     int nstg = 0;                        // SGBM_NSTG: staging depth of k_vertical
     int sweepSat = 0;                    // SGBM_SWEEP_SAT=1: force the saturating S accumulation
-    int hhSplit = 0;                     // SGBM_HH_SPLIT=1: MODE_HH feeds L_hB into the backward sweep instead of the forward one
+    int hhSplit = 1;                     // SGBM_HH_SPLIT=0: MODE_HH feeds L_hB into the forward sweep instead of the backward one
     int smallD = 1;                      // SGBM_SMALLD=0: do not use the whole-vector-per-lane kernels for small numDisparities
     int verbose = 0;                     // SGBM_VERBOSE: print launch geometries to stderr
     int dbgNoSync = 0, dbgStall = 0;     // SGBM_DBG_NOSYNC / SGBM_DBG_STALL (debug-hook builds only)
