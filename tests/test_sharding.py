@@ -140,3 +140,47 @@ def test_ply_round_trip(tmp_path):
     assert pts.dtype == np.float64 and col.dtype == np.float64 and col.max() <= 1.0
     hdr = open(tmp_path / "a.ply", "rb").read(200).decode("ascii", "ignore")
     assert hdr.startswith("ply\nformat binary_little_endian 1.0") and "property double x" in hdr
+
+
+# ------------------------------------------------------------------------------------------------
+# The optional NCCL exchange of SURVEY 8(e) on real GPUs: runs when >= 2 CUDA devices are visible
+# ------------------------------------------------------------------------------------------------
+def _nccl_worker(rank, world, port, tmp):
+    import stereo_reconstruction_cv_b200 as sg
+    from stereo_reconstruction_cv_b200.synth import make_pair
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        W, H, D, n_frames = 640, 200, 64, 5
+        Q = np.array([[1, 0, 0, -W / 2], [0, 1, 0, -H / 2], [0, 0, 0, 500.0], [0, 0, -1, 0]], np.float64)
+        pairs = [make_pair(W, H, D, seed=70 + i)[:2] for i in range(n_frames)]
+        lefts = torch.from_numpy(np.stack([p[0] for p in pairs])).cuda()
+        rights = torch.from_numpy(np.stack([p[1] for p in pairs])).cuda()
+        st = sg.StereoSGBM_create(minDisparity=0, numDisparities=D, blockSize=5, P1=200, P2=800, disp12MaxDiff=1, preFilterCap=63,
+                                  uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, mode=2)
+        start, stop, disp = sharding.compute_shard(st, lefts, rights, world, rank)       # this rank's block, on this rank's GPU
+        clouds = [sg.reprojectCompact(disp[i], Q, None)[0] for i in range(stop - start)]
+        xyz = torch.cat(clouds, 0) if clouds else torch.empty((0, 3), dtype=torch.float32, device="cuda")
+        gx, _ = sharding.gather_point_cloud(xyz, None, dst=0)                              # NCCL: counts, then padded gather
+        if rank == 0:
+            ref = torch.cat([sg.reprojectCompact(st.compute(lefts[i], rights[i]), Q, None)[0] for i in range(n_frames)], 0)
+            assert gx.is_cuda and gx.shape == ref.shape and bool((gx.view(torch.int32) == ref.view(torch.int32)).all()), \
+                "gathered cloud differs from the single-GPU cloud in global frame order"
+            open(os.path.join(tmp, "ok"), "w").write("%d" % ref.shape[0])
+        else:
+            assert gx is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_nccl_world2_shard_and_gather(tmp_path):
+    """Frames block-sharded over two GPUs, clouds gathered over NCCL: equal to the one-GPU result (main.ipynb:726-737
+    for what is gathered).  Needs two visible devices; on a one-GPU box the gloo test above covers the host logic."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 CUDA devices (run with gpurun --gpus 2)")
+    port = _free_port()
+    mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert int(open(tmp_path / "ok").read()) > 1000
