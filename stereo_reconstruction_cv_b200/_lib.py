@@ -78,7 +78,9 @@ def load(path):
 def lib():
     global _LIB
     if _LIB is None:
-        _LIB = load(LIB_PATH)
+        # SGBM_B200_LIB: development override (an experimental build of the SAME library, e.g. build/exp/...); there is
+        # still no fallback of any kind -- a missing file raises
+        _LIB = load(os.environ.get("SGBM_B200_LIB") or LIB_PATH)
     return _LIB
 
 

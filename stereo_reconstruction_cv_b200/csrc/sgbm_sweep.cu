@@ -204,7 +204,11 @@ __device__ __forceinline__ void ring_advance_n(RingPos &r, int n, uint32_t strid
     if (r.left <= 0) { r.left += depth; r.data -= span; r.bar -= barSpan; r.par ^= 1u; }
 }
 __device__ __forceinline__ void bar_arrive(uint32_t addr) { mbar_arrive(SmemBar{addr}); }
+#ifdef SWEEP_NO_PROBES     // experiment: no early probes, every hand-off is one blocking wait
+__device__ __forceinline__ bool bar_test(uint32_t, uint32_t) { return false; }
+#else
 __device__ __forceinline__ bool bar_test(uint32_t addr, uint32_t parity) { return mbar_test_wait(SmemBar{addr}, parity); }
+#endif
 __device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -485,6 +489,7 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
     constexpr uint32_t WAIT_BAR = FINAL ? BAR_FULLM : BAR_FULLV;
     constexpr uint32_t DONE_BAR = FINAL ? (WROLE ? BAR_FULLW : BAR_FREEP) : BAR_FULLM;
     int kk = 0, n = 0, nm = 0;
+    int hs = 0, hsPrev = 0;                               // n % HS and (n - 1) % HS: halo ring slots of this / the previous super-step
     bool okC = false;                                     // early probe of the row's cost stage
     for (int t = 0; t < nRows; t++) {
         SWEEP_PROG(DIR > 0 ? 1 : 3, rwarp == 0);
@@ -496,16 +501,18 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
             if (hasNbr) {
                 if (restart && lg == 0 && !SGBM_DBG_HOOK(a.dbgNoSync)) {
                     const long long t0 = clock64();
-                    const unsigned int *fl = flagIn + ((n - 1) % HS) * R;
+                    const unsigned int *fl = flagIn + hsPrev * R;
                     while (ld_acquire_u32(fl) < (unsigned)n) {
+#ifndef SWEEP_SPIN_POLL
                         __nanosleep(32);
+#endif
                         if (*reinterpret_cast<volatile unsigned int *>(a.dbg) != 0u) break;
                         if (clock64() - t0 > SWEEP_WAIT_LIMIT) { sweep_timeout(a.dbg, DIR > 0 ? 6 : 7, t); break; }
                     }
                 }
                 __syncwarp();
                 if (restart) {
-                    const uint16_t *h = haloIn + (size_t)((n - 1) % HS) * R * haloStride;
+                    const uint16_t *h = haloIn + (size_t)hsPrev * R * haloStride;
                     load_vec_l2<NREG, LPC>(L, h, lg);
                     m = __ldcg(reinterpret_cast<const unsigned int *>(h + Dp));
                 }
@@ -545,7 +552,7 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
             const int pi = DIR > 0 ? col - (xe - R) : col - xs;
             const bool pub = own && pi >= 0 && pi < R;
             if (pub) {
-                uint16_t *h = haloOut + ((size_t)(n % HS) * R + pi) * haloStride;
+                uint16_t *h = haloOut + ((size_t)hs * R + pi) * haloStride;
                 store_vec<NREG, LPC>(Ln, h, lg);
                 if (lg == 0) *reinterpret_cast<unsigned int *>(h + Dp) = mN;
             }
@@ -554,7 +561,7 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
                 // st.release.gpu is itself a release fence: cumulative over the group's stores, which the
                 // __syncwarp above has ordered before this lane (a separate __threadfence() doubled the
                 // MEMBAR / CCTL.IVALL cost of every publication)
-                st_release_u32(flagOut + (n % HS) * R + pi, (unsigned)(n + 1));
+                st_release_u32(flagOut + hs * R + pi, (unsigned)(n + 1));
             }
         }
         // ---- S slot of this row ---------------------------------------------------------------------
@@ -595,6 +602,8 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
         if (++kk == R) {
             kk = 0; n++;
             if (++nm == NB) nm = 0;
+            hsPrev = hs;
+            if (++hs == HS) hs = 0;
         }
     }
 }
