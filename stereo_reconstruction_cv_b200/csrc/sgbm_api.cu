@@ -153,6 +153,7 @@ static void read_knobs(SgbmKnobs &k)
     k.sweepK = env_int("SGBM_SWEEP_K", 0); k.sweepNSC = env_int("SGBM_SWEEP_NSC", 0);
     k.sweepNSI = env_int("SGBM_SWEEP_NSI", 0); k.sweepNWW = env_int("SGBM_SWEEP_NWW", 0);
     k.sweepWRG = env_int("SGBM_SWEEP_WRG", 0);
+    k.sweepPF = env_int("SGBM_SWEEP_PF", -1);
     k.sweepW = env_int("SGBM_SWEEP_W", 1) != 0;
     k.sweep = env_int("SGBM_SWEEP", 1) != 0;
     k.rowstep = env_int("SGBM_ROWSTEP", 0) != 0;

@@ -100,6 +100,7 @@ struct SgbmKnobs {
     int nreg = 0;                        // SGBM_NREG: force the registers-per-lane of the lane mapping (0 = auto)
     int vr = 0;                          // SGBM_VR: rows per super-step of the sweeps (0 = default)
     int sweepK = 0, sweepNSC = 0, sweepNSI = 0, sweepNWW = 0;   // SGBM_SWEEP_K / _NSC / _NSI / _NWW ring depths, WTA warps per row
+    int sweepPF = -1;                    // SGBM_SWEEP_PF: rows of L2 prefetch ahead of the spilling sweep's bulk copies (-1 = default 8, 0 = off)
     int sweepWRG = 0;                    // SGBM_SWEEP_WRG: cap on the row groups of the WTA warps (0 = as many as fit)
     int sweepW = 1;                      // SGBM_SWEEP_W=0: winner-take-all on role C instead of the W role
     int sweep = 1;                       // SGBM_SWEEP=0: lock-step k_vertical instead of the role-specialised sweep

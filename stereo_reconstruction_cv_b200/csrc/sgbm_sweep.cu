@@ -58,6 +58,8 @@ struct SweepArgs {
     unsigned int *dbg;               // [8] hand-off watchdog: {tripped, strip, warp, wait id, row, ...}, zeroed per launch
     unsigned long long *trace;       // debug: clock64 time stamps of one strip [row][role 4][8] (or null)
     int traceStrip;
+    int pfDist;                      // rows by which the producer's L2 prefetch runs ahead of its bulk copies (0 = off); LAST:
+                                     // the register allocation of the WTA kernels is sensitive to the layout of the fields above
 };
 
 // clock64 time stamps of one strip: compiled in only with -DSGBM_SWEEP_TRACING (make TRACE=1); the
@@ -209,6 +211,13 @@ __device__ __forceinline__ bool bar_test(uint32_t, uint32_t) { return false; }
 #else
 __device__ __forceinline__ bool bar_test(uint32_t addr, uint32_t parity) { return mbar_test_wait(SmemBar{addr}, parity); }
 #endif
+// L2 prefetch of a contiguous global range (no destination, no completion): the producer runs it several rows
+// ahead of the bulk copies, so that the copies are served from L2 -- a prefetch depth that does not cost
+// shared memory the way a deeper staging ring does.
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -248,6 +257,51 @@ __device__ __forceinline__ void sweep_producer(const SweepArgs &a, const SweepSm
         if (srcB) srcB += rowStep;
     }
 }
+
+// The same with an L2 prefetch a.pfDist rows ahead: the producer of the spilling (forward) sweep of MODE_HH, whose
+// speed follows the depth of its cost ring.  Kept apart from sweep_producer on purpose: in the winner-take-all
+// kernels the producer lives in the 40-register warpgroup, and any growth of its code showed up as spills there
+// (cfg3 WTA sweep 3.20 -> 3.37 ms).
+__device__ __forceinline__ void sweep_producer_pf(const SweepArgs &a, const SweepSmem &s, int xs, int xe, int yBegin,
+                                               int yStep, int nRows)
+{
+    const Geo &g = a.g;
+    const int Dp = g.Dp, HG = a.R - 1;
+    const int scol0 = xs - HG;
+    const int clo = max(scol0, 0), chi = min(xe + HG, g.W1);
+    const uint32_t colB = a.colB;
+    const uint32_t bytesC = (uint32_t)(chi - clo) * colB, bytesI = (uint32_t)(xe - xs) * colB;
+    RingPos rc = ring_start(s.aC + (uint32_t)(clo - scol0) * colB, s.barC, a.NSC);
+    RingPos ri = ring_start(s.aI, s.barI, a.NSI);
+    const uint16_t *srcC = a.C + (size_t)yBegin * g.rowStride + (size_t)clo * Dp;
+    const uint16_t *srcA = a.inA + (size_t)yBegin * g.rowStride + (size_t)xs * Dp;
+    const uint16_t *srcB = a.nAB > 1 ? a.inB + (size_t)yBegin * g.rowStride + (size_t)xs * Dp : nullptr;
+    const long long rowStep = (long long)yStep * g.rowStride;
+    const int pf = a.pfDist;
+    const long long pfOff = (long long)pf * rowStep;
+    for (int t = 0; t < nRows; t++) {
+        if (pf > 0 && t + pf < nRows) {
+            bulk_prefetch_l2(srcC + pfOff, bytesC);
+            bulk_prefetch_l2(srcA + pfOff, bytesI);
+            if (srcB) bulk_prefetch_l2(srcB + pfOff, bytesI);
+        }
+        SWEEP_TR(3, 0, true);
+        if (t >= a.NSC) sweep_wait(a, SmemBar{rc.bar + BAR_EMPTY}, rc.par ^ 1u, 1, t);
+        SWEEP_TR(3, 1, true);
+        mbar_expect_tx(SmemBar{rc.bar + BAR_FULL}, bytesC);
+        bulk_g2s_a(rc.data, srcC, bytesC, rc.bar + BAR_FULL);
+        if (t >= a.NSI) sweep_wait(a, SmemBar{ri.bar + BAR_EMPTY}, ri.par ^ 1u, 2, t);
+        mbar_expect_tx(SmemBar{ri.bar + BAR_FULL}, bytesI * (uint32_t)a.nAB);
+        bulk_g2s_a(ri.data, srcA, bytesI, ri.bar + BAR_FULL);
+        if (srcB) bulk_g2s_a(ri.data + a.iBB, srcB, bytesI, ri.bar + BAR_FULL);
+        SWEEP_TR(3, 2, true);
+        ring_advance(rc, a.cStrideB, a.cSpanB, 16u, a.cBarSpan, a.NSC);
+        ring_advance(ri, a.iStrideB, a.iSpanB, 16u, a.iBarSpan, a.NSI);
+        srcC += rowStep; srcA += rowStep;
+        if (srcB) srcB += rowStep;
+    }
+}
+
 
 // S accumulation: saturating (A.4) unless the host proved that the sum of all paths fits 16 bits, in
 // which case plain adds are exact and the clamp to 32767 is applied once when the pixel is finished.
@@ -779,7 +833,7 @@ __global__ void __launch_bounds__((SweepMaxThreads<NREG, WROLE>::value), 1) k_sw
     } else if (warp < a.nwV + 2 * a.nwA) {
         sweep_role_diag<NREG, LPC, -1, SAT, false>(a, s, warp - a.nwV - a.nwA, strip, xs, xe, yBegin, yStep, nRows);
     } else if ((threadIdx.x & 31) == 0) {
-        sweep_producer(a, s, xs, xe, yBegin, yStep, nRows);
+        sweep_producer_pf(a, s, xs, xe, yBegin, yStep, nRows);
     }
 }
 
@@ -912,6 +966,7 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
     a.dbgStall = SGBM_DBG_HOOK(kn.dbgStall);
     a.nAB = va.inB ? 2 : 1;
     a.urMagic = g.UR < 99 ? 0xFFFFFFFFu / (unsigned)(100 - g.UR) + 1u : 0u;
+    a.pfDist = kn.sweepPF >= 0 ? kn.sweepPF : 8;
     a.P1p = (unsigned)g.P1 * 0x10001u; a.P2mP1p = (unsigned)(g.P2 - g.P1) * 0x10001u;
     const bool wta = va.sout == nullptr;
     if (WROLE && !wta) return 1;
