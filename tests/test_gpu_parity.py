@@ -304,6 +304,25 @@ def test_kernel_generations_agree(sg, monkeypatch, env):
         assert _mismatch(sg.StereoSGBM_create(**_kw(p)).compute(l, r), oracle.compute(p, l, r)) == 0, (env, mode)
 
 
+@pytest.mark.parametrize("env", [{"SGBM_SWEEP_WRG": "1"}, {"SGBM_SWEEP_WRG": "2"}, {"SGBM_SWEEP_NWW": "1"}, {"SGBM_HH_SPLIT": "0"},
+                                 {"SGBM_SWEEP_PF": "0"}, {"SGBM_SWEEP_PF": "3"}, {"SGBM_SWEEP_K": "3", "SGBM_SWEEP_NSC": "2"},
+                                 {"SGBM_SWEEP_K": "8", "SGBM_SWEEP_NSI": "2"}, {"SGBM_VR": "16"}, {"SGBM_VR": "12", "SGBM_SWEEP_WRG": "3"}])
+def test_sweep_schedule_knobs(sg, monkeypatch, env):
+    """The round-2 schedule options of the sweeps -- row groups of the winner-take-all warps, warps per row, where MODE_HH
+    reads L_hB, the producer's L2 prefetch distance, ring depths, 12 / 16 rows per super-step -- never change a bit: narrow
+    strips (many row groups) and wide ones, few and many disparities, saturating and plain accumulation, three frames each."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for (W, H, D, bs, P1, P2) in [(1200, 90, 64, 5, 200, 800), (2600, 70, 16, 11, 2904, 11616), (500, 100, 128, 3, 72, 288)]:
+        l, r, _ = make_pair(W, H, D, seed=W)
+        for mode in (0, 1):
+            p = OracleParams(0, D, bs, P1, P2, 1, 63, 10, 100, 32, mode)
+            ref = oracle.compute(p, l, r)
+            st = sg.StereoSGBM_create(**_kw(p))
+            for rep in range(3):
+                assert _mismatch(st.compute(l, r), ref) == 0, (env, W, D, mode, rep)
+
+
 @pytest.mark.parametrize("R", [8, 2])
 def test_repeatability_under_load(sg, monkeypatch, R):
     """Strip hand-offs and role hand-offs are timing dependent: 150 back-to-back frames of a
