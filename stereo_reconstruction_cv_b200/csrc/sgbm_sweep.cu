@@ -535,21 +535,35 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
     const int NSC = a.NSC, K = a.K;
     const LaneMasks lm = lane_masks(lg, lastLane);
     const uint32_t lane0 = sm_keep(lane == 0 ? 1u : 0u);
-    // this lane's chunk of column 0 of stage 0 of the cost ring / of slot 0 of the S ring, ring geometry in bytes
+    // this lane's chunk of column 0 of stage 0 of the cost ring / of slot 0 of the S ring
     const uint32_t colB = a.colB;
     RingPos rc = ring_start(s.aC + 16u * (uint32_t)lg, s.barC, NSC);
     RingPos rp = ring_start(s.aP + 16u * (uint32_t)lg, s.barP, K);
     // WROLE: the finished S goes back into the slot and the winner-take-all warps release it
     constexpr uint32_t WAIT_BAR = FINAL ? BAR_FULLM : BAR_FULLV;
     constexpr uint32_t DONE_BAR = FINAL ? (WROLE ? BAR_FULLW : BAR_FREEP) : BAR_FULLM;
-    int kk = 0, n = 0, nm = 0;
+    // Column bookkeeping in window coordinates: q = column - (xs - HG) is the group's place in the staged cost row
+    // (q = p for the path that moves right, q = WW - 1 - p for the one that moves left).  Everything the row loop asks
+    // about the column is an unsigned range test on q against per-thread constants made opaque once:
+    //   active  <=>  q - aLo < aLen      (the chain is inside the strip + its incoming halo, and inside the image)
+    //   own     <=>  active and q - HG < SWs
+    const int SWs = xe - xs, WW = SWs + 2 * HG;
+    int aLoI, aHiI;
+    if (DIR > 0) { aLoI = max(0, HG - xs); aHiI = HG + SWs; }            // col >= 0, col < xe
+    else { aLoI = HG; aHiI = min(WW, g.W1 - xs + HG); }                  // col >= xs, col < W1
+    const uint32_t aLo = sm_keep((uint32_t)aLoI), aLen = sm_keep(exists && aHiI > aLoI ? (uint32_t)(aHiI - aLoI) : 0u);
+    const uint32_t hgU = (uint32_t)HG, swsU = (uint32_t)SWs;
+    // strips at the image border: the chain enters the image when col <= 0 (col >= W1 - 1): predecessor outside
+    const uint32_t edge = sm_keep(hasNbr ? 0u : 1u);
+    const int edgeQ = DIR > 0 ? HG - xs : g.W1 - 1 - xs + HG;            // q of column 0 / column W1 - 1
+    const uint32_t pubOn = sm_keep(canPub ? 1u : 0u);
+    const int pubQ0 = DIR > 0 ? HG + SWs - R : HG;                      // q of the first published column
     int hs = 0, hsPrev = 0;                               // n % HS and (n - 1) % HS: halo ring slots of this / the previous super-step
+    int nm = 0, tq = 0;                                   // tq: first row of the current super-step
     bool okC = false;                                     // early probe of the row's cost stage
-    for (int t = 0; t < nRows; t++) {
-        SWEEP_PROG(DIR > 0 ? 1 : 3, rwarp == 0);
-        SWEEP_PROG(DIR > 0 ? 2 : 4, rwarp == a.nwA - 1);
+    for (int n = 0; tq < nRows; n++) {
         // ---- super-step start: batch nm restarts from the neighbour's published columns -------------
-        if (kk == 0 && t > 0) {
+        if (n > 0) {
             const bool restart = exists && nm == b;
             if (restart) p = i;
             if (hasNbr) {
@@ -561,7 +575,7 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
                         __nanosleep(32);
 #endif
                         if (*reinterpret_cast<volatile unsigned int *>(a.dbg) != 0u) break;
-                        if (clock64() - t0 > SWEEP_WAIT_LIMIT) { sweep_timeout(a.dbg, DIR > 0 ? 6 : 7, t); break; }
+                        if (clock64() - t0 > SWEEP_WAIT_LIMIT) { sweep_timeout(a.dbg, DIR > 0 ? 6 : 7, tq); break; }
                     }
                 }
                 __syncwarp();
@@ -576,89 +590,94 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
                 m = 0;
             }
         }
-        const int col = DIR > 0 ? xs - HG + p : xe - 1 + HG - p;
-        const bool active = exists && (DIR > 0 ? col < xe : col >= xs) && col >= 0 && col < g.W1;
-        const bool own = active && col >= xs && col < xe;
-        const int sidx = active ? col - (xs - HG) : HG;
-        if (!hasNbr && (DIR > 0 ? col <= 0 : col >= g.W1 - 1)) {   // chain enters the image: predecessor outside
+        const int rowsHere = min(R, nRows - tq);
+        const bool pubStep = pubOn && tq + R < nRows;     // a full super-step that is not the image's last rows
+        int q = DIR > 0 ? p : WW - 1 - p;
+        // (rl counts the rows left in the super-step; the row index t = tq + rowsHere - rl is only needed off the hot path)
+        for (int rl = rowsHere; rl > 0; rl--) {
+#if defined(SGBM_SWEEP_TRACING)
+            const int t = tq + rowsHere - rl;
+#endif
+            SWEEP_PROG(DIR > 0 ? 1 : 3, rwarp == 0);
+            SWEEP_PROG(DIR > 0 ? 2 : 4, rwarp == a.nwA - 1);
+            const bool active = (uint32_t)q - aLo < aLen;
+            const bool own = active && (uint32_t)q - hgU < swsU;
+            if (edge && (DIR > 0 ? q <= edgeQ : q >= edgeQ)) {   // chain enters the image: predecessor outside
 #pragma unroll
-            for (int j = 0; j < NREG; j++) L[j] = 0;
-            m = 0;
-        }
-        SWEEP_TR(DIR > 0 ? 1 : 2, 0, rwarp == a.nwA / 2);
-        if (!okC) sweep_wait(a, SmemBar{rc.bar + BAR_FULL}, rc.par, DIR > 0 ? 8 : 9, t);
-        SWEEP_TR(DIR > 0 ? 1 : 2, 1, rwarp == a.nwA / 2);
-        const bool okS = bar_test(rp.bar + WAIT_BAR, rp.par);   // latency hides behind the path step
-        if (__any_sync(0xFFFFFFFFu, active)) {           // inactive groups compute garbage that is never used
-            uint32_t Cc[NREG];
-            lds_vec<NREG, LPC>(Cc, rc.data + (uint32_t)sidx * colB);
-            m = path_step_m<NREG, LPC>(L, m, Cc, a.P1p, a.P2mP1p, lm);
-        }
-        // the cost row is in registers: hand the stage back and look at the next one
-        __syncwarp();
-        if (lane0) bar_arrive(rc.bar + BAR_EMPTY);
-        ring_advance(rc, a.cStrideB, a.cSpanB, 16u, a.cBarSpan, NSC);
-        okC = bar_test(rc.bar + BAR_FULL, rc.par);
-        const uint32_t mN = m;
-        const uint32_t (&Ln)[NREG] = L;
-        // ---- super-step end: publish the columns the neighbour continues ----------------------------
-        if (kk == R - 1 && canPub && t + 1 < nRows) {
-            const int pi = DIR > 0 ? col - (xe - R) : col - xs;
-            const bool pub = own && pi >= 0 && pi < R;
-            if (pub) {
-                uint16_t *h = haloOut + ((size_t)hs * R + pi) * haloStride;
-                store_vec<NREG, LPC>(Ln, h, lg);
-                if (lg == 0) *reinterpret_cast<unsigned int *>(h + Dp) = mN;
+                for (int j = 0; j < NREG; j++) L[j] = 0;
+                m = 0;
+            }
+            SWEEP_TR(DIR > 0 ? 1 : 2, 0, rwarp == a.nwA / 2);
+            if (!okC) sweep_wait(a, SmemBar{rc.bar + BAR_FULL}, rc.par, DIR > 0 ? 8 : 9, tq);
+            SWEEP_TR(DIR > 0 ? 1 : 2, 1, rwarp == a.nwA / 2);
+            const bool okS = bar_test(rp.bar + WAIT_BAR, rp.par);   // latency hides behind the path step
+            if (__any_sync(0xFFFFFFFFu, active)) {       // inactive groups compute garbage that is never used
+                uint32_t Cc[NREG];
+                lds_vec<NREG, LPC>(Cc, rc.data + (active ? (uint32_t)q : hgU) * colB);
+                m = path_step_m<NREG, LPC>(L, m, Cc, a.P1p, a.P2mP1p, lm);
+            }
+            // the cost row is in registers: hand the stage back and look at the next one
+            __syncwarp();
+            if (lane0) bar_arrive(rc.bar + BAR_EMPTY);
+            ring_advance(rc, a.cStrideB, a.cSpanB, 16u, a.cBarSpan, NSC);
+            okC = bar_test(rc.bar + BAR_FULL, rc.par);
+            // ---- super-step end: publish the columns the neighbour continues ------------------------
+            if (pubStep && rl == 1) {
+                const int pi = q - pubQ0;
+                const bool pub = own && pi >= 0 && pi < R;
+                if (pub) {
+                    uint16_t *h = haloOut + ((size_t)hs * R + pi) * haloStride;
+                    store_vec<NREG, LPC>(L, h, lg);
+                    if (lg == 0) *reinterpret_cast<unsigned int *>(h + Dp) = m;
+                }
+                __syncwarp();
+                if (pub && lg == 0) {
+                    // st.release.gpu is itself a release fence: cumulative over the group's stores, which the
+                    // __syncwarp above has ordered before this lane (a separate __threadfence() doubled the
+                    // MEMBAR / CCTL.IVALL cost of every publication)
+                    st_release_u32(flagOut + hs * R + pi, (unsigned)(n + 1));
+                }
+            }
+            // ---- S slot of this row -----------------------------------------------------------------
+            SWEEP_TR(DIR > 0 ? 1 : 2, 2, rwarp == a.nwA / 2);
+            if (!okS) sweep_wait(a, SmemBar{rp.bar + WAIT_BAR}, rp.par, DIR > 0 ? 10 : 11, tq);
+            SWEEP_TR(DIR > 0 ? 1 : 2, 3, rwarp == a.nwA / 2);
+            uint32_t S[NREG];
+            if (own) {
+                const uint32_t ps = rp.data + ((uint32_t)q - hgU) * colB;
+                lds_vec<NREG, LPC>(S, ps);
+#pragma unroll
+                for (int j = 0; j < NREG; j++) S[j] = sacc<SAT>(S[j], L[j]);
+                if (!FINAL || WROLE) sts_vec<NREG, LPC>(S, ps);
+            } else if (FINAL && !WROLE) {
+#pragma unroll
+                for (int j = 0; j < NREG; j++) S[j] = SGBM_MAX_S;
             }
             __syncwarp();
-            if (pub && lg == 0) {
-                // st.release.gpu is itself a release fence: cumulative over the group's stores, which the
-                // __syncwarp above has ordered before this lane (a separate __threadfence() doubled the
-                // MEMBAR / CCTL.IVALL cost of every publication)
-                st_release_u32(flagOut + hs * R + pi, (unsigned)(n + 1));
-            }
-        }
-        // ---- S slot of this row ---------------------------------------------------------------------
-        SWEEP_TR(DIR > 0 ? 1 : 2, 2, rwarp == a.nwA / 2);
-        if (!okS) sweep_wait(a, SmemBar{rp.bar + WAIT_BAR}, rp.par, DIR > 0 ? 10 : 11, t);
-        SWEEP_TR(DIR > 0 ? 1 : 2, 3, rwarp == a.nwA / 2);
-        uint32_t S[NREG];
-        if (own) {
-            const uint32_t ps = rp.data + (uint32_t)(col - xs) * colB;
-            lds_vec<NREG, LPC>(S, ps);
+            if (lane0) bar_arrive(rp.bar + DONE_BAR);
+            SWEEP_TR(DIR > 0 ? 1 : 2, 4, rwarp == a.nwA / 2);
+            if (FINAL && !WROLE && __any_sync(0xFFFFFFFFu, own)) {
+                const int y = yBegin + (tq + rowsHere - rl) * yStep;
+                const int x1 = own ? xs - HG + q : xs;
+                if (a.sout) {
+                    if (own) store_vec<NREG, LPC>(S, a.sout + (size_t)y * g.rowStride + (size_t)x1 * Dp, lg);
+                } else {
+                    if (!SAT) {
 #pragma unroll
-            for (int j = 0; j < NREG; j++) S[j] = sacc<SAT>(S[j], Ln[j]);
-            if (!FINAL || WROLE) sts_vec<NREG, LPC>(S, ps);
-        } else if (FINAL && !WROLE) {
-#pragma unroll
-            for (int j = 0; j < NREG; j++) S[j] = SGBM_MAX_S;
-        }
-        __syncwarp();
-        if (lane0) bar_arrive(rp.bar + DONE_BAR);
-        SWEEP_TR(DIR > 0 ? 1 : 2, 4, rwarp == a.nwA / 2);
-        if (FINAL && !WROLE && __any_sync(0xFFFFFFFFu, own)) {
-            const int y = yBegin + t * yStep;
-            const int x1 = own ? col : xs;
-            if (a.sout) {
-                if (own) store_vec<NREG, LPC>(S, a.sout + (size_t)y * g.rowStride + (size_t)x1 * Dp, lg);
-            } else {
-                if (!SAT) {
-#pragma unroll
-                    for (int j = 0; j < NREG; j++) S[j] = pmin(S[j], SGBM_MAX_S);
+                        for (int j = 0; j < NREG; j++) S[j] = pmin(S[j], SGBM_MAX_S);
+                    }
+                    if (a.sdbg && own) store_vec<NREG, LPC>(S, a.sdbg + (size_t)y * g.rowStride + (size_t)x1 * Dp, lg);
+                    sweep_wta<NREG, LPC>(a, S, ssm, lg, own, x1, y);
                 }
-                if (a.sdbg && own) store_vec<NREG, LPC>(S, a.sdbg + (size_t)y * g.rowStride + (size_t)x1 * Dp, lg);
-                sweep_wta<NREG, LPC>(a, S, ssm, lg, own, x1, y);
             }
+            SWEEP_TR(DIR > 0 ? 1 : 2, 5, rwarp == a.nwA / 2);
+            q += DIR;
+            ring_advance(rp, a.pStrideB, a.pSpanB, 32u, a.pBarSpan, K);
         }
-        SWEEP_TR(DIR > 0 ? 1 : 2, 5, rwarp == a.nwA / 2);
-        p++;
-        ring_advance(rp, a.pStrideB, a.pSpanB, 32u, a.pBarSpan, K);
-        if (++kk == R) {
-            kk = 0; n++;
-            if (++nm == NB) nm = 0;
-            hsPrev = hs;
-            if (++hs == HS) hs = 0;
-        }
+        p += rowsHere; tq += rowsHere;
+        if (++nm == NB) nm = 0;
+        hsPrev = hs;
+        if (++hs == HS) hs = 0;
     }
 }
 
