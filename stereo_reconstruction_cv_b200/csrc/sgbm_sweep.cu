@@ -560,6 +560,11 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
     const int pubQ0 = DIR > 0 ? HG + SWs - R : HG;                      // q of the first published column
     int hs = 0, hsPrev = 0;                               // n % HS and (n - 1) % HS: halo ring slots of this / the previous super-step
     int nm = 0, tq = 0;                                   // tq: first row of the current super-step
+    // spilling sweep: byte pointer to this lane's chunk of column xs - HG of the current output row (advanced per row,
+    // so that the store address is one multiply-add instead of two 64-bit products)
+    char *soutRow = (FINAL && !WROLE && a.sout)
+                        ? reinterpret_cast<char *>(a.sout) + ((long long)yBegin * g.rowStride + (long long)(xs - HG) * Dp) * 2 + 16 * lg : nullptr;
+    const long long soutStep = (long long)yStep * g.rowStride * 2;
     bool okC = false;                                     // early probe of the row's cost stage
     for (int n = 0; tq < nRows; n++) {
         // ---- super-step start: batch nm restarts from the neighbour's published columns -------------
@@ -660,7 +665,11 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
                 const int y = yBegin + (tq + rowsHere - rl) * yStep;
                 const int x1 = own ? xs - HG + q : xs;
                 if (a.sout) {
-                    if (own) store_vec<NREG, LPC>(S, a.sout + (size_t)y * g.rowStride + (size_t)x1 * Dp, lg);
+                    if (own) {
+                        uint4 *po = reinterpret_cast<uint4 *>(soutRow + (size_t)((uint32_t)q * colB));
+#pragma unroll
+                        for (int k4 = 0; k4 < NREG / 4; k4++) po[LPC * k4] = make_uint4(S[4 * k4 + 0], S[4 * k4 + 1], S[4 * k4 + 2], S[4 * k4 + 3]);
+                    }
                 } else {
                     if (!SAT) {
 #pragma unroll
@@ -672,6 +681,7 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
             }
             SWEEP_TR(DIR > 0 ? 1 : 2, 5, rwarp == a.nwA / 2);
             q += DIR;
+            if (FINAL && !WROLE) soutRow += soutStep;
             ring_advance(rp, a.pStrideB, a.pSpanB, 32u, a.pBarSpan, K);
         }
         p += rowsHere; tq += rowsHere;
