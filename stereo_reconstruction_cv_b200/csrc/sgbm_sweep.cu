@@ -328,8 +328,8 @@ __device__ __forceinline__ uint32_t path_step_m(uint32_t (&L)[NREG], uint32_t mp
 {
     const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, L[NREG - 1], 1, LPC) | lm.up;
     const uint32_t dn = __shfl_down_sync(0xFFFFFFFFu, L[0], 1, LPC) | lm.dn;
-    const uint32_t k1 = mp + P2mP1p;                       // (m + P2 - P1) in both halves, no carry (<= 65535)
     uint32_t sPrev = __byte_perm(up, L[0], 0x5432);        // (L[2j-1], L[2j]) for j = 0
+    const uint32_t k1 = mp + P2mP1p;                       // (m + P2 - P1) in both halves, no carry (<= 65535)
 #pragma unroll
     for (int j = 0; j < NREG; j++) {
         const uint32_t nxt = (j + 1 < NREG) ? L[j + 1] : dn;
@@ -892,11 +892,13 @@ static bool sweep_plan(const Geo &g, int numSMs, bool wrole, bool wta, int maxTh
                        size_t *smemOut)
 {
     const int GPW = 32 / g.lpc;
-    // Rows per super-step (every value is covered by tests/test_gpu_parity.py::test_sweep_rows_per_superstep
-    // and a repeatability run; 8 is the fastest at every size measured).
+    // Rows per super-step (1..8 are covered by tests/test_gpu_parity.py::test_sweep_rows_per_superstep and a repeatability
+    // run, 12 / 16 by test_sweep_schedule_knobs).  8 is the fastest with 4 or more lanes per column; with two lanes per
+    // column (numDisparities <= 32) a warp holds 16 column groups, the halo chains of 16 rows per super-step cost no extra
+    // warps, and half as many strip hand-offs win (4K D=16: 1.37 -> 1.18 ms).
     const int Rmin = 1;
     const SgbmKnobs &kn = sgbm_knobs();
-    int R = 8;
+    int R = g.lpc <= 2 ? 16 : 8;
     if (kn.vr > 0) R = kn.vr >= Rmin ? kn.vr : Rmin;
     if (R > 16) R = 16;
     int Kwant = 5, NSCwant = 5, NSIwant = 3;
