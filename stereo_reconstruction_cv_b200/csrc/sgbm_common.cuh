@@ -292,6 +292,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// The same on a barrier named by its shared address.
+__device__ __forceinline__ void mbar_wait(SmemBar bar, uint32_t parity)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .u32 n;\n\t"
+        "mov.u32 n, 0;\n"
+        "SGBM_WAITA:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
+        "@p bra SGBM_DONEA;\n\t"
+        "add.u32 n, n, 1;\n\t"
+        "setp.lt.u32 p, n, 8192;\n\t"
+        "@p bra SGBM_WAITA;\n\t"
+        "trap;\n"
+        "SGBM_DONEA:\n\t"
+        "}" ::"r"(bar.addr), "r"(parity) : "memory");
+}
+
 // One step of the SGM recurrence (A.4) for one column, distributed over a group of LPC lanes:
 //   Ln(d) = C(d) + min(Lp(d), Lp(d-1)+P1, Lp(d+1)+P1, m+P2) - m,   m = min_k Lp(k)
 // Lp / mp : predecessor's path costs and their (packed, broadcast) minimum.
@@ -320,6 +340,40 @@ __device__ __forceinline__ uint32_t path_step(uint32_t (&Ln)[NREG], const uint32
     uint32_t t = local_min<NREG>(Ln);
     if (lg > lastLane) t = SGBM_INF2;
     return group_min<LPC>(t);
+}
+
+// OR-masks of a lane inside its group: all ones where the disparity neighbour below / above the lane's
+// range is outside [0, D) (L(-1) = L(D) = +inf, A.4) and where the whole lane is padding.  Held in registers
+// (made opaque once) so that the row loop does not re-derive them from the thread id.
+struct LaneMasks { uint32_t up, dn, pad; };
+__device__ __forceinline__ LaneMasks lane_masks(int lg, int lastLane)
+{
+    LaneMasks m;
+    m.up = sm_keep(lg == 0 ? 0xFFFFFFFFu : 0u);
+    m.dn = sm_keep(lg >= lastLane ? 0xFFFFFFFFu : 0u);
+    m.pad = sm_keep(lg > lastLane ? 0xFFFFFFFFu : 0u);
+    return m;
+}
+
+// path_step above, in place, with the lane masks instead of per-step comparisons (the row loops of the sweeps and the
+// column loop of the horizontal kernel).
+template <int NREG, int LPC>
+__device__ __forceinline__ uint32_t path_step_m(uint32_t (&L)[NREG], uint32_t mp, const uint32_t (&C)[NREG], uint32_t P1p,
+                                                uint32_t P2mP1p, const LaneMasks &lm)
+{
+    const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, L[NREG - 1], 1, LPC) | lm.up;
+    const uint32_t dn = __shfl_down_sync(0xFFFFFFFFu, L[0], 1, LPC) | lm.dn;
+    uint32_t sPrev = __byte_perm(up, L[0], 0x5432);        // (L[2j-1], L[2j]) for j = 0
+    const uint32_t k1 = mp + P2mP1p;                       // (m + P2 - P1) in both halves, no carry (<= 65535)
+#pragma unroll
+    for (int j = 0; j < NREG; j++) {
+        const uint32_t nxt = (j + 1 < NREG) ? L[j + 1] : dn;
+        const uint32_t sNext = __byte_perm(L[j], nxt, 0x5432);
+        const uint32_t b = paddmin(pmin3(sPrev, sNext, k1), P1p, L[j]);
+        L[j] = b + C[j] - mp;
+        sPrev = sNext;
+    }
+    return group_min<LPC>(local_min<NREG>(L) | lm.pad);
 }
 
 // A multiply-add by an opaque +-1 (a kernel argument the compiler cannot fold) is an IMAD and issues on the

@@ -19,83 +19,121 @@
 // columns per staging chunk: ~8 KB per warp and stage (4 columns at 8 lanes x 16 registers, 16 at 2 x 4)
 template <int NREG, int LPC> struct HzK {
     static const int raw = 4096 / ((32 / LPC) * 2 * NREG * LPC);
-    static const int value = raw < 4 ? 4 : (raw > 16 ? 16 : raw);
+    static const int value = (raw < 4 ? 4 : (raw > 16 ? 16 : raw)) & ~1;   // even: the column loop is unrolled in pairs
 };
 #define HZ_NS 3                      // chunks in flight per warp
 
 // One lane group per image row and direction.  The cost rows are streamed through a per-warp ring
 // of HZ_NS shared-memory stages filled by TMA bulk copies (one contiguous K-column segment per
 // row), so HBM latency is covered by data in flight instead of registers.
-template <int NREG, int LPC>
-__global__ void __launch_bounds__(HZ_THREADS) k_horizontal(Geo g, const uint16_t *__restrict__ C,
-                                                           uint16_t *__restrict__ LhA,
-                                                           uint16_t *__restrict__ LhB, int y0, int nrows)
+// At 4K / D = 256 the kernel is HBM-bound (92 % of the copy peak); with few rows or few disparities it is a pure
+// latency chain of W1 dependent path steps per warp, so the per-column code is kept minimal: the direction is a
+// template parameter, the staged column and the output pointer advance by constants, the next column's cost vector is
+// loaded before the current path step, and the GPW bulk copies of a refill are issued by GPW lanes at once.
+template <int NREG, int LPC, int DIR>
+__device__ __forceinline__ void horizontal_dir(const Geo &g, const uint16_t *__restrict__ C, uint16_t *__restrict__ Lh, int y0,
+                                               int nrows, uint8_t *smem)
 {
-    extern __shared__ __align__(128) uint8_t smem[];
     constexpr int GPW = 32 / LPC;                         // lane groups (rows) per warp
     constexpr int NW = HZ_THREADS / 32;
     constexpr int HZ_K = HzK<NREG, LPC>::value;
+    constexpr int DP = 2 * NREG * LPC;                    // == g.Dp for this lane mapping (sgbm_api.cu make_geo)
+    constexpr uint32_t COLB = 2u * DP;                    // bytes per column vector
+    constexpr int STEPB = DIR ? -(int)COLB : (int)COLB;   // walking direction in bytes, staged and in the volume
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / LPC, lg = lane % LPC;
-    const int W1 = g.W1, Dp = g.Dp, lastLane = g.lanesUsed - 1;
+    const int W1 = g.W1;
     const int rowBase = y0 + (blockIdx.x * NW + warp) * GPW;
     const int rowEnd = y0 + nrows;
     if (rowBase >= rowEnd) return;                        // whole warp idle (warp-uniform)
     int row = rowBase + grp;
     const bool act = row < rowEnd;
     if (!act) row = rowEnd - 1;                           // keep the warp convergent, no stores
-    const int dir = blockIdx.y;                           // 0: predecessor (-1,0), 1: predecessor (+1,0)
-    uint16_t *orow = (dir ? LhB : LhA) + (size_t)row * g.rowStride;
-    const uint32_t P1p = (uint32_t)g.P1 * 0x10001u, P2mP1p = (uint32_t)(g.P2 - g.P1) * 0x10001u;
+    const uint32_t P1p = sm_keep((uint32_t)g.P1 * 0x10001u), P2mP1p = sm_keep((uint32_t)(g.P2 - g.P1) * 0x10001u);
+    const LaneMasks lm = lane_masks(lg, g.lanesUsed - 1);
 
-    const size_t stageElems = (size_t)GPW * HZ_K * Dp;
-    uint16_t *wbuf = reinterpret_cast<uint16_t *>(smem) + (size_t)warp * HZ_NS * stageElems;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)NW * HZ_NS * stageElems * 2) + warp * HZ_NS;
+    constexpr uint32_t stageB = (uint32_t)GPW * HZ_K * COLB;
+    const uint32_t wbufA = smem_u32(smem) + (uint32_t)warp * HZ_NS * stageB;
+    const SmemBar bars{smem_u32(smem) + (uint32_t)NW * HZ_NS * stageB + (uint32_t)warp * HZ_NS * 8u};
     if (lane == 0) {
-        for (int i = 0; i < HZ_NS; i++) mbar_init(&bars[i], 1);
+        for (int i = 0; i < HZ_NS; i++) mbar_init(bars[i], 1);
         mbar_fence_init();
     }
     __syncwarp();
     const int nchunks = (W1 + HZ_K - 1) / HZ_K;
-    auto fill = [&](int ci) {                             // lane 0: chunk ci -> stage ci % HZ_NS
+    // refill of stage ci % HZ_NS with chunk ci: lane 0 arms the barrier, then lanes 0 .. GPW-1 issue one row's copy each
+    const int fr = min(rowBase + (lane < GPW ? lane : 0), rowEnd - 1);
+    const uint16_t *frow = C + (size_t)fr * g.rowStride;
+    auto fill = [&](int ci) {
         const int st = ci % HZ_NS;
         const int s0 = ci * HZ_K, kc = min(HZ_K, W1 - s0);
-        const int xlo = dir ? (W1 - s0 - kc) : s0;        // first (lowest) column of the chunk
-        const uint32_t bytes = (uint32_t)kc * Dp * 2;
-        mbar_expect_tx(&bars[st], bytes * GPW);
-        for (int q = 0; q < GPW; q++) {
-            const int r = min(rowBase + q, rowEnd - 1);
-            bulk_g2s(wbuf + st * stageElems + (size_t)q * HZ_K * Dp, C + (size_t)r * g.rowStride + (size_t)xlo * Dp,
-                     bytes, &bars[st]);
-        }
+        const int xlo = DIR ? (W1 - s0 - kc) : s0;        // first (lowest) column of the chunk
+        const uint32_t bytes = (uint32_t)kc * COLB;
+        if (lane == 0) mbar_expect_tx(bars[st], bytes * GPW);
+        __syncwarp();
+        if (lane < GPW)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(wbufA + (uint32_t)st * stageB + (uint32_t)lane * HZ_K * COLB), "l"(frow + (size_t)xlo * DP), "r"(bytes),
+                           "r"(bars[st].addr) : "memory");
     };
-    if (lane == 0)
-        for (int ci = 0; ci < HZ_NS && ci < nchunks; ci++) fill(ci);
+    for (int ci = 0; ci < HZ_NS && ci < nchunks; ci++) fill(ci);
 
     uint32_t L[NREG], m = 0;
 #pragma unroll
     for (int j = 0; j < NREG; j++) L[j] = 0;              // "predecessor outside" == L = 0, m = 0 (A.4)
+    // output pointer of this lane's chunk of the current column; moves by one column per step
+    char *po = reinterpret_cast<char *>(Lh) + ((size_t)row * g.rowStride + (size_t)(DIR ? W1 - 1 : 0) * DP) * 2 + 16 * lg;
+    const uint32_t laneA = wbufA + (uint32_t)grp * HZ_K * COLB + 16u * (uint32_t)lg;
+    auto store_col = [&](int i) {                         // column i of the chunk (compile-time i: immediate offsets)
+        if (act) {
+            uint4 *p4 = reinterpret_cast<uint4 *>(po + i * STEPB);
+#pragma unroll
+            for (int k4 = 0; k4 < NREG / 4; k4++) p4[LPC * k4] = make_uint4(L[4 * k4 + 0], L[4 * k4 + 1], L[4 * k4 + 2], L[4 * k4 + 3]);
+        }
+    };
     for (int ci = 0; ci < nchunks; ci++) {
         const int st = ci % HZ_NS;
-        mbar_wait(&bars[st], (uint32_t)(ci / HZ_NS) & 1u);
-        const int s0 = ci * HZ_K, kc = min(HZ_K, W1 - s0);
-        const uint16_t *sb = wbuf + st * stageElems + (size_t)grp * HZ_K * Dp;
+        mbar_wait(bars[st], (uint32_t)(ci / HZ_NS) & 1u);
+        const int kc = min(HZ_K, W1 - ci * HZ_K);
+        // staged column 0 of the chunk in walking order: the first for (-1,0), the last for (+1,0)
+        const uint32_t ca = laneA + (uint32_t)st * stageB + (DIR ? (uint32_t)(kc - 1) * COLB : 0u);
+        if (kc == HZ_K) {
+            // full chunk: straight-line code, the next column's cost vector is loaded before the current path step
+            uint32_t Ca[NREG], Cb[NREG];
+            lds_vec<NREG, LPC>(Ca, ca);
 #pragma unroll
-        for (int i = 0; i < HZ_K; i++) {
-            if (i < kc) {
-                const int s = s0 + i;
-                const int x = dir ? W1 - 1 - s : s;
-                uint32_t Cc[NREG], Ln[NREG];
-                load_vec<NREG, LPC>(Cc, sb + (size_t)(dir ? kc - 1 - i : i) * Dp, lg);
-                m = path_step<NREG, LPC>(Ln, L, m, Cc, P1p, P2mP1p, lg, lastLane);
-#pragma unroll
-                for (int j = 0; j < NREG; j++) L[j] = Ln[j];
-                if (act) store_vec<NREG, LPC>(Ln, orow + (size_t)x * Dp, lg);
+            for (int i = 0; i < HZ_K; i += 2) {
+                lds_vec<NREG, LPC>(Cb, ca + (uint32_t)((i + 1) * STEPB));
+                m = path_step_m<NREG, LPC>(L, m, Ca, P1p, P2mP1p, lm);
+                store_col(i);
+                if (i + 2 < HZ_K) lds_vec<NREG, LPC>(Ca, ca + (uint32_t)((i + 2) * STEPB));
+                m = path_step_m<NREG, LPC>(L, m, Cb, P1p, P2mP1p, lm);
+                store_col(i + 1);
+            }
+            po += HZ_K * STEPB;
+        } else {                                          // the row's last, partial chunk
+            for (int i = 0; i < kc; i++) {
+                uint32_t Cc[NREG];
+                lds_vec<NREG, LPC>(Cc, ca + (uint32_t)(i * STEPB));
+                m = path_step_m<NREG, LPC>(L, m, Cc, P1p, P2mP1p, lm);
+                store_col(0);
+                po += STEPB;
             }
         }
         __syncwarp();
-        if (lane == 0 && ci + HZ_NS < nchunks) fill(ci + HZ_NS);
+        if (ci + HZ_NS < nchunks) fill(ci + HZ_NS);
     }
+}
+
+template <int NREG, int LPC>
+__global__ void __launch_bounds__(HZ_THREADS) k_horizontal(Geo g, const uint16_t *__restrict__ C,
+                                                           uint16_t *__restrict__ LhA,
+                                                           uint16_t *__restrict__ LhB, int y0, int nrows)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    // blockIdx.y: 0 = predecessor (-1,0) -> L_hA, 1 = predecessor (+1,0) -> L_hB
+    if (blockIdx.y == 0) horizontal_dir<NREG, LPC, 0>(g, C, LhA, y0, nrows, smem);
+    else horizontal_dir<NREG, LPC, 1>(g, C, LhB, y0, nrows, smem);
 }
 
 // =================================================================================================

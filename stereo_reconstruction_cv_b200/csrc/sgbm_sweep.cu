@@ -308,39 +308,6 @@ __device__ __forceinline__ void sweep_producer_pf(const SweepArgs &a, const Swee
 template <bool SAT>
 __device__ __forceinline__ uint32_t sacc(uint32_t s, uint32_t x) { return SAT ? paddmin(s, x, SGBM_MAX_S) : s + x; }
 
-// OR-masks of a lane inside its group: all ones where the disparity neighbour below / above the lane's
-// range is outside [0, D) (L(-1) = L(D) = +inf, A.4) and where the whole lane is padding.  Held in registers
-// (made opaque once) so that the row loop does not re-derive them from the thread id.
-struct LaneMasks { uint32_t up, dn, pad; };
-__device__ __forceinline__ LaneMasks lane_masks(int lg, int lastLane)
-{
-    LaneMasks m;
-    m.up = sm_keep(lg == 0 ? 0xFFFFFFFFu : 0u);
-    m.dn = sm_keep(lg >= lastLane ? 0xFFFFFFFFu : 0u);
-    m.pad = sm_keep(lg > lastLane ? 0xFFFFFFFFu : 0u);
-    return m;
-}
-
-// path_step of sgbm_common.cuh, in place, with the lane masks instead of per-row comparisons.
-template <int NREG, int LPC>
-__device__ __forceinline__ uint32_t path_step_m(uint32_t (&L)[NREG], uint32_t mp, const uint32_t (&C)[NREG], uint32_t P1p,
-                                                uint32_t P2mP1p, const LaneMasks &lm)
-{
-    const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, L[NREG - 1], 1, LPC) | lm.up;
-    const uint32_t dn = __shfl_down_sync(0xFFFFFFFFu, L[0], 1, LPC) | lm.dn;
-    uint32_t sPrev = __byte_perm(up, L[0], 0x5432);        // (L[2j-1], L[2j]) for j = 0
-    const uint32_t k1 = mp + P2mP1p;                       // (m + P2 - P1) in both halves, no carry (<= 65535)
-#pragma unroll
-    for (int j = 0; j < NREG; j++) {
-        const uint32_t nxt = (j + 1 < NREG) ? L[j + 1] : dn;
-        const uint32_t sNext = __byte_perm(L[j], nxt, 0x5432);
-        const uint32_t b = paddmin(pmin3(sPrev, sNext, k1), P1p, L[j]);
-        L[j] = b + C[j] - mp;
-        sPrev = sNext;
-    }
-    return group_min<LPC>(local_min<NREG>(L) | lm.pad);
-}
-
 // ---- role V: vertical path, starts the S slot of every row ------------------------------------------
 template <int NREG, int LPC, bool SAT>
 __device__ __forceinline__ void sweep_role_v(const SweepArgs &a, const SweepSmem &s, int rwarp, int SW, int nRows)
