@@ -115,7 +115,7 @@ _PAIR_CACHE = {}
 
 
 def make_inputs(W, H, D, seed):
-    from stereo_reconstruction_cv_b200.synth import make_pair
+    from synth import make_pair
     key = (W, H, D, seed)
     if key not in _PAIR_CACHE:
         l, r, _ = make_pair(W, H, D, seed=seed)

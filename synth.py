@@ -1,4 +1,5 @@
-"""Synthetic rectified stereo pairs (SURVEY.md section 8(d) generator).
+"""Synthetic rectified stereo pairs (SURVEY.md section 8(d) generator) -- input generator of bench.py, the tests, smoke() and
+the tools; NOT part of the product package (it uses cv2 for the survey's exact recipe when cv2 is importable).
 
 The reference has no generator of its own (it only ships three JPEG pairs, dataset/d1..d3), so
 the survey defines one: a blurred-noise texture warped by a smooth ground-truth disparity field

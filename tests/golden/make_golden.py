@@ -19,7 +19,7 @@ sys.path.insert(0, os.path.abspath(os.path.join(HERE, "..", "..")))
 import cv2  # noqa: E402
 
 from oracle import OracleParams, cv2_ref  # noqa: E402
-from stereo_reconstruction_cv_b200.synth import make_noise_pair, make_pair  # noqa: E402
+from synth import make_noise_pair, make_pair  # noqa: E402
 
 REF = "/root/reference/dataset"
 NOTEBOOK_Q = np.array([[1, 0, 0, -1909.9754], [0, 1, 0, -1057.74529], [0, 0, 0, 2045.48384],

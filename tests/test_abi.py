@@ -45,3 +45,5 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f
+                # ... nor the reference's implementation: the package computes everything itself
+                assert "import cv2" not in txt and "from cv2" not in txt, f

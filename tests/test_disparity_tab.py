@@ -4,7 +4,7 @@ import pytest
 
 import oracle
 from oracle import OracleParams
-from stereo_reconstruction_cv_b200.synth import make_pair
+from synth import make_pair
 
 
 def test_point_cloud_arrays_is_the_notebook_mask():

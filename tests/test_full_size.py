@@ -24,7 +24,7 @@ import pytest
 
 import oracle
 from oracle import OracleParams
-from stereo_reconstruction_cv_b200.synth import make_pair
+from synth import make_pair
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 FULL = json.load(open(os.path.join(HERE, "golden", "golden_full.json")))

@@ -9,7 +9,7 @@ import pytest
 
 import oracle
 from oracle import OracleParams, cv2_ref
-from stereo_reconstruction_cv_b200.synth import make_noise_pair, make_pair
+from synth import make_noise_pair, make_pair
 
 pytestmark = pytest.mark.gpu
 

@@ -147,7 +147,7 @@ def test_ply_round_trip(tmp_path):
 # ------------------------------------------------------------------------------------------------
 def _nccl_worker(rank, world, port, tmp):
     import stereo_reconstruction_cv_b200 as sg
-    from stereo_reconstruction_cv_b200.synth import make_pair
+    from synth import make_pair
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)

@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 import oracle  # noqa: E402
 from oracle import OracleParams  # noqa: E402
 import stereo_reconstruction_cv_b200 as sg  # noqa: E402
-from stereo_reconstruction_cv_b200.synth import make_noise_pair, make_pair  # noqa: E402
+from synth import make_noise_pair, make_pair  # noqa: E402
 
 bad = 0
 t0 = time.time()

@@ -12,7 +12,7 @@ from stereo_reconstruction_cv_b200 import _lib  # noqa: E402
 
 _lib._LIB = _lib.load(os.path.join(ROOT, "build", "trace", "pkg", "libsgbm_b200.so"))
 import stereo_reconstruction_cv_b200 as sg  # noqa: E402
-from stereo_reconstruction_cv_b200.synth import make_pair  # noqa: E402
+from synth import make_pair  # noqa: E402
 
 CFG = {"cfg1": (3840, 2160, 16, 0, dict(blockSize=11, P1=2904, P2=11616)), "cfg2": (1280, 720, 128, 0, {}),
        "cfg3": (3840, 2160, 256, 1, {}), "cfg4": (1920, 1080, 192, 0, {})}
