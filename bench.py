@@ -18,7 +18,7 @@ the data path).
   cpu_baseline : the reference's own implementation (cv2.StereoSGBM) on a bounded sample, same run
 
 The default run also carries every other BASELINE config in `workloads` (cfg1, cfg2, cfg4, cfg5: value,
-ms, e2e, roofline, cpu_baseline each) and the 512-pair batch of configs[3] in `batch512`: 512 1080p pairs in
+ms, e2e, roofline, cpu_baseline each; cfg1 / cfg2 / cfg4 also as batched calls that run frames side by side) and the 512-pair batch of configs[3] in `batch512`: 512 1080p pairs in
 host memory, split over the N ranks by sharding.shard_range (strong scaling), each rank one compute_batch call.
 
 --impl reference times cv2.StereoSGBM (the oracle port when cv2 is missing) on the box's host cores.
@@ -641,7 +641,7 @@ def run_product(args):
         # the other BASELINE configs, shorter runs; cfg2 / cfg4 both one pair per call and six pairs per call
         wl = {}
         sub_steps = max(5, min(args.steps, 10))
-        for name, f in (("cfg1", 1), ("cfg2", 1), ("cfg2_batch6", 6), ("cfg4", 1), ("cfg4_batch6", 6), ("cfg5", 1)):
+        for name, f in (("cfg1", 1), ("cfg1_batch8", 8), ("cfg2", 1), ("cfg2_batch6", 6), ("cfg4", 1), ("cfg4_batch6", 6), ("cfg5", 1)):
             base = name.split("_")[0]
             r = run_workload(cx, base, sub_steps, 3, fps=f, want_e2e=(f == 1), want_cpu=(f == 1), e2e_reps=3)
             r.pop("config", None)

@@ -67,7 +67,7 @@ enum { ST_START = 0, ST_PREFILTER, ST_COST, ST_COST_ALT, ST_HORIZONTAL, ST_INIT,
 static const char *const kStageNames[ST_COUNT] = {"start", "prefilter", "cost", "cost_alt", "horizontal", "init",
                                                   "vertical_fwd", "vertical_wta", "lrcheck", "median", "speckle"};
 struct ProfMark { int stage; cudaEvent_t ev; unsigned long long launches; };
-#define SGBM_MAX_LANES 3             // frames a batch call runs side by side (each on numSMs / lanes SMs)
+#define SGBM_MAX_LANES 4             // frames a batch call runs side by side (each on numSMs / lanes SMs)
 #define SGBM_MAX_SLOTS (2 * SGBM_MAX_LANES)
 #define SGBM_MAX_BANDS 8
 
@@ -82,7 +82,7 @@ struct sgbm_handle {
     // device workspace (grown on demand); lane 1 exists only while batches run two frames side by side
     void *ws[SGBM_MAX_LANES] = {};
     size_t wsBytes[SGBM_MAX_LANES] = {};
-    int lanesWanted = SGBM_MAX_LANES;   // SGBM_LANES=1 switches the side-by-side batch schedule off
+    int lanesWanted = 0;                // SGBM_LANES (1 switches the side-by-side batch schedule off); 0 = by geometry, see lanes_for
     cudaStream_t laneStream[SGBM_MAX_LANES] = {};   // [0] unused: lane 0 runs on the caller's / the handle's stream
     cudaEvent_t evFork = nullptr, evJoin[SGBM_MAX_LANES] = {};
     // row bands inside one frame: the horizontal kernel of band b runs beside the cost kernel of band b + 1
@@ -432,9 +432,12 @@ static int check_watch(sgbm_handle *h, cudaStream_t st)
 static int lanes_for(const sgbm_handle *h, const Geo &g, int batch, int *sweepSMs)
 {
     *sweepSMs = h->numSMs;
-    if (batch < 2 || h->lanesWanted < 2 || h->prof || h->keep) return 1;
+    // three lanes by default (four were slower at 720p D=128: 172 vs 180 GDE/s); four when a column is only two lanes
+    // (numDisparities <= 32): those frames leave the GPU emptiest
+    const int want = h->lanesWanted > 0 ? h->lanesWanted : (g.lpc <= 2 ? 4 : 3);
+    if (batch < 2 || want < 2 || h->prof || h->keep) return 1;
     if (h->p.mode == SGBM_MODE_SGBM || h->p.mode == SGBM_MODE_HH) {
-        int lanes = h->lanesWanted < batch ? h->lanesWanted : batch;
+        int lanes = want < batch ? want : batch;
         for (; lanes >= 2; lanes--)
             if (h->numSMs / lanes >= 1 && sgbm_sweep_fits(g, h->numSMs / lanes, h->p.mode)) {
                 *sweepSMs = h->numSMs / lanes;
