@@ -160,6 +160,7 @@ static void read_knobs(SgbmKnobs &k)
     k.cost2 = env_int("SGBM_COST2", 1) != 0;
     k.cost3 = env_int("SGBM_COST3", 1) != 0;
     k.cost3NXG = env_int("SGBM_COST3_NXG", 0); k.cost3RB = env_int("SGBM_COST3_RB", 0);
+    k.cost3Pad = env_int("SGBM_COST3_PAD", 0);
     k.nstg = env_int("SGBM_NSTG", 0);
     k.sweepSat = env_int("SGBM_SWEEP_SAT", 0) != 0;
     k.smallD = env_int("SGBM_SMALLD", 1) != 0;

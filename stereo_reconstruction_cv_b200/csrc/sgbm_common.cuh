@@ -107,6 +107,7 @@ struct SgbmKnobs {
     int rowstep = 0;                     // SGBM_ROWSTEP=1: row-at-a-time fallback
     int cost2 = 1, cost3 = 1;            // SGBM_COST2=0 / SGBM_COST3=0: older cost-kernel generations
     int cost3NXG = 0, cost3RB = 0;       // SGBM_COST3_NXG / _RB
+    int cost3Pad = 0;                    // SGBM_COST3_PAD: extra dynamic shared memory (bytes) requested by the cost kernel (occupancy experiments)
     int nstg = 0;                        // SGBM_NSTG: staging depth of k_vertical
     int sweepSat = 0;                    // SGBM_SWEEP_SAT=1: force the saturating S accumulation
     int hhSplit = 1;                     // SGBM_HH_SPLIT=0: MODE_HH feeds L_hB into the forward sweep instead of the backward one

@@ -405,6 +405,7 @@ int sgbm_launch_cost3(const Geo &g, const uint8_t *planes, uint16_t *out, int y0
     if (const int v = sgbm_knobs().cost3RB) { if (v >= 1) a.RB = v; }
     if (a.RB > nrows) a.RB = nrows;
     dim3 grid(tilesX, (nrows + a.RB - 1) / a.RB);
+    if (sgbm_knobs().cost3Pad > 0 && smem + (size_t)sgbm_knobs().cost3Pad <= (size_t)maxSmem) smem += (size_t)sgbm_knobs().cost3Pad;
     const int par = (g.minX1 - R - g.minD - 1) & 1;       // parity of the first walked column's right position
     if (sgbm_knobs().verbose)
         fprintf(stderr, "cost3: R=%d Dw=%d NXG=%d threads=%d smem=%zu nstg=%d RB=%d grid=%dx%d par=%d eshift=%d\n", R, Dw, a.NXG,
