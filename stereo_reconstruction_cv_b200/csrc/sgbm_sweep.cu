@@ -19,8 +19,15 @@
 //
 // In the last sweep of MODE_SGBM / MODE_HH a fourth role W (WROLE kernels) takes the winner-take-all off
 // role C: C writes the finished S back into the slot, W reads it, and setmaxnreg moves registers from
-// the W / producer warpgroups to the path warpgroups.  k_rowstep at the end of this file is the
-// row-at-a-time fallback for geometries no persistent kernel holds.
+// the W / producer warpgroups to the path warpgroups.  The W warps form row groups that take alternate rows
+// (one pass of the WTA is a ~1500-cycle dependent chain: with narrow strips its latency, not its throughput,
+// would set the row period).  k_rowstep at the end of this file is the row-at-a-time fallback for geometries
+// no persistent kernel holds.
+//
+// The row loops are written for instruction count (round 2): every ring is addressed through a RingPos carried in
+// registers (32-bit shared addresses, ld/st.shared with immediate offsets, advanced by additions), the barriers of a
+// stage sit side by side, a diagonal role knows its column as one number in staged-window coordinates, and
+// super-steps are an outer loop.  profiles/r02_sweep_roles_instruction_counts.md has the per-role counts.
 //
 // Strips exchange diagonal state every R rows (a "super-step"): at its end, role A publishes the
 // state of the strip's last R columns, role C that of its first R columns (global memory, a ring of
@@ -206,11 +213,8 @@ __device__ __forceinline__ void ring_advance_n(RingPos &r, int n, uint32_t strid
     if (r.left <= 0) { r.left += depth; r.data -= span; r.bar -= barSpan; r.par ^= 1u; }
 }
 __device__ __forceinline__ void bar_arrive(uint32_t addr) { mbar_arrive(SmemBar{addr}); }
-#ifdef SWEEP_NO_PROBES     // experiment: no early probes, every hand-off is one blocking wait
-__device__ __forceinline__ bool bar_test(uint32_t, uint32_t) { return false; }
-#else
+// (measured in round 2: without the early probes -- every hand-off one blocking wait -- all sweeps are within 0.02 ms)
 __device__ __forceinline__ bool bar_test(uint32_t addr, uint32_t parity) { return mbar_test_wait(SmemBar{addr}, parity); }
-#endif
 // L2 prefetch of a contiguous global range (no destination, no completion): the producer runs it several rows
 // ahead of the bulk copies, so that the copies are served from L2 -- a prefetch depth that does not cost
 // shared memory the way a deeper staging ring does.
@@ -543,9 +547,7 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
                     const long long t0 = clock64();
                     const unsigned int *fl = flagIn + hsPrev * R;
                     while (ld_acquire_u32(fl) < (unsigned)n) {
-#ifndef SWEEP_SPIN_POLL
-                        __nanosleep(32);
-#endif
+                        __nanosleep(32);                  // (spinning instead: cfg3 +0.12 ms, small frames -0.01 ms)
                         if (*reinterpret_cast<volatile unsigned int *>(a.dbg) != 0u) break;
                         if (clock64() - t0 > SWEEP_WAIT_LIMIT) { sweep_timeout(a.dbg, DIR > 0 ? 6 : 7, tq); break; }
                     }
