@@ -46,6 +46,55 @@ def compute_shard(stereo, lefts, rights, world_size=1, rank=0, out=None):
     return start, stop, [stereo.compute(lefts[i], rights[i]) for i in range(start, stop)]
 
 
+def compute_batch_devices(params, lefts, rights, devices=None, out=None):
+    """One process, several GPUs: the batch is block-partitioned over `devices` (default: every visible CUDA device) and
+    every block goes through ONE `compute_batch` call on its own device, from its own host thread (SURVEY.md 8(e):
+    "one worker -- process or thread -- per GPU").  No collective, no peer traffic: each thread owns a StereoSGBM handle
+    bound to its device (sgbm_create binds a handle to the current device; the library serialises per handle and keeps
+    per-device kernel set-up under a lock, so threads on different devices do not interact), and ctypes releases the
+    GIL for the duration of the call.
+
+    params: dict of StereoSGBM_create arguments.  lefts / rights: uint8 numpy (B,H,W) or (B,H,W,3), ideally page-locked.
+    Returns the int16 (B,H,W) disparities in frame order (written into `out` when given)."""
+    import threading
+
+    import torch
+
+    from .stereo import StereoSGBM_create
+    lefts = np.ascontiguousarray(lefts)
+    rights = np.ascontiguousarray(rights)
+    if devices is None:
+        devices = list(range(torch.cuda.device_count()))
+    if not devices:
+        raise RuntimeError("compute_batch_devices needs at least one CUDA device: the engine has no CPU fallback")
+    B, H, W = lefts.shape[:3]
+    if out is None:
+        out = np.empty((B, H, W), np.int16)
+    errors = [None] * len(devices)
+
+    def worker(k, dev):
+        try:
+            start, stop = shard_range(B, len(devices), k)
+            if start == stop:
+                return
+            with torch.cuda.device(dev):
+                st = StereoSGBM_create(**params)          # bound to `dev`
+                st.compute_batch(lefts[start:stop], rights[start:stop], out[start:stop])
+                del st
+        except Exception as e:                            # surfaced in the calling thread
+            errors[k] = e
+
+    threads = [threading.Thread(target=worker, args=(k, d)) for k, d in enumerate(devices)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for e in errors:
+        if e is not None:
+            raise e
+    return out
+
+
 def gather_varlen(t, dst=0, group=None):
     """Gather first-dimension-ragged tensors (e.g. per-rank point clouds, N_r x 3) to rank `dst`.
 

@@ -184,3 +184,28 @@ def test_nccl_world2_shard_and_gather(tmp_path):
     port = _free_port()
     mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert int(open(tmp_path / "ok").read()) > 1000
+
+
+@pytest.mark.gpu
+def test_one_process_multi_gpu_batch():
+    """sharding.compute_batch_devices: one process, one host thread and one handle per GPU, block-partitioned batch, no
+    collective.  Every frame equals the oracle; with two visible devices both are used (and the single-device call agrees)."""
+    import oracle
+    from oracle import OracleParams
+    import stereo_reconstruction_cv_b200 as sg  # noqa: F401
+    from synth import make_pair
+    W, H, D, B = 900, 120, 64, 7
+    pairs = [make_pair(W, H, D, seed=300 + i)[:2] for i in range(B)]
+    ls, rs = np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs])
+    kw = dict(minDisparity=0, numDisparities=D, blockSize=5, P1=200, P2=800, disp12MaxDiff=1, preFilterCap=63, uniquenessRatio=10,
+              speckleWindowSize=100, speckleRange=32, mode=1)
+    ref = np.stack([oracle.compute(OracleParams(**kw), l, r) for l, r in pairs])
+    ndev = torch.cuda.device_count()
+    assert ndev >= 1
+    got = sharding.compute_batch_devices(kw, ls, rs)                       # every visible device
+    assert got.shape == (B, H, W) and got.dtype == np.int16 and np.array_equal(got, ref)
+    assert np.array_equal(sharding.compute_batch_devices(kw, ls, rs, devices=[ndev - 1]), ref)
+    if ndev >= 2:                                                           # more devices than frames: empty blocks are fine
+        assert np.array_equal(sharding.compute_batch_devices(kw, ls[:1], rs[:1], devices=[0, 1]), ref[:1])
+    with pytest.raises(sg.error):                                           # errors of a worker thread reach the caller
+        sharding.compute_batch_devices(dict(kw, numDisparities=2048), ls, rs)
