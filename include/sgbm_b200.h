@@ -84,8 +84,10 @@ int sgbm_get_params(const sgbm_handle *h, sgbm_params *p);
 int sgbm_workspace_bytes(const sgbm_handle *h, int W, int H, int channels, int batch, size_t *out);
 
 /*
- * Disparity for `batch` independent rectified pairs (frames are processed one after another on
- * the stream).  left/right: uint8, `channels` in {1,3} interleaved, row pitch `pitch_bytes`,
+ * Disparity for `batch` independent rectified pairs.  To the caller everything is ordered on
+ * `cuda_stream`; inside, a batch runs up to four frames side by side (each on its share of the SMs,
+ * on internal streams forked from and joined to `cuda_stream`) when the frames are small enough for
+ * that to pay, and two frames in flight otherwise.  left/right: uint8, `channels` in {1,3} interleaved, row pitch `pitch_bytes`,
  * frame stride = pitch_bytes * H.  disp_out: int16 (disparity x16, invalid = (minD-1)*16), row
  * pitch out_pitch_bytes, frame stride out_pitch_bytes * H.  Result is bit-identical to
  * cv2.StereoSGBM.compute inside the parity domain documented in DESIGN.md.
