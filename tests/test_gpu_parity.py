@@ -436,3 +436,51 @@ def test_row_band_schedule(sg, monkeypatch, bands):
                 assert _mismatch(st.compute(ls[rep], rs[rep]), ref[rep]) == 0, (bands, H, mode, rep)
             got = st.compute(torch.from_numpy(ls).cuda(), torch.from_numpy(rs).cuda())
             assert _mismatch(got.cpu().numpy(), ref) == 0, (bands, H, mode, "batch")
+
+
+# ------------------------------------------------------------------------------------------------
+# corners of the parameter / shape domain
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bs,cap", [(13, 63), (15, 31), (17, 15)])
+def test_large_block_sizes(sg, bs, cap):
+    """blockSize > 11 leaves the register-resident cost kernel (r <= 5) for the older generations.  The block sum itself must
+    fit int16 -- (2r+1)^2 * (min(2*ftzero, 255) + 63) <= 32767; beyond that cv2's `short` cost volume wraps
+    (blockSize 21 with preFilterCap 63 can reach 83349) and no unsigned 16-bit engine follows it -- so preFilterCap shrinks
+    as the block grows: 13 / 63, 15 / 31, 17 / 15 are the largest pairs inside the domain.  All four modes against the
+    oracle (and live cv2)."""
+    W, H, D = 420, 90, 32
+    l, r, _ = make_pair(W, H, D, seed=bs)
+    ftzero = max(cap, 15) | 1
+    assert bs * bs * (min(2 * ftzero, 255) + 63) <= 32767
+    for mode in (0, 1, 2, 3):
+        p = OracleParams(0, D, bs, 600, 2400, 1, cap, 10, 100, 32, mode)
+        ref = oracle.compute(p, l, r)
+        assert _mismatch(sg.StereoSGBM_create(**_kw(p)).compute(l, r), ref) == 0, (bs, mode)
+        if cv2_ref.available() and mode != 3:
+            assert _mismatch(cv2_ref.compute(p, l, r), ref) == 0, ("cv2", bs, mode)
+
+
+@pytest.mark.parametrize("D", [320, 512, 1024])
+def test_many_disparities(sg, D):
+    """numDisparities up to the supported maximum (1024): lane mappings with 16 or 32 lanes per column."""
+    W, H = D + 180, 36
+    l, r, _ = make_pair(W, H, D, seed=D)
+    for mode in (0, 1, 2):
+        if mode == 2 and H < 4 * (5 // 2 + 2):
+            continue
+        p = OracleParams(0, D, 5, 200, 800, 1, 63, 10, 50, 2, mode)
+        assert _mismatch(sg.StereoSGBM_create(**_kw(p)).compute(l, r), oracle.compute(p, l, r)) == 0, (D, mode)
+
+
+@pytest.mark.parametrize("H,W", [(1, 120), (2, 97), (3, 64), (5, 41), (37, 26)])
+def test_tiny_and_odd_shapes(sg, H, W):
+    """One to five rows, widths barely above numDisparities + blockSize / 2: every row is first and last row of its paths,
+    strips are one or two columns wide.  (3WAY needs enough rows for its four stripes, so it only runs on the tallest.)"""
+    D = 16
+    l, r = make_noise_pair(W, H, seed=H * 100 + W)
+    for mode in (0, 1, 3) + ((2,) if H >= 37 else ()):
+        for bs in (1, 3, 5):
+            p = OracleParams(0, D, bs, 8 * bs * bs, 32 * bs * bs, 1, 31, 5, 20, 2, mode)
+            if oracle.port.valid_width(p, W) <= bs // 2:
+                continue
+            assert _mismatch(sg.StereoSGBM_create(**_kw(p)).compute(l, r), oracle.compute(p, l, r)) == 0, (H, W, mode, bs)
