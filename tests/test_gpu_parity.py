@@ -397,6 +397,24 @@ def test_handoff_watchdog_reports_and_recovers(sg, monkeypatch):
 
 
 @pytest.mark.parametrize("mode", [0, 1])
+def test_batch_four_lanes_for_two_lane_columns(sg, mode):
+    """numDisparities <= 32 (a column is two lanes): batches run FOUR frames side by side by default.  Nine frames (odd
+    remainder), device tensors and host arrays, repeated calls; every frame equals the oracle."""
+    import torch
+    W, H, D, B = 1500, 64, 16, 9
+    pairs = [make_pair(W, H, D, seed=500 + i)[:2] for i in range(B)]
+    p = OracleParams(0, D, 11, 8 * 3 * 121, 32 * 3 * 121, 1, 63, 10, 100, 32, mode)       # the notebook's parameters (saturating)
+    ref = np.stack([oracle.compute(p, l, r) for l, r in pairs])
+    ls = np.stack([l for l, _ in pairs]); rs = np.stack([r for _, r in pairs])
+    st = sg.StereoSGBM_create(**_kw(p))
+    for rep in range(3):
+        got = st.compute(torch.from_numpy(ls).cuda(), torch.from_numpy(rs).cuda())
+        assert _mismatch(got.cpu().numpy(), ref) == 0, (mode, rep, "device")
+    assert _mismatch(st.compute_batch(ls, rs), ref) == 0, (mode, "host")
+    assert st.workspaceBytes(W, H, 1, batch=B) == 4 * st.workspaceBytes(W, H, 1, batch=1)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
 def test_batch_side_by_side_schedule(sg, monkeypatch, mode):
     """Batched calls run two or three frames side by side, each on its share of the SMs (when the narrower
     sweeps hold the geometry): every frame must equal the oracle, for device tensors and host arrays, odd
