@@ -502,3 +502,46 @@ def test_tiny_and_odd_shapes(sg, H, W):
             if oracle.port.valid_width(p, W) <= bs // 2:
                 continue
             assert _mismatch(sg.StereoSGBM_create(**_kw(p)).compute(l, r), oracle.compute(p, l, r)) == 0, (H, W, mode, bs)
+
+
+def test_one_handle_from_two_streams_and_two_threads(sg):
+    """The workspace belongs to the handle, not to the stream: calls on one handle from different streams (no host
+    synchronisation in between) and from different host threads must not overlap on it -- the library serialises the
+    enqueue and orders each call behind the handle's previous one on the device.  Every result equals the oracle."""
+    import threading
+    import torch
+    W, H, D = 1300, 200, 64
+    pairs = [make_pair(W, H, D, seed=700 + i)[:2] for i in range(4)]
+    p = OracleParams(0, D, 5, 200, 800, 1, 63, 10, 100, 32, 1)
+    ref = [oracle.compute(p, l, r) for l, r in pairs]
+    lt = [torch.from_numpy(l).cuda() for l, _ in pairs]
+    rt = [torch.from_numpy(r).cuda() for _, r in pairs]
+    st = sg.StereoSGBM_create(**_kw(p))
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    torch.cuda.synchronize()
+    for rep in range(5):
+        outs = [None] * 4
+        for i in range(4):                                  # back to back, each on its own stream, nothing waits in between
+            with torch.cuda.stream(streams[i]):
+                outs[i] = st.compute(lt[i], rt[i])
+        torch.cuda.synchronize()
+        for i in range(4):
+            assert _mismatch(outs[i].cpu().numpy(), ref[i]) == 0, ("streams", rep, i)
+    res, errs = [None] * 4, []
+
+    def worker(i):
+        try:
+            for _ in range(6):
+                with torch.cuda.stream(streams[i]):
+                    res[i] = st.compute(lt[i], rt[i])
+                streams[i].synchronize()
+                assert _mismatch(res[i].cpu().numpy(), ref[i]) == 0
+        except Exception as e:                              # pragma: no cover
+            errs.append((i, e))
+
+    th = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
