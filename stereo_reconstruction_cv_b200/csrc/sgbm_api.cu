@@ -163,7 +163,7 @@ static void read_knobs(SgbmKnobs &k)
     k.cost3Pad = env_int("SGBM_COST3_PAD", 0);
     k.nstg = env_int("SGBM_NSTG", 0);
     k.sweepSat = env_int("SGBM_SWEEP_SAT", 0) != 0;
-    k.smallD = env_int("SGBM_SMALLD", 1) != 0;
+    k.sweepRPS = env_int("SGBM_SWEEP_RPS", 0);
     k.hhSplit = env_int("SGBM_HH_SPLIT", 1) != 0;
     k.verbose = env_int("SGBM_VERBOSE", 0) != 0;
 #ifdef SGBM_DEBUG_HOOKS

@@ -101,6 +101,7 @@ struct SgbmKnobs {
     int vr = 0;                          // SGBM_VR: rows per super-step of the sweeps (0 = default)
     int sweepK = 0, sweepNSC = 0, sweepNSI = 0, sweepNWW = 0;   // SGBM_SWEEP_K / _NSC / _NSI / _NWW ring depths, WTA warps per row
     int sweepPF = -1;                    // SGBM_SWEEP_PF: rows of L2 prefetch ahead of the spilling sweep's bulk copies (-1 = default 8, 0 = off)
+    int sweepRPS = 0;                    // SGBM_SWEEP_RPS: rows per ring stage of the sweeps (0 = auto, 1, 2)
     int sweepWRG = 0;                    // SGBM_SWEEP_WRG: cap on the row groups of the WTA warps (0 = as many as fit)
     int sweepW = 1;                      // SGBM_SWEEP_W=0: winner-take-all on role C instead of the W role
     int sweep = 1;                       // SGBM_SWEEP=0: lock-step k_vertical instead of the role-specialised sweep
@@ -111,7 +112,6 @@ struct SgbmKnobs {
     int nstg = 0;                        // SGBM_NSTG: staging depth of k_vertical
     int sweepSat = 0;                    // SGBM_SWEEP_SAT=1: force the saturating S accumulation
     int hhSplit = 1;                     // SGBM_HH_SPLIT=0: MODE_HH feeds L_hB into the forward sweep instead of the backward one
-    int smallD = 1;                      // SGBM_SMALLD=0: do not use the whole-vector-per-lane kernels for small numDisparities
     int verbose = 0;                     // SGBM_VERBOSE: print launch geometries to stderr
     int dbgNoSync = 0, dbgStall = 0;     // SGBM_DBG_NOSYNC / SGBM_DBG_STALL (debug-hook builds only)
     char tracePath[256] = "";            // SGBM_SWEEP_TRACE (tracing builds only)

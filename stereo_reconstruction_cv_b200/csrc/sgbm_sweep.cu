@@ -65,8 +65,12 @@ struct SweepArgs {
     unsigned int *dbg;               // [8] hand-off watchdog: {tripped, strip, warp, wait id, row, ...}, zeroed per launch
     unsigned long long *trace;       // debug: clock64 time stamps of one strip [row][role 4][8] (or null)
     int traceStrip;
-    int pfDist;                      // rows by which the producer's L2 prefetch runs ahead of its bulk copies (0 = off); LAST:
-                                     // the register allocation of the WTA kernels is sensitive to the layout of the fields above
+    int pfDist;                      // rows by which the producer's L2 prefetch runs ahead of its bulk copies (0 = off)
+    // Rows per ring stage (1 or 2).  With two rows per stage every hand-off (wait, arrive, ring advance) is paid once per
+    // two image rows; cRowB / iRowB / pRowB are the bytes of one row inside a stage of the cost / input / S ring.
+    // New fields go LAST: the register allocation of the WTA kernels is sensitive to the layout of the fields above.
+    int rps;
+    unsigned int cRowB, iRowB, pRowB;
 };
 
 // clock64 time stamps of one strip: compiled in only with -DSGBM_SWEEP_TRACING (make TRACE=1); the
@@ -206,6 +210,13 @@ __device__ __forceinline__ void ring_advance(RingPos &r, uint32_t stride, uint32
     r.data += stride; r.bar += barStep;
     if (--r.left == 0) { r.left = depth; r.data -= span; r.bar -= barSpan; r.par ^= 1u; }
 }
+// the same when the row loop has already moved r.data over the rows of the stage (full stages only: the last, partial stage
+// of an image is never followed by another one)
+__device__ __forceinline__ void ring_advance_moved(RingPos &r, uint32_t span, uint32_t barStep, uint32_t barSpan, int depth)
+{
+    r.bar += barStep;
+    if (--r.left == 0) { r.left = depth; r.data -= span; r.bar -= barSpan; r.par ^= 1u; }
+}
 // the same for a role that visits every n-th stage (n <= depth)
 __device__ __forceinline__ void ring_advance_n(RingPos &r, int n, uint32_t stride, uint32_t span, uint32_t barStep, uint32_t barSpan, int depth)
 {
@@ -228,46 +239,18 @@ __device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void *src, uint32
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// ---- producer: TMA bulk copies of the cost row and the input rows of every sweep row ---------------
-__device__ __forceinline__ void sweep_producer(const SweepArgs &a, const SweepSmem &s, int xs, int xe, int yBegin,
-                                               int yStep, int nRows)
-{
-    const Geo &g = a.g;
-    const int Dp = g.Dp, HG = a.R - 1;
-    const int scol0 = xs - HG;
-    const int clo = max(scol0, 0), chi = min(xe + HG, g.W1);
-    const uint32_t colB = a.colB;
-    const uint32_t bytesC = (uint32_t)(chi - clo) * colB, bytesI = (uint32_t)(xe - xs) * colB;
-    RingPos rc = ring_start(s.aC + (uint32_t)(clo - scol0) * colB, s.barC, a.NSC);
-    RingPos ri = ring_start(s.aI, s.barI, a.NSI);
-    const uint16_t *srcC = a.C + (size_t)yBegin * g.rowStride + (size_t)clo * Dp;
-    const uint16_t *srcA = a.inA + (size_t)yBegin * g.rowStride + (size_t)xs * Dp;
-    const uint16_t *srcB = a.nAB > 1 ? a.inB + (size_t)yBegin * g.rowStride + (size_t)xs * Dp : nullptr;
-    const long long rowStep = (long long)yStep * g.rowStride;
-    for (int t = 0; t < nRows; t++) {
-        SWEEP_TR(3, 0, true);
-        if (t >= a.NSC) sweep_wait(a, SmemBar{rc.bar + BAR_EMPTY}, rc.par ^ 1u, 1, t);
-        SWEEP_TR(3, 1, true);
-        mbar_expect_tx(SmemBar{rc.bar + BAR_FULL}, bytesC);
-        bulk_g2s_a(rc.data, srcC, bytesC, rc.bar + BAR_FULL);
-        if (t >= a.NSI) sweep_wait(a, SmemBar{ri.bar + BAR_EMPTY}, ri.par ^ 1u, 2, t);
-        mbar_expect_tx(SmemBar{ri.bar + BAR_FULL}, bytesI * (uint32_t)a.nAB);
-        bulk_g2s_a(ri.data, srcA, bytesI, ri.bar + BAR_FULL);
-        if (srcB) bulk_g2s_a(ri.data + a.iBB, srcB, bytesI, ri.bar + BAR_FULL);
-        SWEEP_TR(3, 2, true);
-        ring_advance(rc, a.cStrideB, a.cSpanB, 16u, a.cBarSpan, a.NSC);
-        ring_advance(ri, a.iStrideB, a.iSpanB, 16u, a.iBarSpan, a.NSI);
-        srcC += rowStep; srcA += rowStep;
-        if (srcB) srcB += rowStep;
-    }
-}
+// Rows per ring stage (template parameter RPS of everything below): 1 or 2.  The 16-register lane mappings
+// (numDisparities >= 256 and a few odd sizes) never have the shared memory for two rows per stage at the widths the
+// persistent sweep holds, so only RPS = 1 is instantiated for them.
+constexpr int SWEEP_RPS_MAX_NREG = 12;
 
-// The same with an L2 prefetch a.pfDist rows ahead: the producer of the spilling (forward) sweep of MODE_HH, whose
-// speed follows the depth of its cost ring.  Kept apart from sweep_producer on purpose: in the winner-take-all
-// kernels the producer lives in the 40-register warpgroup, and any growth of its code showed up as spills there
-// (cfg3 WTA sweep 3.20 -> 3.37 ms).
-__device__ __forceinline__ void sweep_producer_pf(const SweepArgs &a, const SweepSmem &s, int xs, int xe, int yBegin,
-                                               int yStep, int nRows)
+// ---- producer: TMA bulk copies of the cost rows and the input rows of every ring stage ---------------
+// PF: with an L2 prefetch a.pfDist rows ahead -- the producer of the spilling (forward) sweep of MODE_HH, whose speed
+// follows the depth of its cost ring.  Compiled apart on purpose: in the winner-take-all kernels the producer lives in
+// the 40-register warpgroup, and any growth of its code showed up as spills there (cfg3 WTA sweep 3.20 -> 3.37 ms).
+template <int RPS, bool PF>
+__device__ __forceinline__ void sweep_producer_t(const SweepArgs &a, const SweepSmem &s, int xs, int xe, int yBegin,
+                                                 int yStep, int nRows)
 {
     const Geo &g = a.g;
     const int Dp = g.Dp, HG = a.R - 1;
@@ -281,31 +264,37 @@ __device__ __forceinline__ void sweep_producer_pf(const SweepArgs &a, const Swee
     const uint16_t *srcA = a.inA + (size_t)yBegin * g.rowStride + (size_t)xs * Dp;
     const uint16_t *srcB = a.nAB > 1 ? a.inB + (size_t)yBegin * g.rowStride + (size_t)xs * Dp : nullptr;
     const long long rowStep = (long long)yStep * g.rowStride;
-    const int pf = a.pfDist;
+    constexpr int rps = RPS;
+    const int pf = PF ? a.pfDist : 0;
     const long long pfOff = (long long)pf * rowStep;
-    for (int t = 0; t < nRows; t++) {
-        if (pf > 0 && t + pf < nRows) {
-            bulk_prefetch_l2(srcC + pfOff, bytesC);
-            bulk_prefetch_l2(srcA + pfOff, bytesI);
-            if (srcB) bulk_prefetch_l2(srcB + pfOff, bytesI);
+    // (a freshly initialised barrier passes a wait on the opposite parity at once: the first pass over a ring needs no test)
+    for (int t = 0; t < nRows; t += rps) {
+        const int rows = min(rps, nRows - t);
+        if (PF && pf > 0 && t + pf + rps <= nRows) {
+            for (int r = 0; r < rows; r++) {
+                bulk_prefetch_l2(srcC + pfOff + r * rowStep, bytesC);
+                bulk_prefetch_l2(srcA + pfOff + r * rowStep, bytesI);
+                if (srcB) bulk_prefetch_l2(srcB + pfOff + r * rowStep, bytesI);
+            }
         }
         SWEEP_TR(3, 0, true);
-        if (t >= a.NSC) sweep_wait(a, SmemBar{rc.bar + BAR_EMPTY}, rc.par ^ 1u, 1, t);
+        sweep_wait(a, SmemBar{rc.bar + BAR_EMPTY}, rc.par ^ 1u, 1, t);
         SWEEP_TR(3, 1, true);
-        mbar_expect_tx(SmemBar{rc.bar + BAR_FULL}, bytesC);
-        bulk_g2s_a(rc.data, srcC, bytesC, rc.bar + BAR_FULL);
-        if (t >= a.NSI) sweep_wait(a, SmemBar{ri.bar + BAR_EMPTY}, ri.par ^ 1u, 2, t);
-        mbar_expect_tx(SmemBar{ri.bar + BAR_FULL}, bytesI * (uint32_t)a.nAB);
-        bulk_g2s_a(ri.data, srcA, bytesI, ri.bar + BAR_FULL);
-        if (srcB) bulk_g2s_a(ri.data + a.iBB, srcB, bytesI, ri.bar + BAR_FULL);
+        mbar_expect_tx(SmemBar{rc.bar + BAR_FULL}, bytesC * (uint32_t)rows);
+        for (int r = 0; r < rows; r++) bulk_g2s_a(rc.data + (uint32_t)r * a.cRowB, srcC + r * rowStep, bytesC, rc.bar + BAR_FULL);
+        sweep_wait(a, SmemBar{ri.bar + BAR_EMPTY}, ri.par ^ 1u, 2, t);
+        mbar_expect_tx(SmemBar{ri.bar + BAR_FULL}, bytesI * (uint32_t)(a.nAB * rows));
+        for (int r = 0; r < rows; r++) {
+            bulk_g2s_a(ri.data + (uint32_t)r * a.iRowB, srcA + r * rowStep, bytesI, ri.bar + BAR_FULL);
+            if (srcB) bulk_g2s_a(ri.data + (uint32_t)r * a.iRowB + a.iBB, srcB + r * rowStep, bytesI, ri.bar + BAR_FULL);
+        }
         SWEEP_TR(3, 2, true);
         ring_advance(rc, a.cStrideB, a.cSpanB, 16u, a.cBarSpan, a.NSC);
         ring_advance(ri, a.iStrideB, a.iSpanB, 16u, a.iBarSpan, a.NSI);
-        srcC += rowStep; srcA += rowStep;
-        if (srcB) srcB += rowStep;
+        srcC += rows * rowStep; srcA += rows * rowStep;
+        if (srcB) srcB += rows * rowStep;
     }
 }
-
 
 // S accumulation: saturating (A.4) unless the host proved that the sum of all paths fits 16 bits, in
 // which case plain adds are exact and the clamp to 32767 is applied once when the pixel is finished.
@@ -313,7 +302,7 @@ template <bool SAT>
 __device__ __forceinline__ uint32_t sacc(uint32_t s, uint32_t x) { return SAT ? paddmin(s, x, SGBM_MAX_S) : s + x; }
 
 // ---- role V: vertical path, starts the S slot of every row ------------------------------------------
-template <int NREG, int LPC, bool SAT>
+template <int NREG, int LPC, bool SAT, int RPS>
 __device__ __forceinline__ void sweep_role_v(const SweepArgs &a, const SweepSmem &s, int rwarp, int SW, int nRows)
 {
     constexpr int GPW = 32 / LPC;
@@ -334,49 +323,64 @@ __device__ __forceinline__ void sweep_role_v(const SweepArgs &a, const SweepSmem
     uint32_t LB[NREG], mB = 0;
 #pragma unroll
     for (int j = 0; j < NREG; j++) LB[j] = 0;
-    bool okC = false;                                     // early probe of the row's cost stage
-    for (int t = 0; t < nRows; t++) {
-        uint32_t S[NREG];
+    constexpr int rps = RPS;
+    bool okC = false;                                     // early probe of the stage's cost rows
+    for (int t = 0; t < nRows; t += rps) {
+        const int rows = min(rps, nRows - t);
         SWEEP_PROG(0, rwarp == 0);
         SWEEP_TR(0, 0, rwarp == 0);
         if (!okC) sweep_wait(a, SmemBar{rc.bar + BAR_FULL}, rc.par, 3, t);
         SWEEP_TR(0, 1, rwarp == 0);
-        // probes whose latency hides behind the path step
-        const bool okI = bar_test(ri.bar + BAR_FULL, ri.par);
-        const bool okP = t >= K ? bar_test(rp.bar + BAR_FREEP, rp.par ^ 1u) : true;
-        {
-            uint32_t Cc[NREG];
-            lds_vec<NREG, LPC>(Cc, rc.data);
-            mB = path_step_m<NREG, LPC>(LB, mB, Cc, a.P1p, a.P2mP1p, lm);
-        }
-        // the cost row is in registers: hand the stage back and look at the next one
-        __syncwarp();
-        if (lane0) bar_arrive(rc.bar + BAR_EMPTY);
-        ring_advance(rc, a.cStrideB, a.cSpanB, 16u, a.cBarSpan, NSC);
-        okC = bar_test(rc.bar + BAR_FULL, rc.par);
-        SWEEP_TR(0, 2, rwarp == 0);
-        if (!okI) sweep_wait(a, SmemBar{ri.bar + BAR_FULL}, ri.par, 4, t);
-        lds_vec<NREG, LPC>(S, ri.data);
+        // probes whose latency hides behind the first path step
+        bool okI = bar_test(ri.bar + BAR_FULL, ri.par);
+        bool okP = bar_test(rp.bar + BAR_FREEP, rp.par ^ 1u);   // (a fresh barrier passes the opposite parity at once)
+        for (int r = rows; r > 0; r--) {
+            uint32_t S[NREG];
+            {
+                uint32_t Cc[NREG];
+                lds_vec<NREG, LPC>(Cc, rc.data);
+                mB = path_step_m<NREG, LPC>(LB, mB, Cc, a.P1p, a.P2mP1p, lm);
+            }
+            if constexpr (RPS == 1) {
+                // one row per stage: the cost row is in registers, hand the stage back now and look at the next one
+                __syncwarp();
+                if (lane0) bar_arrive(rc.bar + BAR_EMPTY);
+                ring_advance(rc, a.cStrideB, a.cSpanB, 16u, a.cBarSpan, NSC);
+                okC = bar_test(rc.bar + BAR_FULL, rc.par);
+            } else {
+                rc.data += a.cRowB;
+            }
+            SWEEP_TR(0, 2, rwarp == 0);
+            if (!okI) { sweep_wait(a, SmemBar{ri.bar + BAR_FULL}, ri.par, 4, t); okI = true; }
+            lds_vec<NREG, LPC>(S, ri.data);
 #pragma unroll
-        for (int j = 0; j < NREG; j++) S[j] = sacc<SAT>(S[j], LB[j]);
-        if (hasB) {
-            uint32_t Bv[NREG];
-            lds_vec<NREG, LPC>(Bv, ri.data + a.iBB);
+            for (int j = 0; j < NREG; j++) S[j] = sacc<SAT>(S[j], LB[j]);
+            if (hasB) {
+                uint32_t Bv[NREG];
+                lds_vec<NREG, LPC>(Bv, ri.data + a.iBB);
 #pragma unroll
-            for (int j = 0; j < NREG; j++) S[j] = sacc<SAT>(S[j], Bv[j]);
+                for (int j = 0; j < NREG; j++) S[j] = sacc<SAT>(S[j], Bv[j]);
+            }
+            SWEEP_TR(0, 3, rwarp == 0);
+            if (!okP) { sweep_wait(a, SmemBar{rp.bar + BAR_FREEP}, rp.par ^ 1u, 5, t); okP = true; }
+            SWEEP_TR(0, 4, rwarp == 0);
+            if (own) sts_vec<NREG, LPC>(S, rp.data);
+            ri.data += a.iRowB; rp.data += a.pRowB;
         }
-        SWEEP_TR(0, 3, rwarp == 0);
-        if (!okP) sweep_wait(a, SmemBar{rp.bar + BAR_FREEP}, rp.par ^ 1u, 5, t);
-        SWEEP_TR(0, 4, rwarp == 0);
-        if (own) sts_vec<NREG, LPC>(S, rp.data);
+        // the stage's rows are consumed: hand the cost and input stages back, publish the S slot, look at the next stage
         __syncwarp();
         if (lane0) {
-            if (!(SGBM_DBG_HOOK(a.dbgStall) && t == 5 && blockIdx.x == 0)) bar_arrive(rp.bar + BAR_FULLV);
+            if constexpr (RPS > 1) bar_arrive(rc.bar + BAR_EMPTY);
+            if (!(SGBM_DBG_HOOK(a.dbgStall) && t <= 5 && 5 < t + rps && blockIdx.x == 0)) bar_arrive(rp.bar + BAR_FULLV);
             bar_arrive(ri.bar + BAR_EMPTY);
         }
         SWEEP_TR(0, 5, rwarp == 0);
-        ring_advance(ri, a.iStrideB, a.iSpanB, 16u, a.iBarSpan, NSI);
-        ring_advance(rp, a.pStrideB, a.pSpanB, 32u, a.pBarSpan, K);
+        ring_advance_moved(ri, a.iSpanB, 16u, a.iBarSpan, NSI);
+        ring_advance_moved(rp, a.pSpanB, 32u, a.pBarSpan, K);
+        if constexpr (RPS > 1) {
+            ring_advance_moved(rc, a.cSpanB, 16u, a.cBarSpan, NSC);
+            okC = bar_test(rc.bar + BAR_FULL, rc.par);
+        }
     }
 }
 
@@ -462,7 +466,7 @@ __device__ __forceinline__ void sweep_wta(const SweepArgs &a, const uint32_t (&S
 }
 
 // ---- roles A (DIR = +1) and C (DIR = -1, finishes the pixel) -----------------------------------------
-template <int NREG, int LPC, int DIR, bool SAT, bool WROLE>
+template <int NREG, int LPC, int DIR, bool SAT, bool WROLE, int RPS>
 __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepSmem &s, int rwarp, int strip, int xs,
                                                 int xe, int yBegin, int yStep, int nRows)
 {
@@ -536,7 +540,8 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
     char *soutRow = (FINAL && !WROLE && a.sout)
                         ? reinterpret_cast<char *>(a.sout) + ((long long)yBegin * g.rowStride + (long long)(xs - HG) * Dp) * 2 + 16 * lg : nullptr;
     const long long soutStep = (long long)yStep * g.rowStride * 2;
-    bool okC = false;                                     // early probe of the row's cost stage
+    constexpr int rps = RPS;
+    bool okC = false;                                     // early probe of the stage's cost rows
     for (int n = 0; tq < nRows; n++) {
         // ---- super-step start: batch nm restarts from the neighbour's published columns -------------
         if (n > 0) {
@@ -567,91 +572,108 @@ __device__ __forceinline__ void sweep_role_diag(const SweepArgs &a, const SweepS
         const int rowsHere = min(R, nRows - tq);
         const bool pubStep = pubOn && tq + R < nRows;     // a full super-step that is not the image's last rows
         int q = DIR > 0 ? p : WW - 1 - p;
-        // (rl counts the rows left in the super-step; the row index t = tq + rowsHere - rl is only needed off the hot path)
-        for (int rl = rowsHere; rl > 0; rl--) {
+        // (rl counts the rows left in the super-step; the row index t = tq + rowsHere - rl is only needed off the hot path.
+        //  R is a multiple of the rows per ring stage, so a stage never straddles two super-steps.)
+        for (int rl = rowsHere; rl > 0; rl -= rps) {
+            const int rows = min(rps, rl);
 #if defined(SGBM_SWEEP_TRACING)
             const int t = tq + rowsHere - rl;
 #endif
             SWEEP_PROG(DIR > 0 ? 1 : 3, rwarp == 0);
             SWEEP_PROG(DIR > 0 ? 2 : 4, rwarp == a.nwA - 1);
-            const bool active = (uint32_t)q - aLo < aLen;
-            const bool own = active && (uint32_t)q - hgU < swsU;
-            if (edge && (DIR > 0 ? q <= edgeQ : q >= edgeQ)) {   // chain enters the image: predecessor outside
-#pragma unroll
-                for (int j = 0; j < NREG; j++) L[j] = 0;
-                m = 0;
-            }
             SWEEP_TR(DIR > 0 ? 1 : 2, 0, rwarp == a.nwA / 2);
             if (!okC) sweep_wait(a, SmemBar{rc.bar + BAR_FULL}, rc.par, DIR > 0 ? 8 : 9, tq);
             SWEEP_TR(DIR > 0 ? 1 : 2, 1, rwarp == a.nwA / 2);
-            const bool okS = bar_test(rp.bar + WAIT_BAR, rp.par);   // latency hides behind the path step
-            if (__any_sync(0xFFFFFFFFu, active)) {       // inactive groups compute garbage that is never used
-                uint32_t Cc[NREG];
-                lds_vec<NREG, LPC>(Cc, rc.data + (active ? (uint32_t)q : hgU) * colB);
-                m = path_step_m<NREG, LPC>(L, m, Cc, a.P1p, a.P2mP1p, lm);
-            }
-            // the cost row is in registers: hand the stage back and look at the next one
-            __syncwarp();
-            if (lane0) bar_arrive(rc.bar + BAR_EMPTY);
-            ring_advance(rc, a.cStrideB, a.cSpanB, 16u, a.cBarSpan, NSC);
-            okC = bar_test(rc.bar + BAR_FULL, rc.par);
-            // ---- super-step end: publish the columns the neighbour continues ------------------------
-            if (pubStep && rl == 1) {
-                const int pi = q - pubQ0;
-                const bool pub = own && pi >= 0 && pi < R;
-                if (pub) {
-                    uint16_t *h = haloOut + ((size_t)hs * R + pi) * haloStride;
-                    store_vec<NREG, LPC>(L, h, lg);
-                    if (lg == 0) *reinterpret_cast<unsigned int *>(h + Dp) = m;
+            bool okS = bar_test(rp.bar + WAIT_BAR, rp.par);   // latency hides behind the first path step
+            for (int r = rows; r > 0; r--) {
+                const bool active = (uint32_t)q - aLo < aLen;
+                const bool own = active && (uint32_t)q - hgU < swsU;
+                if (edge && (DIR > 0 ? q <= edgeQ : q >= edgeQ)) {   // chain enters the image: predecessor outside
+#pragma unroll
+                    for (int j = 0; j < NREG; j++) L[j] = 0;
+                    m = 0;
                 }
-                __syncwarp();
-                if (pub && lg == 0) {
-                    // st.release.gpu is itself a release fence: cumulative over the group's stores, which the
-                    // __syncwarp above has ordered before this lane (a separate __threadfence() doubled the
-                    // MEMBAR / CCTL.IVALL cost of every publication)
-                    st_release_u32(flagOut + hs * R + pi, (unsigned)(n + 1));
+                if (__any_sync(0xFFFFFFFFu, active)) {       // inactive groups compute garbage that is never used
+                    uint32_t Cc[NREG];
+                    lds_vec<NREG, LPC>(Cc, rc.data + (active ? (uint32_t)q : hgU) * colB);
+                    m = path_step_m<NREG, LPC>(L, m, Cc, a.P1p, a.P2mP1p, lm);
                 }
-            }
-            // ---- S slot of this row -----------------------------------------------------------------
-            SWEEP_TR(DIR > 0 ? 1 : 2, 2, rwarp == a.nwA / 2);
-            if (!okS) sweep_wait(a, SmemBar{rp.bar + WAIT_BAR}, rp.par, DIR > 0 ? 10 : 11, tq);
-            SWEEP_TR(DIR > 0 ? 1 : 2, 3, rwarp == a.nwA / 2);
-            uint32_t S[NREG];
-            if (own) {
-                const uint32_t ps = rp.data + ((uint32_t)q - hgU) * colB;
-                lds_vec<NREG, LPC>(S, ps);
-#pragma unroll
-                for (int j = 0; j < NREG; j++) S[j] = sacc<SAT>(S[j], L[j]);
-                if (!FINAL || WROLE) sts_vec<NREG, LPC>(S, ps);
-            } else if (FINAL && !WROLE) {
-#pragma unroll
-                for (int j = 0; j < NREG; j++) S[j] = SGBM_MAX_S;
-            }
-            __syncwarp();
-            if (lane0) bar_arrive(rp.bar + DONE_BAR);
-            SWEEP_TR(DIR > 0 ? 1 : 2, 4, rwarp == a.nwA / 2);
-            if (FINAL && !WROLE && __any_sync(0xFFFFFFFFu, own)) {
-                const int y = yBegin + (tq + rowsHere - rl) * yStep;
-                const int x1 = own ? xs - HG + q : xs;
-                if (a.sout) {
-                    if (own) {
-                        uint4 *po = reinterpret_cast<uint4 *>(soutRow + (size_t)((uint32_t)q * colB));
-#pragma unroll
-                        for (int k4 = 0; k4 < NREG / 4; k4++) po[LPC * k4] = make_uint4(S[4 * k4 + 0], S[4 * k4 + 1], S[4 * k4 + 2], S[4 * k4 + 3]);
-                    }
+                if constexpr (RPS == 1) {
+                    // one row per stage: the cost row is in registers, hand the stage back now and look at the next one
+                    __syncwarp();
+                    if (lane0) bar_arrive(rc.bar + BAR_EMPTY);
+                    ring_advance(rc, a.cStrideB, a.cSpanB, 16u, a.cBarSpan, NSC);
+                    okC = bar_test(rc.bar + BAR_FULL, rc.par);
                 } else {
-                    if (!SAT) {
-#pragma unroll
-                        for (int j = 0; j < NREG; j++) S[j] = pmin(S[j], SGBM_MAX_S);
-                    }
-                    if (a.sdbg && own) store_vec<NREG, LPC>(S, a.sdbg + (size_t)y * g.rowStride + (size_t)x1 * Dp, lg);
-                    sweep_wta<NREG, LPC>(a, S, ssm, lg, own, x1, y);
+                    rc.data += a.cRowB;
                 }
+                // ---- super-step end: publish the columns the neighbour continues ------------------------
+                if (pubStep && rl + r == rows + 1) {              // last row of the super-step
+                    const int pi = q - pubQ0;
+                    const bool pub = own && pi >= 0 && pi < R;
+                    if (pub) {
+                        uint16_t *h = haloOut + ((size_t)hs * R + pi) * haloStride;
+                        store_vec<NREG, LPC>(L, h, lg);
+                        if (lg == 0) *reinterpret_cast<unsigned int *>(h + Dp) = m;
+                    }
+                    __syncwarp();
+                    if (pub && lg == 0) {
+                        // st.release.gpu is itself a release fence: cumulative over the group's stores, which the
+                        // __syncwarp above has ordered before this lane (a separate __threadfence() doubled the
+                        // MEMBAR / CCTL.IVALL cost of every publication)
+                        st_release_u32(flagOut + hs * R + pi, (unsigned)(n + 1));
+                    }
+                }
+                // ---- S slot of this row -----------------------------------------------------------------
+                SWEEP_TR(DIR > 0 ? 1 : 2, 2, rwarp == a.nwA / 2);
+                if (!okS) { sweep_wait(a, SmemBar{rp.bar + WAIT_BAR}, rp.par, DIR > 0 ? 10 : 11, tq); okS = true; }
+                SWEEP_TR(DIR > 0 ? 1 : 2, 3, rwarp == a.nwA / 2);
+                uint32_t S[NREG];
+                if (own) {
+                    const uint32_t ps = rp.data + ((uint32_t)q - hgU) * colB;
+                    lds_vec<NREG, LPC>(S, ps);
+#pragma unroll
+                    for (int j = 0; j < NREG; j++) S[j] = sacc<SAT>(S[j], L[j]);
+                    if (!FINAL || WROLE) sts_vec<NREG, LPC>(S, ps);
+                } else if (FINAL && !WROLE) {
+#pragma unroll
+                    for (int j = 0; j < NREG; j++) S[j] = SGBM_MAX_S;
+                }
+                if (FINAL && !WROLE && __any_sync(0xFFFFFFFFu, own)) {
+                    const int y = yBegin + (tq + rowsHere - rl + rows - r) * yStep;
+                    const int x1 = own ? xs - HG + q : xs;
+                    if (a.sout) {
+                        if (own) {
+                            uint4 *po = reinterpret_cast<uint4 *>(soutRow + (size_t)((uint32_t)q * colB));
+#pragma unroll
+                            for (int k4 = 0; k4 < NREG / 4; k4++) po[LPC * k4] = make_uint4(S[4 * k4 + 0], S[4 * k4 + 1], S[4 * k4 + 2], S[4 * k4 + 3]);
+                        }
+                    } else {
+                        if (!SAT) {
+#pragma unroll
+                            for (int j = 0; j < NREG; j++) S[j] = pmin(S[j], SGBM_MAX_S);
+                        }
+                        if (a.sdbg && own) store_vec<NREG, LPC>(S, a.sdbg + (size_t)y * g.rowStride + (size_t)x1 * Dp, lg);
+                        sweep_wta<NREG, LPC>(a, S, ssm, lg, own, x1, y);
+                    }
+                }
+                q += DIR;
+                if (FINAL && !WROLE) soutRow += soutStep;
+                rp.data += a.pRowB;
+            }
+            // the stage's rows are consumed: hand the cost stage back, pass the S slot on, look at the next stage
+            __syncwarp();
+            if (lane0) {
+                if constexpr (RPS > 1) bar_arrive(rc.bar + BAR_EMPTY);
+                bar_arrive(rp.bar + DONE_BAR);
+            }
+            SWEEP_TR(DIR > 0 ? 1 : 2, 4, rwarp == a.nwA / 2);
+            ring_advance_moved(rp, a.pSpanB, 32u, a.pBarSpan, K);
+            if constexpr (RPS > 1) {
+                ring_advance_moved(rc, a.cSpanB, 16u, a.cBarSpan, NSC);
+                okC = bar_test(rc.bar + BAR_FULL, rc.par);
             }
             SWEEP_TR(DIR > 0 ? 1 : 2, 5, rwarp == a.nwA / 2);
-            q += DIR;
-            if (FINAL && !WROLE) soutRow += soutStep;
-            ring_advance(rp, a.pStrideB, a.pSpanB, 32u, a.pBarSpan, K);
         }
         p += rowsHere; tq += rowsHere;
         if (++nm == NB) nm = 0;
@@ -739,7 +761,7 @@ __device__ __forceinline__ void sweep_wta_slot(const SweepArgs &a, uint32_t colA
     }
 }
 
-template <int NREG, int LPC, bool SAT>
+template <int NREG, int LPC, bool SAT, int RPS>
 __device__ __forceinline__ void sweep_role_w(const SweepArgs &a, const SweepSmem &s, int wwarp, int xs, int SW, int yBegin,
                                              int yStep, int nRows)
 {
@@ -755,21 +777,27 @@ __device__ __forceinline__ void sweep_role_w(const SweepArgs &a, const SweepSmem
     // the row period of the whole kernel, so the W warps are split into wRG row groups that take alternate rows.
     const int wRG = a.wRG, wPR = a.wPR;
     const int rgrp = wwarp / wPR, wq = wwarp - rgrp * wPR;
+    constexpr int rps = RPS;
     RingPos rp = ring_start(s.aP, s.barP, K);
     if (rgrp) ring_advance_n(rp, rgrp, a.pStrideB, a.pSpanB, 32u, a.pBarSpan, K);
-    for (int t = rgrp; t < nRows; t += wRG) {
-        const int y = yBegin + t * yStep;
+    for (int t = rgrp * rps; t < nRows; t += wRG * rps) {
+        const int rows = min(rps, nRows - t);
         SWEEP_PROG(5, wwarp == 0);
         SWEEP_TR(3, 4, wwarp == 0);
         sweep_wait(a, SmemBar{rp.bar + BAR_FULLW}, rp.par, 12, t);
         SWEEP_TR(3, 5, wwarp == 0);
-        for (int it = 0; it < a.wPass; it++) {
-            const int gi = (it * wPR + wq) * GPW + lane / LPC;
-            const bool own = gi < SW;
-            if (!__any_sync(0xFFFFFFFFu, own)) continue;
-            const int ci = own ? gi : SW - 1;
-            // (groups without a column read column SW-1 along with the warp; all their writes are guarded by own)
-            sweep_wta_slot<NREG, LPC, SAT>(a, rp.data + (uint32_t)ci * colB, lg, padMask, gmask, own, xs + ci, y);
+        uint32_t dp = rp.data;
+        for (int r = 0; r < rows; r++) {
+            const int y = yBegin + (t + r) * yStep;
+            for (int it = 0; it < a.wPass; it++) {
+                const int gi = (it * wPR + wq) * GPW + lane / LPC;
+                const bool own = gi < SW;
+                if (!__any_sync(0xFFFFFFFFu, own)) continue;
+                const int ci = own ? gi : SW - 1;
+                // (groups without a column read column SW-1 along with the warp; all their writes are guarded by own)
+                sweep_wta_slot<NREG, LPC, SAT>(a, dp + (uint32_t)ci * colB, lg, padMask, gmask, own, xs + ci, y);
+            }
+            dp += a.pRowB;
         }
         __syncwarp();
         SWEEP_TR(3, 6, wwarp == 0);
@@ -780,7 +808,7 @@ __device__ __forceinline__ void sweep_role_w(const SweepArgs &a, const SweepSmem
 
 template <int NREG, bool WROLE> struct SweepMaxThreads { static const int value = (NREG >= 12 && !WROLE) ? 768 : 1024; };
 
-template <int NREG, int LPC, bool SAT, bool WROLE>
+template <int NREG, int LPC, bool SAT, bool WROLE, int RPS>
 __global__ void __launch_bounds__((SweepMaxThreads<NREG, WROLE>::value), 1) k_sweep(SweepArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -810,28 +838,28 @@ __global__ void __launch_bounds__((SweepMaxThreads<NREG, WROLE>::value), 1) k_sw
         if (warp < a.aV + 2 * a.aA) {
             if (SPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 72;");
             if (warp < a.aV) {
-                if (warp < a.nwV) sweep_role_v<NREG, LPC, SAT>(a, s, warp, xe - xs, nRows);
+                if (warp < a.nwV) sweep_role_v<NREG, LPC, SAT, RPS>(a, s, warp, xe - xs, nRows);
             } else if (warp < a.aV + a.aA) {
-                if (warp - a.aV < a.nwA) sweep_role_diag<NREG, LPC, +1, SAT, true>(a, s, warp - a.aV, strip, xs, xe, yBegin, yStep, nRows);
+                if (warp - a.aV < a.nwA) sweep_role_diag<NREG, LPC, +1, SAT, true, RPS>(a, s, warp - a.aV, strip, xs, xe, yBegin, yStep, nRows);
             } else {
-                if (warp - a.aV - a.aA < a.nwA) sweep_role_diag<NREG, LPC, -1, SAT, true>(a, s, warp - a.aV - a.aA, strip, xs, xe, yBegin, yStep, nRows);
+                if (warp - a.aV - a.aA < a.nwA) sweep_role_diag<NREG, LPC, -1, SAT, true, RPS>(a, s, warp - a.aV - a.aA, strip, xs, xe, yBegin, yStep, nRows);
             }
         } else {
             if (SPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
             const int ww = warp - a.aV - 2 * a.aA;
-            if (ww < a.nwW) sweep_role_w<NREG, LPC, SAT>(a, s, ww, xs, xe - xs, yBegin, yStep, nRows);
-            else if (ww == a.nwW && (threadIdx.x & 31) == 0) sweep_producer(a, s, xs, xe, yBegin, yStep, nRows);
+            if (ww < a.nwW) sweep_role_w<NREG, LPC, SAT, RPS>(a, s, ww, xs, xe - xs, yBegin, yStep, nRows);
+            else if (ww == a.nwW && (threadIdx.x & 31) == 0) sweep_producer_t<RPS, false>(a, s, xs, xe, yBegin, yStep, nRows);
         }
         return;
     }
     if (warp < a.nwV) {
-        sweep_role_v<NREG, LPC, SAT>(a, s, warp, xe - xs, nRows);
+        sweep_role_v<NREG, LPC, SAT, RPS>(a, s, warp, xe - xs, nRows);
     } else if (warp < a.nwV + a.nwA) {
-        sweep_role_diag<NREG, LPC, +1, SAT, false>(a, s, warp - a.nwV, strip, xs, xe, yBegin, yStep, nRows);
+        sweep_role_diag<NREG, LPC, +1, SAT, false, RPS>(a, s, warp - a.nwV, strip, xs, xe, yBegin, yStep, nRows);
     } else if (warp < a.nwV + 2 * a.nwA) {
-        sweep_role_diag<NREG, LPC, -1, SAT, false>(a, s, warp - a.nwV - a.nwA, strip, xs, xe, yBegin, yStep, nRows);
+        sweep_role_diag<NREG, LPC, -1, SAT, false, RPS>(a, s, warp - a.nwV - a.nwA, strip, xs, xe, yBegin, yStep, nRows);
     } else if ((threadIdx.x & 31) == 0) {
-        sweep_producer_pf(a, s, xs, xe, yBegin, yStep, nRows);
+        sweep_producer_t<RPS, true>(a, s, xs, xe, yBegin, yStep, nRows);
     }
 }
 
@@ -842,17 +870,21 @@ static size_t sweep_layout(SweepArgs &a, int groupsC, bool scratch)
 {
     const Geo &g = a.g;
     const size_t col = (size_t)g.Dp * 2;
+    const size_t rps = (size_t)a.rps;
     size_t off = 0;
-    a.stgCOff = (unsigned)off; off += (size_t)a.NSC * (a.SW + 2 * (a.R - 1)) * col;
-    a.stgIOff = (unsigned)off; off += (size_t)a.NSI * a.nAB * a.SW * col;
-    a.pOff = (unsigned)off; off += (size_t)a.K * a.SW * col;
+    a.stgCOff = (unsigned)off; off += (size_t)a.NSC * rps * (a.SW + 2 * (a.R - 1)) * col;
+    a.stgIOff = (unsigned)off; off += (size_t)a.NSI * rps * a.nAB * a.SW * col;
+    a.pOff = (unsigned)off; off += (size_t)a.K * rps * a.SW * col;
     a.ssmOff = (unsigned)off; if (scratch) off += (size_t)groupsC * col;
     off = (off + 15) & ~(size_t)15;
     a.barOff = (unsigned)off; off += (size_t)(2 * a.NSC + 2 * a.NSI + 4 * a.K) * 8;
     a.colB = (unsigned)col;
-    a.cStrideB = (unsigned)((a.SW + 2 * (a.R - 1)) * col); a.cSpanB = a.cStrideB * (unsigned)a.NSC; a.cBarSpan = 16u * (unsigned)a.NSC;
-    a.iBB = (unsigned)(a.SW * col); a.iStrideB = a.iBB * (unsigned)a.nAB; a.iSpanB = a.iStrideB * (unsigned)a.NSI; a.iBarSpan = 16u * (unsigned)a.NSI;
-    a.pStrideB = a.iBB; a.pSpanB = a.pStrideB * (unsigned)a.K; a.pBarSpan = 32u * (unsigned)a.K;
+    a.cRowB = (unsigned)((a.SW + 2 * (a.R - 1)) * col);
+    a.cStrideB = a.cRowB * (unsigned)rps; a.cSpanB = a.cStrideB * (unsigned)a.NSC; a.cBarSpan = 16u * (unsigned)a.NSC;
+    a.iBB = (unsigned)(a.SW * col); a.iRowB = a.iBB * (unsigned)a.nAB;
+    a.iStrideB = a.iRowB * (unsigned)rps; a.iSpanB = a.iStrideB * (unsigned)a.NSI; a.iBarSpan = 16u * (unsigned)a.NSI;
+    a.pRowB = a.iBB;
+    a.pStrideB = a.pRowB * (unsigned)rps; a.pSpanB = a.pStrideB * (unsigned)a.K; a.pBarSpan = 32u * (unsigned)a.K;
     return off;
 }
 
@@ -871,9 +903,9 @@ static bool sweep_plan(const Geo &g, int numSMs, bool wrole, bool wta, int maxTh
     if (kn.vr > 0) R = kn.vr >= Rmin ? kn.vr : Rmin;
     if (R > 16) R = 16;
     int Kwant = 5, NSCwant = 5, NSIwant = 3;
-    if (kn.sweepK >= 1 && kn.sweepK <= 8) Kwant = kn.sweepK;
-    if (kn.sweepNSC >= 2 && kn.sweepNSC <= 8) NSCwant = kn.sweepNSC;
-    if (kn.sweepNSI >= 2 && kn.sweepNSI <= 8) NSIwant = kn.sweepNSI;
+    if (kn.sweepK >= 1 && kn.sweepK <= 16) Kwant = kn.sweepK;
+    if (kn.sweepNSC >= 2 && kn.sweepNSC <= 16) NSCwant = kn.sweepNSC;
+    if (kn.sweepNSI >= 2 && kn.sweepNSI <= 16) NSIwant = kn.sweepNSI;
     for (; R >= Rmin; R--) {
         int nstrips = numSMs;
         const int minCols = R > 2 ? R : 2;                // every strip owns >= R (and >= 2) columns
@@ -900,21 +932,52 @@ static bool sweep_plan(const Geo &g, int numSMs, bool wrole, bool wta, int maxTh
         }
         if (threads > maxThreads) continue;
         a.SW = SWmax; a.nstrips = nstrips; a.R = R; a.NB = NB;
-        // ring depths: shrink until the layout fits
-        static const int tries[][3] = {{0, 0, 0}, {0, 0, -1}, {0, -1, -1}, {-1, -1, -1}, {-1, -2, -1}, {-2, -2, -1}, {-2, -3, -1}};
         int wRGwant = wrole ? 7 / a.wPR : 1;              // row groups of the WTA warps: each holds one S slot while it works
         if (kn.sweepWRG >= 1 && kn.sweepWRG < wRGwant) wRGwant = kn.sweepWRG;
-        for (const auto &tr : tries) {
-            a.K = Kwant + (kn.sweepK ? 0 : wRGwant - 1) + tr[0]; a.NSC = NSCwant + tr[1]; a.NSI = NSIwant + tr[2];
-            if (a.K < 1) a.K = 1;
-            if (a.NSC < 2) a.NSC = 2;
-            if (a.NSI < 2) a.NSI = 2;
-            if (wrole) {                                  // the path roles keep at least two slots to themselves
-                a.wRG = wRGwant < a.K - 2 ? wRGwant : (a.K - 2 > 1 ? a.K - 2 : 1);
-                a.nwW = a.wPR * a.wRG;
+        // Rows per ring stage.  Two rows per stage halve the hand-off work per image row (waits, arrives, ring advances:
+        // about half of a role's instructions when a lane holds few registers) at the price of coarser rings; taken when the
+        // rings keep their depth in ROWS (three cost stages, three S stages for the path roles, two input stages) --
+        // otherwise (4K at numDisparities = 256: shared memory is full with one row per stage) one row per stage.
+        const int rpsFirst = (kn.sweepRPS == 1 || (R & 1) || g.nreg > SWEEP_RPS_MAX_NREG) ? 1 : 2;
+        for (int rps = rpsFirst; rps >= 1; rps--) {
+            a.rps = rps;
+            if (rps == 2) {
+                // Measured (720p D=128, 1080p D=192, 4K D=16; sweep time against one row per stage): what matters is the depth
+                // of the cost ring -- 3 stages: no gain, 4: -8 %, 5: -10 %, 8: -11 .. -12 %; two input stages are enough,
+                // and the S ring wants two or three slots beside those the WTA row groups hold.
+                const int K2 = kn.sweepK ? Kwant : 4 + wRGwant;
+                static const int tries2[][2] = {{0, 8}, {0, 6}, {0, 5}, {-1, 5}, {-1, 4}, {-2, 4}};
+                bool ok = false;
+                for (const auto &tr : tries2) {
+                    a.K = K2 + (kn.sweepK ? 0 : tr[0]); a.NSC = kn.sweepNSC ? NSCwant : tr[1]; a.NSI = kn.sweepNSI ? NSIwant : 2;
+                    if (a.K < (wrole ? 3 : 2)) a.K = wrole ? 3 : 2;
+                    if (wrole) { a.wRG = wRGwant < a.K - 2 ? wRGwant : (a.K - 2 > 1 ? a.K - 2 : 1); a.nwW = a.wPR * a.wRG; }
+                    const size_t smem = sweep_layout(a, a.nwA * GPW, wta && !wrole);
+                    if (smem <= (size_t)maxSmem) { *threadsOut = threads; *smemOut = smem; ok = true; break; }
+                }
+                if (ok) return true;
+                if (kn.sweepRPS == 2) {                   // forced (tests): shrink the rings as far as the protocol allows
+                    a.K = wrole ? 3 : 2; a.NSC = 2; a.NSI = 2;
+                    if (wrole) { a.wRG = 1; a.nwW = a.wPR; }
+                    const size_t smem2 = sweep_layout(a, a.nwA * GPW, wta && !wrole);
+                    if (smem2 <= (size_t)maxSmem) { *threadsOut = threads; *smemOut = smem2; return true; }
+                }
+                continue;
             }
-            const size_t smem = sweep_layout(a, a.nwA * GPW, wta && !wrole);
-            if (smem <= (size_t)maxSmem) { *threadsOut = threads; *smemOut = smem; return true; }
+            // ring depths: shrink until the layout fits
+            static const int tries[][3] = {{0, 0, 0}, {0, 0, -1}, {0, -1, -1}, {-1, -1, -1}, {-1, -2, -1}, {-2, -2, -1}, {-2, -3, -1}};
+            for (const auto &tr : tries) {
+                a.K = Kwant + (kn.sweepK ? 0 : wRGwant - 1) + tr[0]; a.NSC = NSCwant + tr[1]; a.NSI = NSIwant + tr[2];
+                if (a.K < 1) a.K = 1;
+                if (a.NSC < 2) a.NSC = 2;
+                if (a.NSI < 2) a.NSI = 2;
+                if (wrole) {                                  // the path roles keep at least two slots to themselves
+                    a.wRG = wRGwant < a.K - 2 ? wRGwant : (a.K - 2 > 1 ? a.K - 2 : 1);
+                    a.nwW = a.wPR * a.wRG;
+                }
+                const size_t smem = sweep_layout(a, a.nwA * GPW, wta && !wrole);
+                if (smem <= (size_t)maxSmem) { *threadsOut = threads; *smemOut = smem; return true; }
+            }
         }
     }
     return false;
@@ -940,41 +1003,21 @@ bool sgbm_sweep_fits(const Geo &g, int numSMs, int mode)
     return true;
 }
 
-// Returns 0 on success, 1 if this geometry does not fit the role-specialised sweep (the caller falls
-// back to k_vertical), negative on error.  WROLE: winner-take-all sweep with the dedicated WTA role.
-template <int NREG, int LPC, bool SAT, bool WROLE>
-static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
+// Launch of one planned sweep with the kernel instantiation for its rows per ring stage.
+template <int NREG, int LPC, bool SAT, bool WROLE, int RPS>
+static int launch_sweep_k(SweepArgs &a, const VertArgs &va, int numSMs, int threads, size_t smem, bool wta, cudaStream_t st)
 {
-    constexpr int GPW = 32 / LPC;
     const Geo &g = va.g;
-    auto kern = k_sweep<NREG, LPC, SAT, WROLE>;
+    auto kern = k_sweep<NREG, LPC, SAT, WROLE, RPS>;
     const SgbmKnobs &kn = sgbm_knobs();
-    const int maxSmem = kn.maxSmemOptin;
     static unsigned long long attrDone = 0;   // one bit per device: function attributes are per device
     {
         SgbmDeviceOnce once(attrDone);
         if (once.first) {
-            SGBM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+            SGBM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kn.maxSmemOptin));
             once.done();
         }
     }
-    SweepArgs a;
-    memset(&a, 0, sizeof(a));
-    a.g = g; a.C = va.C; a.inA = va.inA; a.inB = va.inB; a.sout = va.sout; a.sdbg = va.sdbg; a.raw = va.raw;
-    a.d2key = va.d2key; a.backward = va.backward; a.haloA = va.haloA; a.haloC = va.haloC; a.flagA = va.flagA;
-    a.flagC = va.flagC; a.dbgNoSync = va.dbgNoSync;
-    a.dbgStall = SGBM_DBG_HOOK(kn.dbgStall);
-    a.nAB = va.inB ? 2 : 1;
-    a.urMagic = g.UR < 99 ? 0xFFFFFFFFu / (unsigned)(100 - g.UR) + 1u : 0u;
-    a.pfDist = kn.sweepPF >= 0 ? kn.sweepPF : 8;
-    a.P1p = (unsigned)g.P1 * 0x10001u; a.P2mP1p = (unsigned)(g.P2 - g.P1) * 0x10001u;
-    const bool wta = va.sout == nullptr;
-    if (WROLE && !wta) return 1;
-    const int maxThreads = SweepMaxThreads<NREG, WROLE>::value;
-    int threads = 0;
-    size_t smem = 0;
-    const bool found = sweep_plan(g, numSMs, WROLE, wta, maxThreads, maxSmem, a, &threads, &smem);
-    if (!found) return 1;
     int occ = 0;
     SGBM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
     if (occ * numSMs < a.nstrips) return 1;
@@ -992,8 +1035,8 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
         a.traceStrip = a.nstrips / 2;
     }
     if (kn.verbose)
-        fprintf(stderr, "sweep: wrole=%d wta=%d strips=%d SW=%d R=%d NB=%d nwV=%d nwA=%d nwW=%d (x%d row groups) wPass=%d K=%d NSC=%d NSI=%d threads=%d smem=%zu\n",
-                (int)WROLE, (int)wta, a.nstrips, a.SW, a.R, a.NB, a.nwV, a.nwA, a.nwW, a.wRG, a.wPass, a.K, a.NSC, a.NSI, threads, smem);
+        fprintf(stderr, "sweep: wrole=%d wta=%d strips=%d SW=%d R=%d NB=%d nwV=%d nwA=%d nwW=%d (x%d row groups) wPass=%d rows/stage=%d K=%d NSC=%d NSI=%d threads=%d smem=%zu\n",
+                (int)WROLE, (int)wta, a.nstrips, a.SW, a.R, a.NB, a.nwV, a.nwA, a.nwW, a.wRG, a.wPass, a.rps, a.K, a.NSC, a.NSI, threads, smem);
     void *args[] = {&a};
     SGBM_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)kern, dim3(a.nstrips), dim3(threads), args, smem, st));
     sgbm_count_launch(1);
@@ -1006,10 +1049,40 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
         if (FILE *f = fopen(tracePath, "wb")) { fwrite(hbuf, 1, traceBytes, f); fclose(f); }
         free(hbuf);
         cudaFree(a.trace);
-        fprintf(stderr, "sweep trace: H=%d strips=%d R=%d NB=%d nwV=%d nwA=%d K=%d NSC=%d NSI=%d threads=%d smem=%zu\n", g.H,
-                a.nstrips, a.R, a.NB, a.nwV, a.nwA, a.K, a.NSC, a.NSI, threads, smem);
+        fprintf(stderr, "sweep trace: H=%d strips=%d R=%d NB=%d nwV=%d nwA=%d K=%d NSC=%d NSI=%d rows/stage=%d threads=%d smem=%zu\n", g.H,
+                a.nstrips, a.R, a.NB, a.nwV, a.nwA, a.K, a.NSC, a.NSI, a.rps, threads, smem);
     }
     return 0;
+}
+
+// Returns 0 on success, 1 if this geometry does not fit the role-specialised sweep (the caller falls
+// back to k_vertical), negative on error.  WROLE: winner-take-all sweep with the dedicated WTA role.
+template <int NREG, int LPC, bool SAT, bool WROLE>
+static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
+{
+    const Geo &g = va.g;
+    const SgbmKnobs &kn = sgbm_knobs();
+    SweepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = g; a.C = va.C; a.inA = va.inA; a.inB = va.inB; a.sout = va.sout; a.sdbg = va.sdbg; a.raw = va.raw;
+    a.d2key = va.d2key; a.backward = va.backward; a.haloA = va.haloA; a.haloC = va.haloC; a.flagA = va.flagA;
+    a.flagC = va.flagC; a.dbgNoSync = va.dbgNoSync;
+    a.dbgStall = SGBM_DBG_HOOK(kn.dbgStall);
+    a.nAB = va.inB ? 2 : 1;
+    a.urMagic = g.UR < 99 ? 0xFFFFFFFFu / (unsigned)(100 - g.UR) + 1u : 0u;
+    a.pfDist = kn.sweepPF >= 0 ? kn.sweepPF : 8;
+    a.P1p = (unsigned)g.P1 * 0x10001u; a.P2mP1p = (unsigned)(g.P2 - g.P1) * 0x10001u;
+    const bool wta = va.sout == nullptr;
+    if (WROLE && !wta) return 1;
+    const int maxThreads = SweepMaxThreads<NREG, WROLE>::value;
+    int threads = 0;
+    size_t smem = 0;
+    const bool found = sweep_plan(g, numSMs, WROLE, wta, maxThreads, kn.maxSmemOptin, a, &threads, &smem);
+    if (!found) return 1;
+    if constexpr (NREG <= SWEEP_RPS_MAX_NREG) {
+        if (a.rps == 2) return launch_sweep_k<NREG, LPC, SAT, WROLE, 2>(a, va, numSMs, threads, smem, wta, st);
+    }
+    return launch_sweep_k<NREG, LPC, SAT, WROLE, 1>(a, va, numSMs, threads, smem, wta, st);
 }
 
 // the winner-take-all sweep first tries the kernel with the dedicated WTA role (SGBM_SWEEP_W=0 disables it)

@@ -306,10 +306,14 @@ def test_kernel_generations_agree(sg, monkeypatch, env):
 
 @pytest.mark.parametrize("env", [{"SGBM_SWEEP_WRG": "1"}, {"SGBM_SWEEP_WRG": "2"}, {"SGBM_SWEEP_NWW": "1"}, {"SGBM_HH_SPLIT": "0"},
                                  {"SGBM_SWEEP_PF": "0"}, {"SGBM_SWEEP_PF": "3"}, {"SGBM_SWEEP_K": "3", "SGBM_SWEEP_NSC": "2"},
-                                 {"SGBM_SWEEP_K": "8", "SGBM_SWEEP_NSI": "2"}, {"SGBM_VR": "16"}, {"SGBM_VR": "12", "SGBM_SWEEP_WRG": "3"}])
+                                 {"SGBM_SWEEP_K": "8", "SGBM_SWEEP_NSI": "2"}, {"SGBM_VR": "16"}, {"SGBM_VR": "12", "SGBM_SWEEP_WRG": "3"},
+                                 {"SGBM_SWEEP_RPS": "1"}, {"SGBM_SWEEP_RPS": "2"}, {"SGBM_SWEEP_RPS": "2", "SGBM_VR": "2"},
+                                 {"SGBM_SWEEP_RPS": "2", "SGBM_SWEEP_K": "3", "SGBM_SWEEP_NSC": "2"},
+                                 {"SGBM_SWEEP_RPS": "2", "SGBM_SWEEP_K": "12", "SGBM_SWEEP_NSC": "9", "SGBM_SWEEP_NSI": "4"}])
 def test_sweep_schedule_knobs(sg, monkeypatch, env):
     """The round-2 schedule options of the sweeps -- row groups of the winner-take-all warps, warps per row, where MODE_HH
-    reads L_hB, the producer's L2 prefetch distance, ring depths, 12 / 16 rows per super-step -- never change a bit: narrow
+    reads L_hB, the producer's L2 prefetch distance, ring depths, 12 / 16 rows per super-step, one or two rows per ring
+    stage -- never change a bit: narrow
     strips (many row groups) and wide ones, few and many disparities, saturating and plain accumulation, three frames each."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -321,6 +325,22 @@ def test_sweep_schedule_knobs(sg, monkeypatch, env):
             st = sg.StereoSGBM_create(**_kw(p))
             for rep in range(3):
                 assert _mismatch(st.compute(l, r), ref) == 0, (env, W, D, mode, rep)
+
+
+@pytest.mark.parametrize("H", [1, 2, 3, 9, 95, 97])
+@pytest.mark.parametrize("rps", ["1", "2"])
+def test_sweep_rows_per_stage_odd_heights(sg, monkeypatch, H, rps):
+    """Two image rows per ring stage: the last stage of an odd-height image holds one row, super-steps end on stage
+    boundaries; every mode that sweeps, forward and backward, against the same frames with one row per stage."""
+    monkeypatch.setenv("SGBM_SWEEP_RPS", rps)
+    for (W, D, bs) in [(900, 64, 5), (1400, 16, 9), (800, 192, 3)]:
+        l, r, _ = make_pair(W, H, D, seed=H + D)
+        for mode in (0, 1):
+            p = OracleParams(0, D, bs, 8 * bs * bs, 32 * bs * bs, 1, 63, 10, 0, 0, mode)
+            ref = oracle.compute(p, l, r)
+            st = sg.StereoSGBM_create(**_kw(p))
+            for rep in range(2):
+                assert _mismatch(st.compute(l, r), ref) == 0, (H, rps, W, D, mode, rep)
 
 
 @pytest.mark.parametrize("R", [8, 2])
