@@ -168,6 +168,15 @@ int sgbm_remap_linear_u8(const uint8_t *src, int src_w, int src_h, int channels,
                          void *cuda_stream);
 
 /*
+ * Page-locked host memory for results.  A result array that lives in page-locked memory receives the
+ * device -> host copy of sgbm_compute_host directly (no staging copy, no page faults of a freshly
+ * allocated array): the Python binding hands out the arrays `stereo.compute(imgL, imgR)` returns
+ * (main.ipynb:668) from a recycling pool of such blocks.  cudaHostAlloc(portable) / cudaFreeHost.
+ */
+int sgbm_host_alloc(size_t bytes, void **out);
+int sgbm_host_free(void *p);
+
+/*
  * Test hooks (used by tests/ only): copy an internal stage of the LAST frame computed by `h` to
  * a host buffer in canonical [y][x1][d] int16 order.  which: 0 = block cost C, 1 = aggregated S
  * (only after sgbm_debug_keep(h,1) was set before compute), 2 = raw disparity before median.

@@ -27,6 +27,8 @@ int sgbm_launch_vertical(VertArgs &a, int ndir, int numSMs, cudaStream_t st);
 bool sgbm_sweep_fits(const Geo &g, int numSMs, int mode);
 int sgbm_launch_fill_i16(int16_t *p, size_t n, int v, cudaStream_t st);
 int sgbm_launch_lrcheck(const Geo &g, int16_t *raw, const unsigned int *d2key, cudaStream_t st);
+int sgbm_launch_init_wta(int16_t *raw, unsigned int *d2key, size_t n, int INV, cudaStream_t st);
+int sgbm_launch_lr_median(const Geo &g, const int16_t *raw, const unsigned int *d2key, int16_t *dst, long long dstPitchElems, cudaStream_t st);
 int sgbm_launch_median(const int16_t *src, int16_t *dst, int W, int H, long long dstPitchElems, cudaStream_t st);
 int sgbm_launch_speckles(int16_t *img, int W, int H, int newVal, int maxSize, int maxDiff, void *scratch, cudaStream_t st);
 int sgbm_launch_disp_to_float(const int16_t *d, float *out, size_t n, cudaStream_t st);
@@ -570,8 +572,7 @@ static int compute_frame(sgbm_handle *h, int lane, int sweepSMs, const Geo &g, c
         for (int b = 0; b < bands; b++) SGBM_CUDA_CHECK(cudaStreamWaitEvent(st, h->evBandJoin[lane][b], 0));
     } else if ((rc = sgbm_launch_horizontal(g, C, LhA, LhB, 0, g.H, st))) return rc;
     if ((rc = prof_mark(h, ST_HORIZONTAL, st))) return rc;
-    if ((rc = sgbm_launch_fill_i16(raw, (size_t)g.W * g.H, g.INV, st))) return rc;
-    SGBM_CUDA_CHECK(cudaMemsetAsync(d2key, 0xFF, (size_t)g.W * g.H * 4, st));
+    if ((rc = sgbm_launch_init_wta(raw, d2key, (size_t)g.W * g.H, g.INV, st))) return rc;
     if ((rc = prof_mark(h, ST_INIT, st))) return rc;
 
     VertArgs a;
@@ -611,13 +612,15 @@ static int compute_frame(sgbm_handle *h, int lane, int sweepSMs, const Geo &g, c
         break;
     }
     if ((rc = prof_mark(h, ST_VERT_WTA, st))) return rc;
-    if ((rc = sgbm_launch_lrcheck(g, raw, d2key, st))) return rc;
+    // LR check and 3x3 median are one kernel; with the debug hook on, the stand-alone LR check runs first so that
+    // sgbm_debug_fetch(2) finds the checked raw disparity (the check is idempotent)
+    if (h->keep && (rc = sgbm_launch_lrcheck(g, raw, d2key, st))) return rc;
     if ((rc = prof_mark(h, ST_LRCHECK, st))) return rc;
     const bool dense = outPitchElems == g.W;
     const bool speck = p.speckleWindowSize > 0;
     int16_t *mdst = (speck && !dense) ? med : out;
     long long mpitch = (speck && !dense) ? g.W : outPitchElems;
-    if ((rc = sgbm_launch_median(raw, mdst, g.W, g.H, mpitch, st))) return rc;
+    if ((rc = sgbm_launch_lr_median(g, raw, d2key, mdst, mpitch, st))) return rc;
     if ((rc = prof_mark(h, ST_MEDIAN, st))) return rc;
     if (speck) {
         if ((rc = sgbm_launch_speckles(mdst, g.W, g.H, g.INV, p.speckleWindowSize, 16 * p.speckleRange, base + L.speck, st))) return rc;
@@ -909,6 +912,25 @@ extern "C" int sgbm_remap_linear_u8(const uint8_t *src, int src_w, int src_h, in
     if (src_w > 32767 || src_h > 32767) return sgbm_fail(SGBM_E_UNSUPPORTED, "source larger than 32767 pixels (cv2 asserts the same for fixed-point remap)");
     return sgbm_launch_remap_linear(src, src_w, src_h, channels, (long long)src_pitch_bytes, map1, map2, W, H, dst,
                                     (long long)dst_pitch_bytes, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int sgbm_host_alloc(size_t bytes, void **out)
+{
+    if (!out || bytes == 0) return sgbm_fail(SGBM_E_INVALID_ARG, "bad argument");
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *out = nullptr;
+        return sgbm_fail(SGBM_E_NOMEM, "cudaHostAlloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return 0;
+}
+extern "C" int sgbm_host_free(void *p)
+{
+    if (!p) return 0;
+    SGBM_CUDA_CHECK(cudaFreeHost(p));
+    return 0;
 }
 
 extern "C" int sgbm_debug_keep(sgbm_handle *h, int on)

@@ -13,6 +13,22 @@ __global__ void k_fill_i16(int16_t *p, size_t n, int16_t v)
     if (i < n) p[i] = v;
 }
 
+// Start of a frame's winner-take-all: raw disparity = INV everywhere, disp2 keys = "never hit".  One kernel, 128-bit stores.
+__global__ void k_init_wta(int16_t *raw, unsigned int *d2key, size_t n, int INV)
+{
+    const size_t i8 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (i8 >= n) return;
+    const unsigned int v2 = ((unsigned int)INV & 0xFFFFu) * 0x10001u;
+    if (i8 + 8 <= n) {
+        *reinterpret_cast<uint4 *>(raw + i8) = make_uint4(v2, v2, v2, v2);
+        const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        reinterpret_cast<uint4 *>(d2key + i8)[0] = ones;
+        reinterpret_cast<uint4 *>(d2key + i8)[1] = ones;
+    } else {
+        for (size_t i = i8; i < n; i++) { raw[i] = (int16_t)INV; d2key[i] = 0xFFFFFFFFu; }
+    }
+}
+
 // ---- LR check ---------------------------------------------------------------------------------
 // d2key[y][x2] = (cost << 16) | (0xFFFF - x1) of the winning left pixel, 0xFFFFFFFF if never hit.
 // disp2[x2] = (x1 + minX1) - x2 for a hit, INV (the x16-scaled marker, [P2]) otherwise.
@@ -57,6 +73,62 @@ __global__ void k_median3x3(const int16_t *src, int16_t *dst, int W, int H, long
     cswap(p3, p6); cswap(p1, p4); cswap(p2, p5); cswap(p4, p7); cswap(p4, p2); cswap(p6, p4);
     cswap(p4, p2);
     dst[(size_t)y * dstPitchElems + x] = (int16_t)p4;
+}
+
+// ---- LR check + 3x3 median in one pass (the frame pipeline; the two kernels above serve the debug hook and the public
+// medianBlur3) ----------------------------------------------------------------------------------------------------------
+// A CTA produces a LM_TW x LM_TH tile of the median: it first applies the LR check to the (LM_TW + 2) x (LM_TH + 2) raw
+// pixels the tile's windows touch (replicate border = the checked value of the clamped pixel) into shared memory, then takes
+// the medians from there: the raw image is read once and the checked image never exists in HBM.
+#define LM_TW 128
+#define LM_TH 16
+#define LM_THREADS 256
+__device__ __forceinline__ int lr_checked(const int16_t *raw, const unsigned int *d2key, int W, int x, int y, int minX1, int maxX1,
+                                          int minD, int INV, int DMD)
+{
+    const int d1 = raw[(size_t)y * W + x];
+    if (d1 == INV || x < minX1 || x >= maxX1) return d1;
+    const unsigned int *krow = d2key + (size_t)y * W;
+    const int _d = d1 >> 4, d_ = (d1 + 15) >> 4;
+    const int _x = x - _d, x_ = x - d_;
+    bool bad0 = false, bad1 = false;
+    if (0 <= _x && _x < W) { const int v = disp2_at(krow, _x, minX1, INV); bad0 = v >= minD && abs(v - _d) > DMD; }
+    if (0 <= x_ && x_ < W) { const int v = disp2_at(krow, x_, minX1, INV); bad1 = v >= minD && abs(v - d_) > DMD; }
+    return (bad0 && bad1) ? INV : d1;
+}
+
+__global__ void __launch_bounds__(LM_THREADS) k_lr_median(const int16_t *raw, const unsigned int *d2key, int16_t *dst, int W, int H,
+                                                           long long dstPitchElems, int minX1, int maxX1, int minD, int INV, int DMD)
+{
+    __shared__ int16_t tile[LM_TH + 2][LM_TW + 2 + 2];
+    const int x0 = blockIdx.x * LM_TW, y0 = blockIdx.y * LM_TH;
+    for (int idx = threadIdx.x; idx < (LM_TH + 2) * (LM_TW + 2); idx += LM_THREADS) {
+        const int ty = idx / (LM_TW + 2), tx = idx - ty * (LM_TW + 2);
+        const int gy = min(max(y0 + ty - 1, 0), H - 1), gx = min(max(x0 + tx - 1, 0), W - 1);
+        tile[ty][tx] = (int16_t)lr_checked(raw, d2key, W, gx, gy, minX1, maxX1, minD, INV, DMD);
+    }
+    __syncthreads();
+    // thread -> two adjacent columns x four rows
+    const int cx = (threadIdx.x & 63) * 2, ry = (threadIdx.x >> 6) * 4;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int y = y0 + ry + r;
+        if (y >= H) break;
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const int x = x0 + cx + c;
+            if (x >= W) break;
+            const int16_t *t0 = &tile[ry + r][cx + c];
+            int p0 = t0[0], p1 = t0[1], p2 = t0[2];
+            int p3 = t0[LM_TW + 4], p4 = t0[LM_TW + 5], p5 = t0[LM_TW + 6];
+            int p6 = t0[2 * (LM_TW + 4)], p7 = t0[2 * (LM_TW + 4) + 1], p8 = t0[2 * (LM_TW + 4) + 2];
+            cswap(p1, p2); cswap(p4, p5); cswap(p7, p8); cswap(p0, p1); cswap(p3, p4); cswap(p6, p7);
+            cswap(p1, p2); cswap(p4, p5); cswap(p7, p8); cswap(p0, p3); cswap(p5, p8); cswap(p4, p7);
+            cswap(p3, p6); cswap(p1, p4); cswap(p2, p5); cswap(p4, p7); cswap(p4, p2); cswap(p6, p4);
+            cswap(p4, p2);
+            dst[(size_t)y * dstPitchElems + x] = (int16_t)p4;
+        }
+    }
 }
 
 // ---- speckle filter: connected components by union-find ----------------------------------------
@@ -392,6 +464,25 @@ __global__ void k_compact_scatter(const int16_t *disp, QMat Q, int W, int H, con
 int sgbm_launch_fill_i16(int16_t *p, size_t n, int v, cudaStream_t st)
 {
     k_fill_i16<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, (int16_t)v);
+    sgbm_count_launch(1);
+    SGBM_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int sgbm_launch_init_wta(int16_t *raw, unsigned int *d2key, size_t n, int INV, cudaStream_t st)
+{
+    const size_t threads = (n + 7) / 8;
+    k_init_wta<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(raw, d2key, n, INV);
+    sgbm_count_launch(1);
+    SGBM_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int sgbm_launch_lr_median(const Geo &g, const int16_t *raw, const unsigned int *d2key, int16_t *dst, long long dstPitchElems,
+                          cudaStream_t st)
+{
+    dim3 grid((g.W + LM_TW - 1) / LM_TW, (g.H + LM_TH - 1) / LM_TH);
+    k_lr_median<<<grid, LM_THREADS, 0, st>>>(raw, d2key, dst, g.W, g.H, dstPitchElems, g.minX1, g.maxX1, g.minD, g.INV, g.DMD);
     sgbm_count_launch(1);
     SGBM_CUDA_CHECK(cudaGetLastError());
     return 0;

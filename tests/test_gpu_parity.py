@@ -274,6 +274,57 @@ def test_host_batch_pipeline(sg):
             assert _mismatch(out[i], oracle.compute(p, pairs[i][0], pairs[i][1])) == 0, "frame %d of batch %d" % (i, B)
 
 
+def test_results_live_in_recycled_page_locked_memory(sg, monkeypatch):
+    """compute(numpy, numpy) returns a new array per call (cv2's contract) out of a recycling pool of page-locked
+    blocks: results stay intact while they (or views of them) are alive, blocks are reused once they are dropped,
+    the pool is bounded, a caller-supplied `disparity` array is written in place, and reprojectImageTo3D's host
+    result takes the same route."""
+    import gc
+    from stereo_reconstruction_cv_b200 import _hostpool as _pinned
+    W, H, D = 1100, 520, 32                          # 1.1 MB of int16: above the pool's minimum
+    pairs = [make_pair(W, H, D, seed=70 + i)[:2] for i in range(3)]
+    p = OracleParams(0, D, 5, 200, 800, 1, 63, 10, 100, 32, 0)
+    refs = [oracle.compute(p, a, b) for a, b in pairs]
+    st = sg.StereoSGBM_create(**_kw(p))
+    gc.collect()
+    base = _pinned.stats()["outstanding_bytes"]
+    outs = [st.compute(a, b) for a, b in pairs]       # three live results: three different blocks
+    assert len({o.ctypes.data for o in outs}) == 3
+    assert _pinned.stats()["outstanding_bytes"] - base >= 3 * W * H * 2
+    for o, ref in zip(outs, refs):
+        assert o.dtype == np.int16 and o.flags.c_contiguous and o.flags.writeable and _mismatch(o, ref) == 0
+    view = outs[0][100:200, 50:]                      # a view keeps its block out of the pool
+    addr0 = outs[0].ctypes.data
+    del outs, o
+    gc.collect()
+    again = [st.compute(a, b) for a, b in pairs]
+    assert addr0 not in {a.ctypes.data for a in again}
+    assert _mismatch(view, refs[0][100:200, 50:]) == 0
+    addrs = {a.ctypes.data for a in again}
+    del again, view
+    gc.collect()
+    assert _pinned.stats()["outstanding_bytes"] == base
+    o = st.compute(*pairs[1])                         # a dropped block comes back
+    assert o.ctypes.data in addrs | {addr0} and _mismatch(o, refs[1]) == 0
+    # caller-supplied output, dense and strided
+    dst = np.zeros((H, W), np.int16)
+    assert st.compute(pairs[2][0], pairs[2][1], dst) is dst and _mismatch(dst, refs[2]) == 0
+    wide = np.zeros((H, W + 6), np.int16)
+    assert _mismatch(st.compute(pairs[2][0], pairs[2][1], wide[:, 3:W + 3]), refs[2]) == 0 and not wide[:, :3].any()
+    # a bounded pool: beyond the cap results are ordinary arrays, and still right
+    monkeypatch.setattr(_pinned, "MAX_OUTSTANDING", _pinned.stats()["outstanding_bytes"] + W * H * 2)
+    o2 = st.compute(*pairs[0])
+    assert o2.flags.owndata and _mismatch(o2, refs[0]) == 0
+    monkeypatch.undo()
+    # the point-cloud side
+    Q = np.array([[1, 0, 0, -W / 2], [0, 1, 0, -H / 2], [0, 0, 0, 800.0], [0, 0, 1 / 60.0, 0]])
+    f = (refs[0].astype(np.float32) / 16)
+    xyz = sg.reprojectImageTo3D(f, Q)
+    assert xyz.shape == (H, W, 3) and xyz.dtype == np.float32
+    assert np.array_equal(xyz.view(np.uint32), oracle.reproject_f32(f, Q).view(np.uint32))
+    _pinned.trim()
+
+
 # ------------------------------------------------------------------------------------------------
 # the sweep's strip hand-off: every legal number of rows per super-step, wide enough for many strips
 # ------------------------------------------------------------------------------------------------
