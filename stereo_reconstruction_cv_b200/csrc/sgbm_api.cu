@@ -27,6 +27,7 @@ int sgbm_launch_vertical(VertArgs &a, int ndir, int numSMs, cudaStream_t st);
 bool sgbm_sweep_fits(const Geo &g, int numSMs, int mode);
 int sgbm_launch_fill_i16(int16_t *p, size_t n, int v, cudaStream_t st);
 int sgbm_launch_lrcheck(const Geo &g, int16_t *raw, const unsigned int *d2key, cudaStream_t st);
+int sgbm_launch_pad_cost(const Geo &g, uint16_t *C, int nrows, int value, cudaStream_t st);
 int sgbm_launch_init_wta(int16_t *raw, unsigned int *d2key, size_t n, int INV, cudaStream_t st);
 int sgbm_launch_lr_median(const Geo &g, const int16_t *raw, const unsigned int *d2key, int16_t *dst, long long dstPitchElems, cudaStream_t st);
 int sgbm_launch_median(const int16_t *src, int16_t *dst, int W, int H, long long dstPitchElems, cudaStream_t st);
@@ -186,6 +187,19 @@ static int check_device(const sgbm_handle *h)
     return 0;
 }
 
+// Cost of a padding disparity (numDisparities % 8 != 0), or -1 when no value works.  It has to act as +infinity in the path
+// step (A.4) without leaving 16 bits:  L_pad = C_pad + min(..) - m  lies in [C_pad, C_pad + P2], so C_pad + P2 <= 65535; it
+// must never be the minimum over d nor the better neighbour of d = D - 1:  C_pad + P1 >= m + P2 with m <= cMax + P2.
+// Hence C_pad = 65535 - P2, possible when cMax + 3 P2 - P1 <= 65535.  What the sums S hold at those disparities does not
+// matter (they may wrap): every winner-take-all masks them (mask_pad_regs).
+static int pad_cost_value(const Geo &g)
+{
+    const long long pixMax = (long long)(2 * g.ftzero < 255 ? 2 * g.ftzero : 255) + 63;
+    const long long cMax = (long long)g.cn * (2 * g.r + 1) * (2 * g.r + 1) * pixMax;
+    const long long v = 65535 - g.P2;
+    return v >= cMax + 2ll * g.P2 - g.P1 ? (int)v : -1;
+}
+
 // Effective parameters and geometry (A.0) + lane mapping.  Returns 0 or an error code.
 static int make_geo(const sgbm_params &p, int W, int H, int cn, Geo &g)
 {
@@ -213,8 +227,18 @@ static int make_geo(const sgbm_params &p, int W, int H, int cn, Geo &g)
     if (!(W - (g.minD + g.D) > p.blockSize / 2) || g.W1 <= 0)
         return sgbm_fail(SGBM_E_BAD_SIZE, "image width %d too small for minDisparity=%d numDisparities=%d blockSize=%d",
                          W, g.minD, g.D, p.blockSize);
-    if (g.D % 8 != 0 || g.D > 1024)
-        return sgbm_fail(SGBM_E_UNSUPPORTED, "numDisparities must be a multiple of 8 and <= 1024 (got %d)", g.D);
+    if (g.D > 1024) return sgbm_fail(SGBM_E_UNSUPPORTED, "numDisparities must be <= 1024 (got %d)", g.D);
+    // numDisparities that are not a multiple of 8 (cv2 documents % 16 but accepts anything; SURVEY 8(c), [P16]): computed
+    // on volumes as wide as the next multiple of 8 whose padding disparities carry a large constant cost (pad_cost_value).
+    // Not for MODE_SGBM_3WAY (cv2's own SIMD tail makes its results irregular there, A.6), not for odd values (the cost
+    // kernels work on disparity pairs) and not below 4.
+    const int Dc = (g.D + 7) & ~7;
+    if (Dc != g.D) {
+        if (p.mode == SGBM_MODE_SGBM_3WAY)
+            return sgbm_fail(SGBM_E_UNSUPPORTED, "MODE_SGBM_3WAY needs numDisparities %% 8 == 0 (got %d)", g.D);
+        if ((g.D & 1) || g.D < 4)
+            return sgbm_fail(SGBM_E_UNSUPPORTED, "numDisparities must be even and >= 4 when it is not a multiple of 8 (got %d)", g.D);
+    }
     if (g.P2 > 32767) return sgbm_fail(SGBM_E_UNSUPPORTED, "P2 must be <= 32767 (got %d)", g.P2);
     if (g.UR > 100 || (p.mode == SGBM_MODE_SGBM_3WAY && g.UR >= 100))
         return sgbm_fail(SGBM_E_UNSUPPORTED, "uniquenessRatio %d is not supported", g.UR);
@@ -223,14 +247,14 @@ static int make_geo(const sgbm_params &p, int W, int H, int cn, Geo &g)
     if (g.W1 > 65535) return sgbm_fail(SGBM_E_UNSUPPORTED, "valid width %d > 65535", g.W1);
     // lane mapping: D = 2*nreg*lanesUsed, lpc = pow2 >= lanesUsed (>= 2); maximise lanesUsed/lpc
     static const int prefBig[4] = {16, 12, 8, 4}, prefSmall[4] = {8, 12, 16, 4};
-    const int *pref = g.D >= 192 ? prefBig : prefSmall;
+    const int *pref = Dc >= 192 ? prefBig : prefSmall;
     const int forced = kn.nreg;
     double bestEff = -1;
     for (int i = 0; i < 4; i++) {
         int nreg = pref[i];
         if (forced && nreg != forced) continue;
-        if (g.D % (2 * nreg)) continue;
-        int lanes = g.D / (2 * nreg);
+        if (Dc % (2 * nreg)) continue;
+        int lanes = Dc / (2 * nreg);
         if (lanes > 32) continue;
         int lpc = 2;
         while (lpc < lanes) lpc <<= 1;
@@ -242,6 +266,9 @@ static int make_geo(const sgbm_params &p, int W, int H, int cn, Geo &g)
     g.lpcShift = 0;
     while ((1 << g.lpcShift) < g.lpc) g.lpcShift++;
     g.rowStride = (long long)g.W1 * g.Dp;
+    if (Dc != g.D && pad_cost_value(g) < 0)
+        return sgbm_fail(SGBM_E_UNSUPPORTED, "numDisparities %d (not a multiple of 8) needs cMax + 3*P2 - P1 <= 65535 (blockSize %d, P2 %d)",
+                         g.D, 2 * g.r + 1, g.P2);
     return 0;
 }
 
@@ -502,6 +529,7 @@ static int compute_frame(sgbm_handle *h, int lane, int sweepSMs, const Geo &g, c
     // fallback for geometries the new kernel does not hold (rc == 1) and for A/B runs (SGBM_COST2=0)
     bool cost2 = h->knobs.cost2 != 0, cost3 = h->knobs.cost3 != 0;
     int bands = 1, bandRows = g.H;
+    const int padCost = (g.D & 7) ? pad_cost_value(g) : -1;      // numDisparities % 8 != 0: see pad_cost_value
     if (!cost2) cost3 = false;
     if (cost3) {
         rc = sgbm_cost3_supported(g);
@@ -527,6 +555,7 @@ static int compute_frame(sgbm_handle *h, int lane, int sweepSMs, const Geo &g, c
             const int y0 = b * bandRows, nr = g.H - y0 < bandRows ? g.H - y0 : bandRows;
             if ((rc = sgbm_launch_cost3(g, planes, C + (size_t)y0 * g.rowStride, y0, nr, 0, st)))
                 return rc < 0 ? rc : sgbm_fail(SGBM_E_UNSUPPORTED, "cost kernel geometry changed between plan and launch");
+            if (padCost >= 0 && (rc = sgbm_launch_pad_cost(g, C + (size_t)y0 * g.rowStride, nr, padCost, st))) return rc;
             if (bands > 1) {
                 cudaStream_t bs = h->bandStream[lane][b];
                 SGBM_CUDA_CHECK(cudaEventRecord(h->evBand[lane][b], st));
@@ -538,6 +567,7 @@ static int compute_frame(sgbm_handle *h, int lane, int sweepSMs, const Geo &g, c
         if (cost3 && p.mode == SGBM_MODE_HH4 && g.r > 0) {            // A.9: the last r rows carry C = 0
             const int nz = g.r < g.H ? g.r : g.H;
             SGBM_CUDA_CHECK(cudaMemsetAsync(C + (size_t)(g.H - nz) * g.rowStride, 0, (size_t)nz * g.rowStride * 2, st));
+            if (padCost >= 0 && (rc = sgbm_launch_pad_cost(g, C + (size_t)(g.H - nz) * g.rowStride, nz, padCost, st))) return rc;
         }
         if (!cost3) {
             rc = sgbm_launch_cost2(g, planes, C, 0, g.H, 0, p.mode == SGBM_MODE_HH4, st);
@@ -550,6 +580,7 @@ static int compute_frame(sgbm_handle *h, int lane, int sweepSMs, const Geo &g, c
         if ((rc = prof_mark(h, ST_PREFILTER, st))) return rc;
         if ((rc = sgbm_launch_cost(g, planes, C, 0, g.H, 0, p.mode == SGBM_MODE_HH4, st))) return rc;
     }
+    if (!cost3 && padCost >= 0 && (rc = sgbm_launch_pad_cost(g, C, g.H, padCost, st))) return rc;
     if ((rc = prof_mark(h, ST_COST, st))) return rc;
     const int ss = (g.H + 3) / 4;
     int ov = 0;

@@ -377,6 +377,24 @@ __device__ __forceinline__ uint32_t path_step_m(uint32_t (&L)[NREG], uint32_t mp
     return group_min<LPC>(local_min<NREG>(L) | lm.pad);
 }
 
+// numDisparities that are not a multiple of 8 (cv2 accepts them): the volumes are as wide as the next multiple of 8, the
+// cost volume carries a large constant at the padding disparities d in [D, Dc) (sgbm_api.cu: k_pad_cost), which makes them
+// inert in the path step (never the minimum, never the better neighbour of d = D - 1), and the winner-take-all hides
+// them: in the last used lane the registers from local index padFrom on are forced to all ones.
+template <int NREG>
+__device__ __forceinline__ void mask_pad_regs(uint32_t (&S)[NREG], bool lastUsedLane, int padFrom)
+{
+    if (lastUsedLane) {
+#pragma unroll
+        for (int j = 0; j < NREG; j++) {
+            if (2 * j >= padFrom) S[j] = 0xFFFFFFFFu;
+            else if (2 * j + 1 >= padFrom) S[j] |= 0xFFFF0000u;
+        }
+    }
+}
+// local index (inside the last used lane) of the first padding disparity; 2 * nreg when there is none
+__host__ __device__ __forceinline__ int sgbm_pad_from(const Geo &g) { return g.D - (g.lanesUsed - 1) * 2 * g.nreg; }
+
 // A multiply-add by an opaque +-1 (a kernel argument the compiler cannot fold) is an IMAD and issues on the
 // FMA pipe; the packed min / max / permute instructions issue on the ALU pipe only, at half rate.  Used
 // by sgbm_cost3.cu, where the ALU pipe is the nearest bound.  (Tried in the path step as well, b + (C - m)

@@ -417,6 +417,10 @@ __global__ void __launch_bounds__(NDIR == 1 ? 128 : VertMaxThreads<NREG>::value,
             } else {
                 // ---- winner-take-all (A.5 / A.6) --------------------------------------------------
                 if (a.sdbg && own) store_vec<NREG, LPC>(S, a.sdbg + (size_t)y * g.rowStride + (size_t)x1 * Dp, lg);
+                {
+                    const int padFrom = sgbm_pad_from(g);             // numDisparities % 8 != 0: hide the padding disparities
+                    if (padFrom < 2 * NREG) mask_pad_regs<NREG>(S, lg == lastLane, padFrom);
+                }
                 uint32_t tm = local_min<NREG>(S);
                 if (lg > lastLane) tm = SGBM_INF2;
                 const uint32_t mS2 = group_min<LPC>(tm);

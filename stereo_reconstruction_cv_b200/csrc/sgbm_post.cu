@@ -29,6 +29,18 @@ __global__ void k_init_wta(int16_t *raw, unsigned int *d2key, size_t n, int INV)
     }
 }
 
+// numDisparities % 8 != 0: the padding disparities d in [D, Dc) of every column of `nrows` rows of the cost volume get the
+// constant that makes them inert in the path step (sgbm_api.cu: pad_cost_value).  Rare configurations: plain 16-bit stores.
+__global__ void k_pad_cost(uint16_t *C, long long ncols, int Dp, int D, int Dc, int nreg, int lpc, int value)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int npad = Dc - D;
+    if (i >= ncols * npad) return;
+    const long long col = i / npad;
+    const int d = D + (int)(i - col * npad);
+    C[col * Dp + sgbm_pos(d, nreg, lpc)] = (uint16_t)value;
+}
+
 // ---- LR check ---------------------------------------------------------------------------------
 // d2key[y][x2] = (cost << 16) | (0xFFFF - x1) of the winning left pixel, 0xFFFFFFFF if never hit.
 // disp2[x2] = (x1 + minX1) - x2 for a hit, INV (the x16-scaled marker, [P2]) otherwise.
@@ -464,6 +476,17 @@ __global__ void k_compact_scatter(const int16_t *disp, QMat Q, int W, int H, con
 int sgbm_launch_fill_i16(int16_t *p, size_t n, int v, cudaStream_t st)
 {
     k_fill_i16<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, (int16_t)v);
+    sgbm_count_launch(1);
+    SGBM_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int sgbm_launch_pad_cost(const Geo &g, uint16_t *C, int nrows, int value, cudaStream_t st)
+{
+    const int Dc = (g.D + 7) & ~7;
+    if (Dc == g.D || nrows <= 0) return 0;
+    const long long ncols = (long long)g.W1 * nrows, n = ncols * (Dc - g.D);
+    k_pad_cost<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(C, ncols, g.Dp, g.D, Dc, g.nreg, g.lpc, value);
     sgbm_count_launch(1);
     SGBM_CUDA_CHECK(cudaGetLastError());
     return 0;

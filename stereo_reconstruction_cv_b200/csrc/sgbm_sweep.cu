@@ -71,6 +71,7 @@ struct SweepArgs {
     // New fields go LAST: the register allocation of the WTA kernels is sensitive to the layout of the fields above.
     int rps;
     unsigned int cRowB, iRowB, pRowB;
+    int wtaSlow;                     // numDisparities % 8 != 0: sweep_wta hides the padding disparities of the last used lane
 };
 
 // clock64 time stamps of one strip: compiled in only with -DSGBM_SWEEP_TRACING (make TRACE=1); the
@@ -390,11 +391,12 @@ __device__ __forceinline__ void sweep_role_v(const SweepArgs &a, const SweepSmem
 // uniqueness scan re-reads S from shared scratch with the window around the winner masked and
 // combines the lanes' verdicts with one ballot.
 template <int NREG, int LPC>
-__device__ __forceinline__ void sweep_wta(const SweepArgs &a, const uint32_t (&S)[NREG], uint16_t *ssm, int lg, bool own,
+__device__ __forceinline__ void sweep_wta(const SweepArgs &a, uint32_t (&S)[NREG], uint16_t *ssm, int lg, bool own,
                                           int x1, int y)
 {
     const Geo &g = a.g;
     const int lastLane = g.lanesUsed - 1;
+    if (a.wtaSlow) mask_pad_regs<NREG>(S, lg == lastLane, sgbm_pad_from(g));    // (a no-op unless numDisparities % 8 != 0)
     __syncwarp();
     store_vec<NREG, LPC>(S, ssm, lg);                     // scratch for the sub-pixel neighbours / masked re-scan
     uint32_t km[NREG];
@@ -1072,6 +1074,7 @@ static int launch_sweep_t(const VertArgs &va, int numSMs, cudaStream_t st)
     a.urMagic = g.UR < 99 ? 0xFFFFFFFFu / (unsigned)(100 - g.UR) + 1u : 0u;
     a.pfDist = kn.sweepPF >= 0 ? kn.sweepPF : 8;
     a.P1p = (unsigned)g.P1 * 0x10001u; a.P2mP1p = (unsigned)(g.P2 - g.P1) * 0x10001u;
+    a.wtaSlow = sgbm_pad_from(g) < 2 * g.nreg ? 1 : 0;
     const bool wta = va.sout == nullptr;
     if (WROLE && !wta) return 1;
     const int maxThreads = SweepMaxThreads<NREG, WROLE>::value;
@@ -1090,7 +1093,10 @@ template <int NREG, int LPC, bool SAT>
 static int launch_sweep_any(const VertArgs &va, int numSMs, cudaStream_t st)
 {
     if (va.sout == nullptr) {
-        if (sgbm_knobs().sweepW) {
+        // numDisparities % 8 != 0 stays on the kernels whose winner-take-all masks the padding disparities in registers
+        // (sweep_wta): the W warps of the 16-register mappings run under a 40-register cap, and ANY code added to their pixel
+        // loop -- even an out-of-line call behind a uniform branch -- showed up as spills (cfg3 WTA sweep 3.17 -> 3.37 ms)
+        if (sgbm_knobs().sweepW && sgbm_pad_from(va.g) >= 2 * va.g.nreg) {
             const int rc = launch_sweep_t<NREG, LPC, SAT, true>(va, numSMs, st);
             if (rc <= 0) return rc;
         }
@@ -1175,6 +1181,7 @@ static int launch_rowstep_t(const VertArgs &va, cudaStream_t st)
     a.sw.g = g; a.sw.C = va.C; a.sw.inA = va.inA; a.sw.inB = va.inB; a.sw.sout = va.sout; a.sw.sdbg = va.sdbg;
     a.sw.raw = va.raw; a.sw.d2key = va.d2key;
     a.sw.urMagic = g.UR < 99 ? 0xFFFFFFFFu / (unsigned)(100 - g.UR) + 1u : 0u;
+    a.sw.wtaSlow = sgbm_pad_from(g) < 2 * g.nreg ? 1 : 0;
     a.state = va.rowState;
     if (!a.state) return sgbm_fail(-3, "row-step fallback has no state buffer");
     const int threads = 128, groups = threads / LPC;

@@ -394,6 +394,58 @@ def test_sweep_rows_per_stage_odd_heights(sg, monkeypatch, H, rps):
                 assert _mismatch(st.compute(l, r), ref) == 0, (H, rps, W, D, mode, rep)
 
 
+@pytest.mark.parametrize("D", [4, 6, 10, 12, 20, 36, 44, 100, 250])
+def test_num_disparities_not_a_multiple_of_8(sg, D):
+    """cv2 documents numDisparities % 16 == 0 but accepts anything ([P16]): even values >= 4 run on volumes
+    padded to the next multiple of 8 whose padding disparities are inert in the path step and masked in every
+    winner-take-all.  MODE_SGBM, MODE_HH and MODE_HH4 against the oracle (which equals cv2 there) and against live cv2;
+    the notebook's penalties (saturating accumulation), a 3-channel pair, minDisparity != 0, several strips."""
+    import torch
+    cases = [(900, 70, 5, 200, 800, 0, 1), (1300, 40, 11, 2904, 11616, 0, 1), (420, 60, 3, 216, 864, -3, 3), (2100, 33, 7, 392, 1568, 5, 1)]
+    for (W, H, bs, P1, P2, minD, cn) in cases:
+        if W - D - abs(minD) < 40:
+            continue
+        l, r, _ = make_pair(W, H, max(D, 8), seed=D + W)
+        if cn == 3:
+            l = np.stack([l, np.roll(l, 1, 0), l // 2 + 7], -1).astype(np.uint8)
+            r = np.stack([r, np.roll(r, 1, 0), r // 2 + 7], -1).astype(np.uint8)
+        for mode in (0, 1, 3):
+            p = OracleParams(minD, D, bs, P1 * cn, P2 * cn, 1, 63, 10, 60, 16, mode)
+            ref = oracle.compute(p, l, r)
+            st = sg.StereoSGBM_create(**_kw(p))
+            assert _mismatch(st.compute(l, r), ref) == 0, (D, W, bs, mode, "host")
+            got = st.compute(torch.from_numpy(l).cuda(), torch.from_numpy(r).cuda()).cpu().numpy()
+            assert _mismatch(got, ref) == 0, (D, W, bs, mode, "device")
+            if cv2_ref.available() and mode != 3:             # (cv2's MODE_HH4 is not repeatable: DESIGN.md section 2)
+                assert _mismatch(got, cv2_ref.compute(p, l, r)) == 0, (D, W, bs, mode, "cv2")
+    # batches side by side and the fallback kernels
+    l, r, _ = make_pair(700, 64, max(D, 8), seed=D)
+    p = OracleParams(0, D, 5, 200, 800, 1, 63, 10, 0, 0, 0)
+    ref = oracle.compute(p, l, r)
+    out = sg.StereoSGBM_create(**_kw(p)).compute_batch(np.stack([l] * 5), np.stack([r] * 5))
+    assert all(_mismatch(out[i], ref) == 0 for i in range(5))
+
+
+@pytest.mark.parametrize("env", [{"SGBM_SWEEP_W": "0"}, {"SGBM_SWEEP": "0"}, {"SGBM_ROWSTEP": "1"}, {"SGBM_COST3": "0"}, {"SGBM_COST2": "0"},
+                                 {"SGBM_SWEEP_RPS": "1"}])
+def test_num_disparities_not_a_multiple_of_8_fallback_kernels(sg, monkeypatch, env):
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for D in (12, 36, 100):
+        l, r, _ = make_pair(800, 50, D, seed=D)
+        for mode in (0, 1, 3):
+            p = OracleParams(0, D, 5, 200, 800, 1, 63, 10, 100, 32, mode)
+            assert _mismatch(sg.StereoSGBM_create(**_kw(p)).compute(l, r), oracle.compute(p, l, r)) == 0, (env, D, mode)
+
+
+def test_num_disparities_unsupported_values(sg):
+    l, r, _ = make_pair(300, 40, 16, seed=1)
+    for kw in (dict(numDisparities=21), dict(numDisparities=2), dict(numDisparities=20, mode=2), dict(numDisparities=1032),
+               dict(numDisparities=20, blockSize=11, P1=2904, P2=22000)):
+        with pytest.raises(sg.error):
+            sg.StereoSGBM_create(**kw).compute(l, r)
+
+
 @pytest.mark.parametrize("R", [8, 2])
 def test_repeatability_under_load(sg, monkeypatch, R):
     """Strip hand-offs and role hand-offs are timing dependent: 150 back-to-back frames of a
