@@ -8,10 +8,11 @@ import re
 import sys
 
 D = sys.argv[1]
+# optional: workload tag of the second table set (cfg2: 144 strips x 720 rows, k_sweep<8,8,0,1,2> with two rows per ring stage)
 STRIPS, ROWS = 148, 2160
 
 
-def analyse(nm, roles):
+def analyse(nm, roles, STRIPS=STRIPS, ROWS=ROWS):
     rows = list(csv.DictReader(open('%s/sass_%s.csv' % (D, nm))))
     ex = [int(float(r['executed'] or 0)) for r in rows]
     sass = [r['sass'] for r in rows]
@@ -58,11 +59,16 @@ txt = ["# Per-role instruction counts of the cfg3 sweeps (round 2, final build)"
        "(148 strips x 2160 rows).", "",
        "Round 1 for comparison (`r01_sweep_wta_instruction_mix_v9.md`): 2.80 G warp instructions in the WTA sweep (8760 per SM "
        "and row), 2.05 G in the forward sweep; role V ~300 per row.", ""]
-for nm, roles, title in (('wta', [('V', 7), ('A', 8), ('C', 8), ('W', 7), ('producer', 1)], 'k_sweep<16,8,0,1> (backward sweep + WTA)'),
-                         ('fwd', [('V', 7), ('A', 8), ('C', 8), ('producer', 1)], 'k_sweep<16,8,0,0> (forward sweep, spills S)')):
-    allns, packed, out = analyse(nm, roles)
+import os
+for nm, roles, title, geo in (('wta', [('V', 7), ('A', 8), ('C', 8), ('W', 7), ('producer', 1)], 'k_sweep<16,8,0,1,1> (cfg3 backward sweep + WTA)', (148, 2160)),
+                              ('fwd', [('V', 7), ('A', 8), ('C', 8), ('producer', 1)], 'k_sweep<16,8,0,0,1> (cfg3 forward sweep, spills S)', (148, 2160)),
+                              ('cfg2_wta', [('V', 2), ('A', 4), ('C', 4), ('W', 6), ('producer', 1)],
+                               'k_sweep<8,8,0,1,2> (cfg2: 1280x720 D=128 MODE_SGBM, TWO rows per ring stage; 144 strips of 8 columns)', (144, 720))):
+    if not os.path.exists('%s/sass_%s.csv' % (D, nm)):
+        continue
+    allns, packed, out = analyse(nm, roles, *geo)
     txt += ["## %s" % title, "",
             "non-spin instructions (instrumented pass): %.3f G = %.0f per SM and row; packed min / max / add-min / permute share %.1f %%"
-            % (allns / 1e9, allns / (STRIPS * ROWS), 100 * packed / allns), "",
+            % (allns / 1e9, allns / (geo[0] * geo[1]), 100 * packed / allns), "",
             "| role | warps | share | instr / warp-row | top opcodes (per warp-row) |", "|---|---|---|---|---|"] + out + [""]
 print('\n'.join(txt))
