@@ -51,7 +51,7 @@ extern "C" {
 /* The 11 integers of cv2.StereoSGBM_create, same names and meaning (main.ipynb:655-666). */
 typedef struct sgbm_params {
     int minDisparity;
-    int numDisparities;   /* > 0, <= 1024; a multiple of 8, or any even value >= 4 outside MODE_SGBM_3WAY (cv2 accepts those too) */
+    int numDisparities;   /* > 0, <= 1024; a multiple of 8, or any value >= 4 outside MODE_SGBM_3WAY (cv2 accepts those too) */
     int blockSize;
     int P1;
     int P2;

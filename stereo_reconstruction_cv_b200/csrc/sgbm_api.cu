@@ -187,6 +187,17 @@ static int check_device(const sgbm_handle *h)
     return 0;
 }
 
+// Geometry handed to the prefilter / cost kernels.  They work on disparity PAIRS; for an odd numDisparities they compute
+// one disparity more (d = D reads the right image at x - maxD >= 0 for every valid x, so the operand is in range) and
+// k_pad_cost overwrites it together with the other padding disparities.  Everything else about the geometry -- valid
+// range, lane mapping, strides -- is the true one.
+static Geo cost_geo(const Geo &g)
+{
+    Geo c = g;
+    if (g.D & 1) { c.D = g.D + 1; c.maxD = g.maxD + 1; }
+    return c;
+}
+
 // Cost of a padding disparity (numDisparities % 8 != 0), or -1 when no value works.  It has to act as +infinity in the path
 // step (A.4) without leaving 16 bits:  L_pad = C_pad + min(..) - m  lies in [C_pad, C_pad + P2], so C_pad + P2 <= 65535; it
 // must never be the minimum over d nor the better neighbour of d = D - 1:  C_pad + P1 >= m + P2 with m <= cMax + P2.
@@ -230,14 +241,14 @@ static int make_geo(const sgbm_params &p, int W, int H, int cn, Geo &g)
     if (g.D > 1024) return sgbm_fail(SGBM_E_UNSUPPORTED, "numDisparities must be <= 1024 (got %d)", g.D);
     // numDisparities that are not a multiple of 8 (cv2 documents % 16 but accepts anything; SURVEY 8(c), [P16]): computed
     // on volumes as wide as the next multiple of 8 whose padding disparities carry a large constant cost (pad_cost_value).
-    // Not for MODE_SGBM_3WAY (cv2's own SIMD tail makes its results irregular there, A.6), not for odd values (the cost
-    // kernels work on disparity pairs) and not below 4.
+    // Not for MODE_SGBM_3WAY (cv2's own SIMD tail makes its results irregular there, A.6) and not below 4 (the masked
+    // uniqueness scan needs a disparity outside the winner's window).  Odd values: see cost_geo.
     const int Dc = (g.D + 7) & ~7;
     if (Dc != g.D) {
         if (p.mode == SGBM_MODE_SGBM_3WAY)
             return sgbm_fail(SGBM_E_UNSUPPORTED, "MODE_SGBM_3WAY needs numDisparities %% 8 == 0 (got %d)", g.D);
-        if ((g.D & 1) || g.D < 4)
-            return sgbm_fail(SGBM_E_UNSUPPORTED, "numDisparities must be even and >= 4 when it is not a multiple of 8 (got %d)", g.D);
+        if (g.D < 4)
+            return sgbm_fail(SGBM_E_UNSUPPORTED, "numDisparities must be >= 4 (got %d)", g.D);
     }
     if (g.P2 > 32767) return sgbm_fail(SGBM_E_UNSUPPORTED, "P2 must be <= 32767 (got %d)", g.P2);
     if (g.UR > 100 || (p.mode == SGBM_MODE_SGBM_3WAY && g.UR >= 100))
@@ -283,7 +294,7 @@ static void ws_layout(const Geo &g, const sgbm_params &p, int numSMs, int keep, 
     size_t vol = (size_t)g.rowStride * g.H * 2;
     L.watch = take(64);       // hand-off watchdog of the sweep (sgbm_sweep.cu); first, so its place never moves
     {   // prefilter output: the larger of the two generations' formats (sgbm_cost.cu / sgbm_cost2.cu)
-        const size_t v1 = (size_t)2 * g.cn * 6 * g.W * g.H, v2 = sgbm_cost2_planes_bytes(g);
+        const size_t v1 = (size_t)2 * g.cn * 6 * g.W * g.H, v2 = sgbm_cost2_planes_bytes(cost_geo(g));
         L.planes = take(v1 > v2 ? v1 : v2);
     }
     L.C = take(vol);
@@ -530,14 +541,15 @@ static int compute_frame(sgbm_handle *h, int lane, int sweepSMs, const Geo &g, c
     bool cost2 = h->knobs.cost2 != 0, cost3 = h->knobs.cost3 != 0;
     int bands = 1, bandRows = g.H;
     const int padCost = (g.D & 7) ? pad_cost_value(g) : -1;      // numDisparities % 8 != 0: see pad_cost_value
+    const Geo gc = cost_geo(g);
     if (!cost2) cost3 = false;
     if (cost3) {
-        rc = sgbm_cost3_supported(g);
+        rc = sgbm_cost3_supported(gc);
         if (rc < 0) return rc;
         cost3 = rc == 1;
     }
     if (cost2) {
-        if ((rc = sgbm_launch_prefilter2(g, left, right, pitch, planes, cost3 ? sgbm_cost3_eshift(g) : 0, cost3 ? 1 : 0, st))) return rc;
+        if ((rc = sgbm_launch_prefilter2(gc, left, right, pitch, planes, cost3 ? sgbm_cost3_eshift(gc) : 0, cost3 ? 1 : 0, st))) return rc;
         if ((rc = prof_mark(h, ST_PREFILTER, st))) return rc;
         // third generation (sgbm_cost3.cu): register-resident pixel costs; 1-channel, blockSize <= 11
         // Row bands (large frames, whole-GPU schedule): a row of the horizontal paths needs only its own cost
@@ -553,7 +565,7 @@ static int compute_frame(sgbm_handle *h, int lane, int sweepSMs, const Geo &g, c
         }
         for (int b = 0; cost3 && b < bands; b++) {
             const int y0 = b * bandRows, nr = g.H - y0 < bandRows ? g.H - y0 : bandRows;
-            if ((rc = sgbm_launch_cost3(g, planes, C + (size_t)y0 * g.rowStride, y0, nr, 0, st)))
+            if ((rc = sgbm_launch_cost3(gc, planes, C + (size_t)y0 * g.rowStride, y0, nr, 0, st)))
                 return rc < 0 ? rc : sgbm_fail(SGBM_E_UNSUPPORTED, "cost kernel geometry changed between plan and launch");
             if (padCost >= 0 && (rc = sgbm_launch_pad_cost(g, C + (size_t)y0 * g.rowStride, nr, padCost, st))) return rc;
             if (bands > 1) {
@@ -570,15 +582,15 @@ static int compute_frame(sgbm_handle *h, int lane, int sweepSMs, const Geo &g, c
             if (padCost >= 0 && (rc = sgbm_launch_pad_cost(g, C + (size_t)(g.H - nz) * g.rowStride, nz, padCost, st))) return rc;
         }
         if (!cost3) {
-            rc = sgbm_launch_cost2(g, planes, C, 0, g.H, 0, p.mode == SGBM_MODE_HH4, st);
+            rc = sgbm_launch_cost2(gc, planes, C, 0, g.H, 0, p.mode == SGBM_MODE_HH4, st);
             if (rc < 0) return rc;
             if (rc == 1) cost2 = false;
         }
     }
     if (!cost2) {
-        if ((rc = sgbm_launch_prefilter(g, left, right, pitch, planes, st))) return rc;
+        if ((rc = sgbm_launch_prefilter(gc, left, right, pitch, planes, st))) return rc;
         if ((rc = prof_mark(h, ST_PREFILTER, st))) return rc;
-        if ((rc = sgbm_launch_cost(g, planes, C, 0, g.H, 0, p.mode == SGBM_MODE_HH4, st))) return rc;
+        if ((rc = sgbm_launch_cost(gc, planes, C, 0, g.H, 0, p.mode == SGBM_MODE_HH4, st))) return rc;
     }
     if (!cost3 && padCost >= 0 && (rc = sgbm_launch_pad_cost(g, C, g.H, padCost, st))) return rc;
     if ((rc = prof_mark(h, ST_COST, st))) return rc;
@@ -593,8 +605,8 @@ static int compute_frame(sgbm_handle *h, int lane, int sweepSMs, const Geo &g, c
             if (s0 == 0) continue;
             int nr = g.r < g.H - s0 ? g.r : g.H - s0;
             uint16_t *dst = Calt + (size_t)(n - 1) * g.r * g.rowStride;
-            rc = cost3 ? sgbm_launch_cost3(g, planes, dst, s0, nr, s0, st)
-                 : cost2 ? sgbm_launch_cost2(g, planes, dst, s0, nr, s0, 0, st) : sgbm_launch_cost(g, planes, dst, s0, nr, s0, 0, st);
+            rc = cost3 ? sgbm_launch_cost3(gc, planes, dst, s0, nr, s0, st)
+                 : cost2 ? sgbm_launch_cost2(gc, planes, dst, s0, nr, s0, 0, st) : sgbm_launch_cost(gc, planes, dst, s0, nr, s0, 0, st);
             if (rc) return rc < 0 ? rc : sgbm_fail(SGBM_E_UNSUPPORTED, "cost kernel geometry changed between launches");
         }
     }

@@ -394,9 +394,9 @@ def test_sweep_rows_per_stage_odd_heights(sg, monkeypatch, H, rps):
                 assert _mismatch(st.compute(l, r), ref) == 0, (H, rps, W, D, mode, rep)
 
 
-@pytest.mark.parametrize("D", [4, 6, 10, 12, 20, 36, 44, 100, 250])
+@pytest.mark.parametrize("D", [4, 5, 6, 7, 9, 10, 12, 20, 21, 27, 36, 44, 99, 100, 250, 255])
 def test_num_disparities_not_a_multiple_of_8(sg, D):
-    """cv2 documents numDisparities % 16 == 0 but accepts anything ([P16]): even values >= 4 run on volumes
+    """cv2 documents numDisparities % 16 == 0 but accepts anything ([P16]): values >= 4, odd ones too, run on volumes
     padded to the next multiple of 8 whose padding disparities are inert in the path step and masked in every
     winner-take-all.  MODE_SGBM, MODE_HH and MODE_HH4 against the oracle (which equals cv2 there) and against live cv2;
     the notebook's penalties (saturating accumulation), a 3-channel pair, minDisparity != 0, several strips."""
@@ -431,7 +431,7 @@ def test_num_disparities_not_a_multiple_of_8(sg, D):
 def test_num_disparities_not_a_multiple_of_8_fallback_kernels(sg, monkeypatch, env):
     for k, v in env.items():
         monkeypatch.setenv(k, v)
-    for D in (12, 36, 100):
+    for D in (12, 21, 36, 100):
         l, r, _ = make_pair(800, 50, D, seed=D)
         for mode in (0, 1, 3):
             p = OracleParams(0, D, 5, 200, 800, 1, 63, 10, 100, 32, mode)
@@ -440,7 +440,7 @@ def test_num_disparities_not_a_multiple_of_8_fallback_kernels(sg, monkeypatch, e
 
 def test_num_disparities_unsupported_values(sg):
     l, r, _ = make_pair(300, 40, 16, seed=1)
-    for kw in (dict(numDisparities=21), dict(numDisparities=2), dict(numDisparities=20, mode=2), dict(numDisparities=1032),
+    for kw in (dict(numDisparities=3), dict(numDisparities=2), dict(numDisparities=20, mode=2), dict(numDisparities=21, mode=2), dict(numDisparities=1032),
                dict(numDisparities=20, blockSize=11, P1=2904, P2=22000)):
         with pytest.raises(sg.error):
             sg.StereoSGBM_create(**kw).compute(l, r)
