@@ -553,11 +553,13 @@ static int compute_frame(sgbm_handle *h, int lane, int sweepSMs, const Geo &g, c
         if ((rc = prof_mark(h, ST_PREFILTER, st))) return rc;
         // third generation (sgbm_cost3.cu): register-resident pixel costs; 1-channel, blockSize <= 11
         // Row bands (large frames, whole-GPU schedule): a row of the horizontal paths needs only its own cost
-        // row, so band b's horizontal kernel runs on a side stream beside band b + 1's cost kernel.  Both lean
-        // on the shared-memory data pipe, so the gain is mostly tail filling: 4K D=256 MODE_HH 11.39 -> 11.13 ms
-        // with two bands, 11.30 with four or eight.
+        // row, so band b's horizontal kernel runs on a high-priority side stream beside band b + 1's cost kernel.  Both
+        // lean on the shared-memory data pipe and a 211 KB cost CTA leaves no room for a horizontal CTA on its SM, so what
+        // overlaps are the tails of the waves.  Six bands (end of round 2, 4K D=256): MODE_HH 10.23 -> 9.90 ms, 3WAY
+        // 6.97 -> 6.76 ms; 2 / 3 / 4 / 5 / 8 bands: 10.23 / 9.95 / 9.92 / 9.92 / 10.04 ms; at 1080p bands only cost
+        // (1.86 -> 2.06 ms with two), so smaller frames keep one.
         if (cost3) {
-            bands = h->bandsWanted > 0 ? h->bandsWanted : (sweepSMs == h->numSMs && (long long)g.W1 * g.H * g.Dp >= (1ll << 30) ? 2 : 1);
+            bands = h->bandsWanted > 0 ? h->bandsWanted : (sweepSMs == h->numSMs && (long long)g.W1 * g.H * g.Dp >= (1ll << 30) ? 6 : 1);
             if (p.mode == SGBM_MODE_HH4) bands = 1;                    // (its zeroed last rows are written after the cost kernel)
             bandRows = ((g.H + bands - 1) / bands + 15) / 16 * 16;
             bands = (g.H + bandRows - 1) / bandRows;

@@ -26,6 +26,11 @@ template <int NREG, int LPC> struct HzK {
 // One lane group per image row and direction.  The cost rows are streamed through a per-warp ring
 // of HZ_NS shared-memory stages filled by TMA bulk copies (one contiguous K-column segment per
 // row), so HBM latency is covered by data in flight instead of registers.
+// (Measured and rejected, end of round 2: the same kernel without shared memory -- the next three columns' cost vectors
+// prefetched into registers by plain 128-bit loads, 96 registers, so that one of its CTAs fits on an SM BESIDE a 211 KB cost
+// CTA.  Alone it is as fast as this one at 4K D=256 (2.57 ms) and slower on small frames (1080p 0.68 vs 0.46 ms); run beside
+// the cost kernel of the next row band it made cost + horizontal 4.9 / 7.8 / 5.2 ms with 2 / 4 / 8 bands against 4.2 ms, with
+// low stream priority 6.9 / 7.8 / 6.1 ms: sharing the SM costs the cost kernel far more than the overlap returns.)
 // At 4K / D = 256 the kernel is HBM-bound (92 % of the copy peak); with few rows or few disparities it is a pure
 // latency chain of W1 dependent path steps per warp, so the per-column code is kept minimal: the direction is a
 // template parameter, the staged column and the output pointer advance by constants, the next column's cost vector is
