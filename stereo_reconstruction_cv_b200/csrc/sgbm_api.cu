@@ -559,7 +559,10 @@ static int compute_frame(sgbm_handle *h, int lane, int sweepSMs, const Geo &g, c
         // 6.97 -> 6.76 ms; 2 / 3 / 4 / 5 / 8 bands: 10.23 / 9.95 / 9.92 / 9.92 / 10.04 ms; at 1080p bands only cost
         // (1.86 -> 2.06 ms with two), so smaller frames keep one.
         if (cost3) {
-            bands = h->bandsWanted > 0 ? h->bandsWanted : (sweepSMs == h->numSMs && (long long)g.W1 * g.H * g.Dp >= (1ll << 30) ? 6 : 1);
+            const long long elems = (long long)g.W1 * g.H * g.Dp;
+            // (2560x1440 D=256 MODE_HH: 5.58 / 5.33 / 5.31 / 5.35 / 5.46 ms with 1 / 2 / 3 / 4 / 6 bands; 4K D=128 and D=192 do not care)
+            const int autoBands = sweepSMs != h->numSMs ? 1 : (elems >= (1ll << 30) ? 6 : (g.nreg >= 16 && elems >= (3ll << 28) ? 3 : 1));
+            bands = h->bandsWanted > 0 ? h->bandsWanted : autoBands;
             if (p.mode == SGBM_MODE_HH4) bands = 1;                    // (its zeroed last rows are written after the cost kernel)
             bandRows = ((g.H + bands - 1) / bands + 15) / 16 * 16;
             bands = (g.H + bandRows - 1) / bandRows;
