@@ -24,6 +24,10 @@
 // would set the row period).  k_rowstep at the end of this file is the row-at-a-time fallback for geometries
 // no persistent kernel holds.
 //
+// A ring stage holds one or two image rows (template parameter RPS): with two, a role waits, advances and arrives once per
+// two rows ("wait, (path step, S update) x 2, arrive"), super-steps are multiples of the stage height and the last stage of
+// an odd-height image holds one row.  It pays only when the cost ring stays deep (>= 4 stages): see sweep_plan.
+//
 // The row loops are written for instruction count (round 2): every ring is addressed through a RingPos carried in
 // registers (32-bit shared addresses, ld/st.shared with immediate offsets, advanced by additions), the barriers of a
 // stage sit side by side, a diagonal role knows its column as one number in staged-window coordinates, and

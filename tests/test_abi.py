@@ -38,6 +38,21 @@ def test_no_cpu_fallback(built):
         sg.StereoSGBM_create(numDisparities=16)
 
 
+def test_result_pool_without_page_locked_memory(built):
+    """The recycling pool of page-locked result blocks (_hostpool.py) only decides WHERE a result array lives: when no
+    page-locked memory can be had (here: no CUDA device) it hands out ordinary arrays, and small results never use it."""
+    import numpy as np
+    import torch
+    from stereo_reconstruction_cv_b200 import _hostpool
+    small = _hostpool.empty((64, 64), np.int16)
+    assert small.flags.owndata and small.shape == (64, 64) and small.dtype == np.int16
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    big = _hostpool.empty((1200, 1000), np.int16)
+    assert big.flags.owndata and big.shape == (1200, 1000)
+    assert _hostpool.stats() == {"outstanding_bytes": 0, "cached_bytes": 0}
+
+
 def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "stereo_reconstruction_cv_b200")
     for dirpath, _, files in os.walk(pkg):
