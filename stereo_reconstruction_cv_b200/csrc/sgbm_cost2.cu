@@ -110,7 +110,6 @@ __global__ void __launch_bounds__(PF3_TX) k_prefilter3(const uint8_t *__restrict
                                                        uint32_t *__restrict__ rpairs, int RPW, int eshift)
 {
     __shared__ uint8_t sgt[2][PF3_TX + 4];                // g, t at x0-1 .. x0+TX+1
-    __shared__ uint8_t s6[6][PF3_TX + 2];                 // the six plane values at x0 .. x0+TX
     const int tid = threadIdx.x, x0 = blockIdx.x * PF3_TX, y = blockIdx.y, im = blockIdx.z;
     const uint8_t *img = im ? right : left;
     const uint8_t *r0 = img + (long long)y * pitch, *rm = img + (long long)max(y - 1, 0) * pitch,
@@ -126,24 +125,23 @@ __global__ void __launch_bounds__(PF3_TX) k_prefilter3(const uint8_t *__restrict
         sgt[0][i] = (uint8_t)gv; sgt[1][i] = (uint8_t)tv;
     }
     __syncthreads();
-    for (int i = tid; i < PF3_TX + 1; i += PF3_TX) {
+    // value, half-sample minimum and maximum (A.2) of plane q at tile position i (image column x0 + i), straight from the
+    // staged g / t values: the six plane values of a pixel never go through shared memory (the kernel is bound by
+    // instruction issue, not by memory: 200 instructions per pixel before this, most of them byte-sized shared accesses)
+    auto six = [&](int q, int i, uint32_t &v0o, uint32_t &loo, uint32_t &hio) {
         const int x = x0 + i;
-        if (x < W) {
-#pragma unroll
-            for (int q = 0; q < 2; q++) {
-                const int v0 = sgt[q][i + 1];
-                int lo = v0, hi = v0;
-                if (x > 0) { const int v1 = (v0 + sgt[q][i]) >> 1; lo = min(lo, v1); hi = max(hi, v1); }
-                if (x < W - 1) { const int v1 = (v0 + sgt[q][i + 2]) >> 1; lo = min(lo, v1); hi = max(hi, v1); }
-                s6[3 * q + 0][i] = (uint8_t)v0; s6[3 * q + 1][i] = (uint8_t)lo; s6[3 * q + 2][i] = (uint8_t)hi;
-            }
-        }
-    }
-    __syncthreads();
+        const int v0 = sgt[q][i + 1];
+        int lo = v0, hi = v0;
+        if (x > 0) { const int v1 = (v0 + sgt[q][i]) >> 1; lo = min(lo, v1); hi = max(hi, v1); }
+        if (x < W - 1) { const int v1 = (v0 + sgt[q][i + 2]) >> 1; lo = min(lo, v1); hi = max(hi, v1); }
+        v0o = (uint32_t)v0; loo = (uint32_t)lo; hio = (uint32_t)hi;
+    };
     if (im == 0) {
         const int x = x0 + tid;
         if (x < W) {
-            const uint32_t a0 = s6[0][tid], a1 = s6[1][tid], a2 = s6[2][tid], a3 = s6[3][tid], a4 = s6[4][tid], a5 = s6[5][tid];
+            uint32_t a0, a1, a2, a3, a4, a5;
+            six(0, tid, a0, a1, a2);
+            six(1, tid, a3, a4, a5);
             uint4 *o = leftX + ((size_t)y * W + x) * 2;
             o[0] = make_uint4((a0 + 256u) * 0x10001u, (256u - a0) * 0x10001u, (256u - a2) * 0x10001u, (a1 + 256u) * 0x10001u);
             o[1] = make_uint4((a3 + 256u) * 0x10001u, (256u - a3) * 0x10001u, (256u - a5) * 0x10001u, (a4 + 256u) * 0x10001u);
@@ -152,9 +150,14 @@ __global__ void __launch_bounds__(PF3_TX) k_prefilter3(const uint8_t *__restrict
         const int i = 2 * tid, x = x0 + i;                // even right position: lo = v(x+1), hi = v(x)
         if (x < W) {
             const int i1 = x + 1 < W ? i + 1 : i;
+            uint32_t e[6], o1[6];
+            six(0, i, e[0], e[1], e[2]);
+            six(1, i, e[3], e[4], e[5]);
+            six(0, i1, o1[0], o1[1], o1[2]);
+            six(1, i1, o1[3], o1[4], o1[5]);
 #pragma unroll
             for (int p = 0; p < 6; p++)
-                rpairs[((size_t)p * H + y) * 2 * RPW + (x >> 1) + eshift] = (uint32_t)s6[p][i1] | ((uint32_t)s6[p][i] << 16);
+                rpairs[((size_t)p * H + y) * 2 * RPW + (x >> 1) + eshift] = o1[p] | (e[p] << 16);
         }
     }
 }
