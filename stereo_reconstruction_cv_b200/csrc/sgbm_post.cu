@@ -222,49 +222,101 @@ __global__ void __launch_bounds__(CC_THREADS) k_cc_runs(const int16_t *img, int 
     }
 }
 
+// The three kernels below handle CC_PX consecutive pixels of a row per thread: their work per pixel is a few dependent
+// global loads (labels, roots, sizes), so with one pixel per thread they were bound by load latency at ~25 % issue
+// utilisation; four independent chains per thread hide it (4K: merge 0.082 / count 0.067 / apply 0.041 ms before).
+#define CC_PX 4
+
 // vertical merges: one union per contact between a run of row y and a run of row y+1
 __global__ void k_cc_merge(const int16_t *img, int *label, int W, int H, int newVal, int maxDiff)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * CC_PX;
     const int y = blockIdx.y;
-    if (x >= W || y + 1 >= H) return;
-    const int i = y * W + x;
-    const int a = img[i], b = img[i + W];
-    if (!cc_link(a, b, newVal, maxDiff)) return;
-    if (x > 0) {                                          // the same two runs already touched at x-1?
-        const int a0 = img[i - 1], b0 = img[i + W - 1];
-        if (cc_link(a0, a, newVal, maxDiff) && cc_link(b0, b, newVal, maxDiff) && cc_link(a0, b0, newVal, maxDiff)) return;
+    if (x0 >= W || y + 1 >= H) return;
+    const int16_t *ra = img + (size_t)y * W, *rb = ra + W;
+    int a[CC_PX + 1], b[CC_PX + 1];                       // columns x0 - 1 .. x0 + CC_PX - 1
+#pragma unroll
+    for (int k = 0; k <= CC_PX; k++) {
+        const int x = x0 - 1 + k;
+        const bool in = x >= 0 && x < W;
+        a[k] = in ? ra[x] : newVal;
+        b[k] = in ? rb[x] : newVal;
     }
-    uf_union(label, label[i], label[i + W]);
+    bool todo[CC_PX];
+    int la[CC_PX], lb[CC_PX];
+#pragma unroll
+    for (int k = 0; k < CC_PX; k++) {
+        const int x = x0 + k;
+        bool t = x < W && cc_link(a[k + 1], b[k + 1], newVal, maxDiff);
+        // the same two runs already touched at x-1?
+        if (t && x > 0 && cc_link(a[k], a[k + 1], newVal, maxDiff) && cc_link(b[k], b[k + 1], newVal, maxDiff) &&
+            cc_link(a[k], b[k], newVal, maxDiff)) t = false;
+        todo[k] = t;
+        la[k] = lb[k] = 0;
+        if (t) { la[k] = label[y * W + x]; lb[k] = label[(y + 1) * W + x]; }
+    }
+#pragma unroll
+    for (int k = 0; k < CC_PX; k++)
+        if (todo[k]) uf_union(label, la[k], lb[k]);
 }
 
 // run ends add their run length to the root's size and flatten the run start's label
 __global__ void k_cc_count(const int16_t *img, int *label, int *size, int W, int H, int newVal, int maxDiff)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * CC_PX;
     const int y = blockIdx.y;
-    if (x >= W) return;
-    const int i = y * W + x;
-    const int v = img[i];
-    if (v == newVal) return;
-    const bool runEnd = (x + 1 >= W) || !cc_link(v, img[i + 1], newVal, maxDiff);
-    if (!runEnd) return;
-    const bool runStart = (x == 0) || !cc_link(img[i - 1], v, newVal, maxDiff);
-    const int s = runStart ? i : label[i];               // non-start pixels keep pointing at their run start
-    const int r = uf_find(label, s);
-    atomicAdd(&size[r], i - s + 1);
-    if (r != s) atomicMin(&label[s], r);                  // flatten: k_cc_apply reaches the root in two loads
+    if (x0 >= W) return;
+    const int16_t *row = img + (size_t)y * W;
+    int v[CC_PX + 2];                                     // columns x0 - 1 .. x0 + CC_PX
+#pragma unroll
+    for (int k = 0; k < CC_PX + 2; k++) {
+        const int x = x0 - 1 + k;
+        v[k] = (x >= 0 && x < W) ? row[x] : newVal;
+    }
+    int s[CC_PX];
+    bool end[CC_PX];
+#pragma unroll
+    for (int k = 0; k < CC_PX; k++) {
+        const int x = x0 + k, i = y * W + x;
+        const int c = v[k + 1];
+        end[k] = x < W && c != newVal && !cc_link(c, v[k + 2], newVal, maxDiff);          // (v past the row is newVal: no link)
+        s[k] = 0;
+        if (end[k]) {
+            const bool runStart = !cc_link(v[k], c, newVal, maxDiff);                      // (v before the row is newVal)
+            s[k] = runStart ? i : label[i];               // non-start pixels keep pointing at their run start
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < CC_PX; k++) {
+        if (!end[k]) continue;
+        const int i = y * W + x0 + k;
+        const int r = uf_find(label, s[k]);
+        atomicAdd(&size[r], i - s[k] + 1);
+        if (r != s[k]) atomicMin(&label[s[k]], r);        // flatten: k_cc_apply reaches the root in two loads
+    }
 }
 
 __global__ void k_cc_apply(int16_t *img, const int *label, const int *size, int n, int newVal, int maxSize)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int s = label[i];
-    if (s < 0) return;
-    int r = s, p = label[r];
-    while (p != r) { r = p; p = label[r]; }               // labels are final here
-    if (size[r] <= maxSize) img[i] = (int16_t)newVal;
+    const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * CC_PX;
+    if (i0 >= n) return;
+    int s[CC_PX], p[CC_PX];
+#pragma unroll
+    for (int k = 0; k < CC_PX; k++) s[k] = i0 + k < n ? label[i0 + k] : -1;
+#pragma unroll
+    for (int k = 0; k < CC_PX; k++) p[k] = s[k] >= 0 ? label[s[k]] : -1;          // first hop of all four chains at once
+#pragma unroll
+    for (int k = 0; k < CC_PX; k++) {
+        if (s[k] < 0) continue;
+        int r = s[k], q = p[k];
+        while (q != r) { r = q; q = label[r]; }           // labels are final here
+        s[k] = r;
+    }
+#pragma unroll
+    for (int k = 0; k < CC_PX; k++) p[k] = s[k] >= 0 ? size[s[k]] : 0x7FFFFFFF;
+#pragma unroll
+    for (int k = 0; k < CC_PX; k++)
+        if (p[k] <= maxSize) img[i0 + k] = (int16_t)newVal;
 }
 
 // ---- float conversion + reprojection --------------------------------------------------------------
@@ -535,10 +587,10 @@ int sgbm_launch_speckles(int16_t *img, int W, int H, int newVal, int maxSize, in
     int n = W * H;
     int *label = (int *)scratch, *size = label + n;
     k_cc_runs<<<H, CC_THREADS, 0, st>>>(img, label, size, W, newVal, maxDiff);
-    dim3 grid((W + 255) / 256, H);
+    dim3 grid((W + 256 * CC_PX - 1) / (256 * CC_PX), H);
     k_cc_merge<<<grid, 256, 0, st>>>(img, label, W, H, newVal, maxDiff);
     k_cc_count<<<grid, 256, 0, st>>>(img, label, size, W, H, newVal, maxDiff);
-    k_cc_apply<<<(n + 255) / 256, 256, 0, st>>>(img, label, size, n, newVal, maxSize);
+    k_cc_apply<<<(n + 256 * CC_PX - 1) / (256 * CC_PX), 256, 0, st>>>(img, label, size, n, newVal, maxSize);
     sgbm_count_launch(4);
     SGBM_CUDA_CHECK(cudaGetLastError());
     return 0;
