@@ -25,7 +25,6 @@ int sgbm_launch_cost3(const Geo &g, const uint8_t *planes, uint16_t *out, int y0
 int sgbm_launch_horizontal(const Geo &g, const uint16_t *C, uint16_t *LhA, uint16_t *LhB, int y0, int nrows, cudaStream_t st);
 int sgbm_launch_vertical(VertArgs &a, int ndir, int numSMs, cudaStream_t st);
 bool sgbm_sweep_fits(const Geo &g, int numSMs, int mode);
-int sgbm_launch_fill_i16(int16_t *p, size_t n, int v, cudaStream_t st);
 int sgbm_launch_lrcheck(const Geo &g, int16_t *raw, const unsigned int *d2key, cudaStream_t st);
 int sgbm_launch_pad_cost(const Geo &g, uint16_t *C, int nrows, int value, cudaStream_t st);
 int sgbm_launch_init_wta(int16_t *raw, unsigned int *d2key, size_t n, int INV, cudaStream_t st);

@@ -1,17 +1,14 @@
 // sgbm_post.cu -- per-pixel tail of the path for sm_100a (all HBM-bound, one thread per pixel):
-//   k_lrcheck      : disp12MaxDiff left-right consistency check (A.5)
-//   k_median3x3    : the always-on 3x3 median of cv2.StereoSGBM.compute (A.7)
+//   k_init_wta     : raw disparity = INV, disp2 keys = never hit, before a frame's winner-take-all
+//   k_pad_cost     : constant cost of the padding disparities when numDisparities % 8 != 0
+//   k_lr_median    : disp12MaxDiff left-right consistency check (A.5) + the always-on 3x3 median (A.7) in one tiled pass
+//   k_lrcheck      : the LR check alone (debug hook: sgbm_debug_fetch of the raw disparity)
+//   k_median3x3    : the 3x3 median alone (public medianBlur3)
 //   k_cc_*         : cv2.filterSpeckles as connected components (lock-free union-find) (A.7)
 //   k_disp_to_float: .astype(float32)/16 and positivity mask               (main.ipynb:668-670)
 //   k_reproject    : cv2.reprojectImageTo3D in fp64, bit exact             (main.ipynb:697, A.8)
 //   k_compact_*    : finite/positive mask + ordered gather to XYZ/RGB      (main.ipynb:726-737)
 #include "sgbm_common.cuh"
-
-__global__ void k_fill_i16(int16_t *p, size_t n, int16_t v)
-{
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
 
 // Start of a frame's winner-take-all: raw disparity = INV everywhere, disp2 keys = "never hit".  One kernel, 128-bit stores.
 __global__ void k_init_wta(int16_t *raw, unsigned int *d2key, size_t n, int INV)
@@ -525,14 +522,6 @@ __global__ void k_compact_scatter(const int16_t *disp, QMat Q, int W, int H, con
 // =================================================================================================
 // host launchers
 // =================================================================================================
-int sgbm_launch_fill_i16(int16_t *p, size_t n, int v, cudaStream_t st)
-{
-    k_fill_i16<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, (int16_t)v);
-    sgbm_count_launch(1);
-    SGBM_CUDA_CHECK(cudaGetLastError());
-    return 0;
-}
-
 int sgbm_launch_pad_cost(const Geo &g, uint16_t *C, int nrows, int value, cudaStream_t st)
 {
     const int Dc = (g.D + 7) & ~7;
