@@ -67,6 +67,8 @@ __global__ void k_lrcheck(int16_t *raw, const unsigned int *d2key, int W, int H,
 
 // ---- 3x3 median, replicate border -----------------------------------------------------------------
 __device__ __forceinline__ void cswap(int &a, int &b) { int t = min(a, b); b = max(a, b); a = t; }
+// the same on two signed 16-bit values per register
+__device__ __forceinline__ void pcswap(uint32_t &a, uint32_t &b) { const uint32_t t = __vmins2(a, b); b = __vmaxs2(a, b); a = t; }
 
 __global__ void k_median3x3(const int16_t *src, int16_t *dst, int W, int H, long long dstPitchElems)
 {
@@ -109,7 +111,7 @@ __device__ __forceinline__ int lr_checked(const int16_t *raw, const unsigned int
 __global__ void __launch_bounds__(LM_THREADS) k_lr_median(const int16_t *raw, const unsigned int *d2key, int16_t *dst, int W, int H,
                                                            long long dstPitchElems, int minX1, int maxX1, int minD, int INV, int DMD)
 {
-    __shared__ int16_t tile[LM_TH + 2][LM_TW + 2 + 2];
+    __shared__ __align__(16) int16_t tile[LM_TH + 2][LM_TW + 2 + 2];
     const int x0 = blockIdx.x * LM_TW, y0 = blockIdx.y * LM_TH;
     for (int idx = threadIdx.x; idx < (LM_TH + 2) * (LM_TW + 2); idx += LM_THREADS) {
         const int ty = idx / (LM_TW + 2), tx = idx - ty * (LM_TW + 2);
@@ -117,26 +119,29 @@ __global__ void __launch_bounds__(LM_THREADS) k_lr_median(const int16_t *raw, co
         tile[ty][tx] = (int16_t)lr_checked(raw, d2key, W, gx, gy, minX1, maxX1, minD, INV, DMD);
     }
     __syncthreads();
-    // thread -> two adjacent columns x four rows
+    // thread -> two adjacent columns x four rows.  The two columns' 3x3 windows are sorted together as packed signed 16-bit
+    // pairs (low half: column cx, high half: column cx + 1): one 19-exchange network of packed min / max per two pixels.
     const int cx = (threadIdx.x & 63) * 2, ry = (threadIdx.x >> 6) * 4;
+    uint32_t P[6][3];                                     // tile rows ry .. ry + 5, window columns 0 .. 2
+#pragma unroll
+    for (int t = 0; t < 6; t++) {
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(&tile[ry + t][cx]);      // cx is even, rows are 4-byte aligned
+        const uint32_t w0 = w[0], w1 = w[1];
+        P[t][0] = w0; P[t][1] = __byte_perm(w0, w1, 0x5432); P[t][2] = w1;
+    }
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         const int y = y0 + ry + r;
         if (y >= H) break;
-#pragma unroll
-        for (int c = 0; c < 2; c++) {
-            const int x = x0 + cx + c;
-            if (x >= W) break;
-            const int16_t *t0 = &tile[ry + r][cx + c];
-            int p0 = t0[0], p1 = t0[1], p2 = t0[2];
-            int p3 = t0[LM_TW + 4], p4 = t0[LM_TW + 5], p5 = t0[LM_TW + 6];
-            int p6 = t0[2 * (LM_TW + 4)], p7 = t0[2 * (LM_TW + 4) + 1], p8 = t0[2 * (LM_TW + 4) + 2];
-            cswap(p1, p2); cswap(p4, p5); cswap(p7, p8); cswap(p0, p1); cswap(p3, p4); cswap(p6, p7);
-            cswap(p1, p2); cswap(p4, p5); cswap(p7, p8); cswap(p0, p3); cswap(p5, p8); cswap(p4, p7);
-            cswap(p3, p6); cswap(p1, p4); cswap(p2, p5); cswap(p4, p7); cswap(p4, p2); cswap(p6, p4);
-            cswap(p4, p2);
-            dst[(size_t)y * dstPitchElems + x] = (int16_t)p4;
-        }
+        uint32_t p0 = P[r][0], p1 = P[r][1], p2 = P[r][2], p3 = P[r + 1][0], p4 = P[r + 1][1], p5 = P[r + 1][2], p6 = P[r + 2][0],
+                 p7 = P[r + 2][1], p8 = P[r + 2][2];
+        pcswap(p1, p2); pcswap(p4, p5); pcswap(p7, p8); pcswap(p0, p1); pcswap(p3, p4); pcswap(p6, p7);
+        pcswap(p1, p2); pcswap(p4, p5); pcswap(p7, p8); pcswap(p0, p3); pcswap(p5, p8); pcswap(p4, p7);
+        pcswap(p3, p6); pcswap(p1, p4); pcswap(p2, p5); pcswap(p4, p7); pcswap(p4, p2); pcswap(p6, p4);
+        pcswap(p4, p2);
+        const int x = x0 + cx;
+        if (x < W) dst[(size_t)y * dstPitchElems + x] = (int16_t)(p4 & 0xFFFFu);
+        if (x + 1 < W) dst[(size_t)y * dstPitchElems + x + 1] = (int16_t)(p4 >> 16);
     }
 }
 
