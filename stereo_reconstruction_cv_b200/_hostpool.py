@@ -5,7 +5,8 @@ pageable array costs a staging copy plus one page fault per 4 KB on first touch 
 the call, more than the kernels of the notebook's own parameters take.  Results therefore come from a recycling pool
 of page-locked blocks (C ABI: sgbm_host_alloc / sgbm_host_free): the device -> host copy lands in the array directly,
 and a block goes back to the pool when the last array (or view) that uses it is garbage collected.  The arrays behave
-like any other ndarray (writeable, C-contiguous; `owndata` is False).  The pool is bounded: beyond MAX_OUTSTANDING
+like any other ndarray (writeable, C-contiguous; `owndata` is False).  Page-locking costs about a millisecond per megabyte,
+so only results between MIN_BYTES and MAX_BYTES use the pool, and the pool is bounded: beyond MAX_OUTSTANDING
 bytes held by live results -- a caller that keeps every frame -- new results are ordinary pageable arrays again."""
 import atexit
 import ctypes as C
@@ -16,6 +17,7 @@ import numpy as np
 from . import _lib
 
 MIN_BYTES = 1 << 20            # small results are not worth a page-locked block
+MAX_BYTES = 256 << 20          # ... and page-locking a huge one (a whole batch's result) costs more than the staged copy it saves
 MAX_OUTSTANDING = 2 << 30      # page-locked bytes in live result arrays
 MAX_CACHED = 512 << 20         # page-locked bytes kept for reuse
 _GRAIN = 1 << 20
@@ -78,7 +80,7 @@ def empty(shape, dtype):
     """np.empty(shape, dtype) in page-locked memory when the pool allows it, an ordinary array otherwise."""
     dtype = np.dtype(dtype)
     nbytes = int(np.prod(shape)) * dtype.itemsize
-    if nbytes >= MIN_BYTES:
+    if MIN_BYTES <= nbytes <= MAX_BYTES:
         blk = _take(nbytes)
         if blk is not None:
             return np.asarray(_Block(blk[0], blk[1], shape, dtype))
