@@ -183,6 +183,12 @@ int sgbm_host_free(void *p);
  */
 int sgbm_debug_keep(sgbm_handle *h, int on);
 int sgbm_debug_fetch(sgbm_handle *h, int which, void *host_dst, size_t bytes);
+/* Host logic only, no device needed: the strip / ring schedule the sweep planner picks for frames of this size on a GPU
+ * with `num_sms` SMs and `max_smem_bytes` of shared memory per CTA.  out16 = { found, strips, columns per strip, rows per
+ * super-step, chain batches, rows per ring stage, S slots, cost stages, input stages, warps of role V, of each diagonal
+ * role, of role W, W row groups, W warps per row, threads, shared-memory bytes }.  tests/test_host_logic.py. */
+int sgbm_debug_sweep_plan(const sgbm_params *p, int W, int H, int channels, int num_sms, int max_smem_bytes, int w_role,
+                          int input_volumes, int *out16);
 
 
 /*

@@ -17,7 +17,7 @@ SYMBOLS = [
     "sgbm_reproject_compact_scratch_bytes", "sgbm_filter_speckles", "sgbm_median3x3",
     "sgbm_debug_keep", "sgbm_debug_fetch", "sgbm_microbench_int16", "sgbm_kernel_launches",
     "sgbm_profile_enable", "sgbm_profile_read", "sgbm_init_rectify_map", "sgbm_remap_linear_u8",
-    "sgbm_status", "sgbm_reproject_ex", "sgbm_host_alloc", "sgbm_host_free",
+    "sgbm_status", "sgbm_reproject_ex", "sgbm_host_alloc", "sgbm_host_free", "sgbm_debug_sweep_plan",
 ]
 
 
@@ -65,6 +65,7 @@ def load(path):
     L.sgbm_reproject_ex.argtypes = [vp, i, vp, i, i, i, i, vp, vp, vp]
     L.sgbm_host_alloc.argtypes = [sz, C.POINTER(C.c_void_p)]
     L.sgbm_host_free.argtypes = [vp]
+    L.sgbm_debug_sweep_plan.argtypes = [vp, i, i, i, i, i, i, i, vp]
     L.sgbm_kernel_launches.argtypes = []
     L.sgbm_kernel_launches.restype = C.c_ulonglong
     L.sgbm_debug_keep.argtypes = [vp, i]

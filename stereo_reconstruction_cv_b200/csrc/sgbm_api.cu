@@ -25,6 +25,7 @@ int sgbm_launch_cost3(const Geo &g, const uint8_t *planes, uint16_t *out, int y0
 int sgbm_launch_horizontal(const Geo &g, const uint16_t *C, uint16_t *LhA, uint16_t *LhB, int y0, int nrows, cudaStream_t st);
 int sgbm_launch_vertical(VertArgs &a, int ndir, int numSMs, cudaStream_t st);
 bool sgbm_sweep_fits(const Geo &g, int numSMs, int mode);
+bool sgbm_sweep_plan_debug(const Geo &g, int numSMs, int maxSmem, int wrole, int nAB, int *out);
 int sgbm_launch_lrcheck(const Geo &g, int16_t *raw, const unsigned int *d2key, cudaStream_t st);
 int sgbm_launch_pad_cost(const Geo &g, uint16_t *C, int nrows, int value, cudaStream_t st);
 int sgbm_launch_init_wta(int16_t *raw, unsigned int *d2key, size_t n, int INV, cudaStream_t st);
@@ -977,6 +978,18 @@ extern "C" int sgbm_host_free(void *p)
 {
     if (!p) return 0;
     SGBM_CUDA_CHECK(cudaFreeHost(p));
+    return 0;
+}
+
+extern "C" int sgbm_debug_sweep_plan(const sgbm_params *p, int W, int H, int channels, int num_sms, int max_smem_bytes, int w_role,
+                                     int input_volumes, int *out16)
+{
+    if (!p || !out16 || num_sms < 1 || max_smem_bytes < 1 || input_volumes < 1 || input_volumes > 2)
+        return sgbm_fail(SGBM_E_INVALID_ARG, "bad argument");
+    Geo g;
+    const int rc = make_geo(*p, W, H, channels, g);       // (default knobs: no handle, no device)
+    if (rc) return rc;
+    sgbm_sweep_plan_debug(g, num_sms, max_smem_bytes, w_role, input_volumes, out16);
     return 0;
 }
 

@@ -989,6 +989,22 @@ static bool sweep_plan(const Geo &g, int numSMs, bool wrole, bool wta, int maxTh
     return false;
 }
 
+// Test hook (sgbm_debug_sweep_plan): the schedule the planner picks for a geometry, without a device.
+// out[16] = { found, nstrips, SW, R, NB, rps, K, NSC, NSI, nwV, nwA, nwW, wRG, wPR, threads, smem bytes }
+bool sgbm_sweep_plan_debug(const Geo &g, int numSMs, int maxSmem, int wrole, int nAB, int *out)
+{
+    SweepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = g; a.nAB = nAB;
+    int threads = 0;
+    size_t smem = 0;
+    const int maxThreads = wrole ? 1024 : (g.nreg >= 12 ? 768 : 1024);
+    const bool found = sweep_plan(g, numSMs, wrole != 0, true, maxThreads, maxSmem, a, &threads, &smem);
+    const int v[16] = {found ? 1 : 0, a.nstrips, a.SW, a.R, a.NB, a.rps, a.K, a.NSC, a.NSI, a.nwV, a.nwA, a.nwW, a.wRG, a.wPR, threads, (int)smem};
+    for (int i = 0; i < 16; i++) out[i] = v[i];
+    return found;
+}
+
 // Whether the persistent sweeps of mode SGBM (0) / HH (1) hold this geometry on `numSMs` SMs: what the
 // batch entry points ask before they run two frames side by side, each on half of the GPU.
 bool sgbm_sweep_fits(const Geo &g, int numSMs, int mode)
