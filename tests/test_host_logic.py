@@ -79,3 +79,24 @@ def test_sweep_plan_known_geometries(lib):
     # little shared memory: one row per stage, shallower rings, or nothing
     small = plan(lib, 1280, 720, 128, 0, 148, 1, 2, smem=48 * 1024)
     assert small["found"] == 0 or small["smem"] <= 48 * 1024
+
+
+def test_parameter_validation_without_a_device(lib):
+    """make_geo (the same function sgbm_compute runs first) through the planner hook: what is rejected, and with which code."""
+    def rc(W=640, H=48, cn=1, **kw):
+        base = dict(minDisparity=0, numDisparities=64, blockSize=5, P1=200, P2=800, disp12MaxDiff=1, preFilterCap=63,
+                    uniquenessRatio=10, speckleWindowSize=0, speckleRange=0, mode=0)
+        base.update(kw)
+        p = lib.SgbmParams(*[base[n] for n in ("minDisparity", "numDisparities", "blockSize", "P1", "P2", "disp12MaxDiff",
+                                               "preFilterCap", "uniquenessRatio", "speckleWindowSize", "speckleRange", "mode")])
+        out = (C.c_int * 16)()
+        return lib.lib().sgbm_debug_sweep_plan(C.byref(p), W, H, cn, 148, MAX_SMEM, 1, 2, out)
+    assert rc() == 0
+    for D in (4, 5, 20, 21, 250, 255, 1024):                      # any numDisparities >= 4 outside MODE_SGBM_3WAY
+        assert rc(W=1400, numDisparities=D) == 0, D
+    assert rc(numDisparities=20, mode=2) != 0 and rc(numDisparities=24, mode=2) == 0
+    for bad in (dict(numDisparities=0), dict(numDisparities=-16), dict(numDisparities=3), dict(numDisparities=1032, W=2000),
+                dict(W=60), dict(W=0), dict(H=0), dict(cn=2), dict(mode=7), dict(P2=40000), dict(uniquenessRatio=101),
+                dict(uniquenessRatio=100, mode=2), dict(minDisparity=3000), dict(numDisparities=20, blockSize=11, P1=2904, P2=22000)):
+        assert rc(**bad) != 0, bad
+    assert b"numDisparities" in lib.lib().sgbm_last_error()
