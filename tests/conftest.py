@@ -24,3 +24,20 @@ def golden():
 @pytest.fixture(scope="session")
 def golden_meta():
     return json.load(open(os.path.join(GOLDEN_DIR, "golden_digests.json")))
+
+
+@pytest.fixture(scope="session")
+def numdisp_cases():
+    """(name, params, left, right, cv2 disparity) for numDisparities that are not a multiple of 8: committed cv2 outputs
+    (tests/golden/make_golden_numdisp.py), inputs regenerated from the recorded recipe."""
+    from oracle import OracleParams
+    from synth import make_noise_pair, make_pair
+    meta = json.load(open(os.path.join(GOLDEN_DIR, "golden_numdisp.json")))
+    arrs = np.load(os.path.join(GOLDEN_DIR, "golden_numdisp.npz"))
+    out = []
+    for name, c in sorted(meta["cases"].items()):
+        c = dict(c)
+        W, H, kind, seed = c.pop("W"), c.pop("H"), c.pop("kind"), c.pop("seed")
+        l, r = make_pair(W, H, max(c["numDisparities"], 8), seed=seed)[:2] if kind == "synth" else make_noise_pair(W, H, seed=seed)
+        out.append((name, OracleParams(**c), l, r, arrs[name + "__disp"]))
+    return out

@@ -438,6 +438,15 @@ def test_num_disparities_not_a_multiple_of_8_fallback_kernels(sg, monkeypatch, e
             assert _mismatch(sg.StereoSGBM_create(**_kw(p)).compute(l, r), oracle.compute(p, l, r)) == 0, (env, D, mode)
 
 
+def test_num_disparities_golden_vectors(sg, numdisp_cases):
+    """The committed cv2 vectors for numDisparities 4 ... 100 (tests/golden/make_golden_numdisp.py)."""
+    n = 0
+    for name, p, l, r, ref in numdisp_cases:
+        assert _mismatch(sg.StereoSGBM_create(**_kw(p)).compute(l, r), ref) == 0, name
+        n += 1
+    assert n == 36
+
+
 def test_num_disparities_unsupported_values(sg):
     l, r, _ = make_pair(300, 40, 16, seed=1)
     for kw in (dict(numDisparities=3), dict(numDisparities=2), dict(numDisparities=20, mode=2), dict(numDisparities=21, mode=2), dict(numDisparities=1032),

@@ -52,6 +52,16 @@ def test_golden_digest_mid(golden_meta):
         assert hashlib.sha256(got.tobytes()).hexdigest() == g["disp_sha256"], name
 
 
+def test_golden_num_disparities_not_a_multiple_of_8(numdisp_cases):
+    """cv2 accepts any positive numDisparities ([P16]); the oracle equals the committed cv2 vectors for
+    4 ... 100, odd values included (tests/golden/make_golden_numdisp.py)."""
+    n = 0
+    for name, p, l, r, ref in numdisp_cases:
+        assert int((oracle.compute(p, l, r) != ref).sum()) == 0, name
+        n += 1
+    assert n == 36
+
+
 def test_invalid_sizes_raise():
     l, r = make_noise_pair(40, 20, seed=0)
     with pytest.raises(ValueError):
